@@ -1,0 +1,90 @@
+/* oracle/oracle.h -- CPU restatement of the reference's hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * liboracle.so (or oracle/_ref/), and only as the checker or the CPU baseline.  The product
+ * library (se-195-project-ray-tracer_b200/librt_b200.so) has no CPU fallback and never links this.
+ *
+ * Parity status:
+ *   Whitted  : PINNED   -- oracle == oracle/_ref (the reference's own raytracer_non_OpenCL.c compiled
+ *                          unmodified) == the reference's golden image test.bmp (800x600), byte for byte.
+ *   smallpt  : the reference ships no golden image or known-answer vector for the path tracer
+ *              ("parity unpinned" by reference artefacts); it is pinned here against oracle/_ref,
+ *              i.e. outputs of the reference's own smallptCPU.cpp / geomfunc.h run in this container
+ *              (colors, pixels and RNG state bit-exact), and against the known-answer vectors that
+ *              SURVEY.md 9.2 recorded from those compiled reference functions.
+ *
+ * Numerics: the reference builds both CPU twins as C++ (/TP), so sqrt/sin/cos/pow/exp/fabs on
+ * float arguments are the single-precision overloads; this restatement calls sqrtf/sinf/cosf/
+ * powf/expf/fabsf explicitly and must be compiled without FMA contraction (see Makefile).
+ */
+#ifndef ORACLE_H
+#define ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Whitted tracer (Raytracer3.2.03/raytracer/OpenCL Raytracer/raytracer_non_OpenCL.c) ---- */
+
+typedef struct { float x, y, z, w; } ow_f4;
+
+/* Same 96-byte layout as the reference's Primitive_2 (common.h:49-63). */
+typedef struct {
+    ow_f4 color;
+    float refl, diff, refr, refr_index, spec, dummy_3;
+    int32_t type;            /* 0 = plane, 1 = sphere */
+    uint8_t is_light, pad_[3];
+    ow_f4 normal, center;
+    float depth, radius, sq_radius, r_radius;
+} ow_prim;
+
+typedef struct {
+    uint64_t traced_rays;    /* nearest-hit queries (raytrace() calls) */
+    uint64_t shadow_rays;    /* any-hit queries started towards sphere lights */
+    uint64_t sphere_tests;   /* sphere_intersect evaluations, shadow loops included */
+    uint64_t plane_tests;    /* plane_intersect evaluations */
+    uint32_t queue_high_water;
+} ow_counters;
+
+/* Renders rows [y0,y1) of a w x h frame.  pixels: uchar4[w*h] (full-frame indexing);
+ * hit_ids: int[w*h*9] or NULL, primary-ray hit primitive per sub-sample ((tx+1)*3+(ty+1));
+ * ctr: accumulated into, may be NULL. */
+void oracle_whitted_rows(uint8_t *pixels, int32_t *hit_ids, int w, int h, int y0, int y1,
+                         const ow_prim *prims, int n, ow_counters *ctr);
+/* Row-parallel over `threads` host threads (results identical to 1 thread). */
+void oracle_whitted_render(uint8_t *pixels, int32_t *hit_ids, int w, int h,
+                           const ow_prim *prims, int n, int threads, ow_counters *ctr);
+
+/* ---- smallpt path tracer (smallptgpu-v1.6: smallptCPU.cpp, geomfunc.h, simplernd.h) ---- */
+
+typedef struct { float x, y, z; } op_vec;
+typedef struct { float rad; op_vec p, e, c; int32_t refl; } op_sphere;   /* 44 bytes, geom.h:43-47 */
+typedef struct { op_vec orig, target, dir, x, y; } op_camera;            /* 60 bytes, camera.h:29-34 */
+
+typedef struct {
+    uint64_t samples;
+    uint64_t nearest_queries;   /* Intersect() calls  */
+    uint64_t shadow_queries;    /* IntersectP() calls */
+    uint64_t sphere_tests;      /* SphereIntersect() evaluations */
+} op_counters;
+
+float oracle_pt_get_random(uint32_t *s0, uint32_t *s1);
+float oracle_pt_sphere_intersect(const op_sphere *s, const float *o3, const float *d3);
+void oracle_pt_update_camera(op_camera *cam, int w, int h);
+
+/* integrator: 0 = path tracing, 1 = direct lighting.  colors: float[3*w*h], seeds: u32[2*w*h],
+ * both indexed by the CPU twin's flipped index i=(h-1-y)*w+x and updated in place; passes
+ * pass0 .. pass0+n_passes-1 are applied to every pixel of rows [y0,y1).  pixels may be NULL. */
+void oracle_pt_rows(int integrator, const op_sphere *sph, uint32_t n, const op_camera *cam,
+                    int w, int h, int y0, int y1, int pass0, int n_passes,
+                    float *colors, uint32_t *seeds, uint32_t *pixels, op_counters *ctr);
+void oracle_pt_render(int integrator, const op_sphere *sph, uint32_t n, const op_camera *cam,
+                      int w, int h, int pass0, int n_passes,
+                      float *colors, uint32_t *seeds, uint32_t *pixels, int threads, op_counters *ctr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
