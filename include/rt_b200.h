@@ -1,0 +1,209 @@
+/* include/rt_b200.h -- C ABI of the B200-native renderer (librt_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of markrosoft/se-195-project-ray-tracer: the per-pixel
+ * kernels that its single-threaded host programs launch through OpenCL.  The reference has no
+ * plugin registry or FFI; "the interface" is each kernel's argument list plus the buffer
+ * lifecycle around clEnqueueNDRangeKernel.  Every entry point below names the reference call
+ * site it replaces.  Abbreviations (paths relative to the reference root):
+ *     SPT/  = smallptgpu-v1.6/
+ *     R323/ = Raytracer3.2.03/raytracer/OpenCL Raytracer/
+ *
+ * Conventions:
+ *   - plain C, plain pointers and sizes; no CUDA, torch or C++ types in any signature;
+ *   - every host array is caller-allocated and caller-freed; device memory belongs to the context;
+ *   - every call returns RT_OK (0) or a negative rt_status; nothing calls exit() (the reference
+ *     prints and exit(-1)s: SPT/smallptGPU.cpp:119-122; or returns 1 up to main: R323/raytracer.c:708-713);
+ *     rt_last_error() gives the message;
+ *   - calls are synchronous unless named *_launch; a context is not thread-safe;
+ *   - there is no CPU fallback: without a CUDA device rt_init() fails with RT_ERR_NO_DEVICE.
+ *
+ * The POD structs are layout-identical to the reference's own (static_asserts in the library),
+ * under rt_-prefixed names so that a reference translation unit can include this header next to
+ * its own vec.h / geom.h / camera.h / common.h and simply cast.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ data model */
+
+typedef struct { float x, y, z; } rt_vec;                      /* SPT/vec.h:27-29   Vec    (12 B) */
+typedef struct { rt_vec o, d; } rt_ray;                        /* SPT/geom.h:32-34  Ray    (24 B) */
+enum { RT_DIFF = 0, RT_SPEC = 1, RT_REFR = 2 };                /* SPT/geom.h:39-41  enum Refl     */
+typedef struct {                                               /* SPT/geom.h:43-47  Sphere (44 B) */
+    float rad;
+    rt_vec p, e, c;
+    int32_t refl;
+} rt_sphere;
+typedef struct { rt_vec orig, target, dir, x, y; } rt_camera;  /* SPT/camera.h:29-34 Camera (60 B) */
+
+typedef struct { float x, y, z, w; } rt_float4;                /* R323/common.h:11-13 float_4 */
+typedef struct { unsigned char x, y, z, w; } rt_uchar4;        /* R323/common.h:15-17 uchar_4 */
+enum { RT_PLANE = 0, RT_SPHERE = 1 };                          /* R323/common.h:24-27 prim_type */
+typedef struct {                                               /* R323/common.h:49-63 Primitive_2 (96 B) */
+    rt_float4 m_color;
+    float m_refl, m_diff, m_refr, m_refr_index, m_spec, dummy_3;
+    int32_t type;
+    uint8_t is_light, pad_[3];
+    rt_float4 normal, center;
+    float depth, radius, sq_radius, r_radius;
+} rt_primitive;
+
+typedef enum {
+    RT_OK = 0,
+    RT_ERR_NO_DEVICE = -1,   /* no usable CUDA device / driver: the product never falls back to the CPU */
+    RT_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed; see rt_last_error() */
+    RT_ERR_ARG = -3,         /* bad argument (null pointer, non-positive size, unknown integrator ...) */
+    RT_ERR_STATE = -4,       /* call order: e.g. rt_pt_render before rt_pt_resize / set_scene / set_camera */
+    RT_ERR_CAPACITY = -5,    /* scene too large for this build's on-chip staging (Whitted only) */
+    RT_ERR_IO = -6           /* scene file could not be read / parsed */
+} rt_status;
+
+typedef struct rt_ctx rt_ctx;
+
+/* Work counters of the most recent counted launch (rt_set_counting).  The same quantities the
+ * oracle counts; SURVEY.md 8d derives the algorithmic FLOPs from them
+ * (smallpt: 17 per sphere test; Whitted: 16 per sphere test, 12 per plane test). */
+typedef struct {
+    uint64_t nearest_queries;  /* Whitted raytrace() calls (R323/raytracer_non_OpenCL.c:179) / smallpt Intersect() (SPT/geomfunc.h:71) */
+    uint64_t shadow_queries;   /* Whitted shadow rays (:223-241) / smallpt IntersectP() (SPT/geomfunc.h:94) */
+    uint64_t sphere_tests;     /* sphere_intersect (:111) / SphereIntersect (SPT/geomfunc.h:32) evaluations */
+    uint64_t plane_tests;      /* plane_intersect (:95) evaluations; 0 for smallpt */
+    uint64_t samples;          /* smallpt: pixel samples; Whitted: primary rays */
+} rt_counters;
+
+/* ------------------------------------------------------------------ context */
+
+/* Replaces SetUpOpenCL (SPT/smallptGPU.cpp:209-615) and initialize_openCL (R323/raytracer.c:84-415):
+ * binds one CUDA device, creates the stream and the persistent-kernel work counters.
+ * One context per GPU; one process per GPU under torchrun passes LOCAL_RANK as `device`. */
+int rt_init(rt_ctx **ctx, int device);
+/* Replaces FreeBuffers + the clRelease* sequence (SPT/smallptGPU.cpp:76-98; R323/raytracer.c:642-684). */
+void rt_destroy(rt_ctx *ctx);
+/* Message of the last failing call on this context (ctx may be NULL for rt_init failures). */
+const char *rt_last_error(const rt_ctx *ctx);
+/* Number of SMs, SM clock (kHz) and name of the bound device; any pointer may be NULL. */
+int rt_device_info(const rt_ctx *ctx, int *sm_count, int *sm_clock_khz, char *name, int name_cap);
+
+/* Multi-GPU image sharding (not in the reference, which drives one OpenCL device).
+ * The frame is cut into tiles of `tile_rows` rows; this context renders the tiles t with
+ * t % world == rank and leaves every other row of its buffers untouched.  Per-pixel indices and
+ * seeds stay global, so each pixel runs exactly the 1-GPU instruction stream.  Default 0/1/8. */
+int rt_set_shard(rt_ctx *ctx, int rank, int world, int tile_rows);
+/* Enable (1) / disable (0) the work counters; counted launches are slower, never time them. */
+int rt_set_counting(rt_ctx *ctx, int enabled);
+int rt_get_counters(rt_ctx *ctx, rt_counters *out);
+/* Launch tuning (no reference counterpart; the reference's only knob is the OpenCL work-group size
+ * argument of its command line, SPT/RUN_SCENE_*.bat).  Keys: */
+enum {
+    RT_TUNE_PT_MAX_RESIDENT_BYTES = 0,  /* sphere (p, rad^2) arrays larger than this are streamed through shared memory in chunks */
+    RT_TUNE_PT_CHUNK_SPHERES = 1,       /* spheres per chunk in that mode */
+    RT_TUNE_MAX_BLOCKS_PER_SM = 2       /* cap on resident CTAs per SM (0 = as many as fit) */
+};
+int rt_set_tuning(rt_ctx *ctx, int key, int value);
+
+/* ------------------------------------------------------------------ Whitted tracer
+ *
+ * One call = one frame of R323/raytracer_kernel.cl:246-383 (`raytracer_kernel`), with the numerics
+ * of its CPU twin R323/raytracer_non_OpenCL.c:285-450 (`raytracer_non_kernel`), which is what
+ * release 3.2.03 actually runs (R323/raytracer.c:752-756) and what the golden test.bmp shows. */
+
+/* Replaces run_openCL_kernel (R323/raytracer.c:417-640: clSetKernelArg x6, clEnqueueNDRangeKernel,
+ * clWaitForEvents, clEnqueueReadBuffer) and has the CPU twin's signature
+ * raytracer_non_kernel(uchar_4*, int, int, Primitive_2*, int) (R323/raytracer.c:11-16) plus the
+ * context and a hit-ID tap.  pixels_out: w*h uchar4, row-major, top row first, (r,g,b,0).
+ * hit_id_out: NULL, or int[w*h*9]: the primitive index returned by raytrace() for each of the
+ * nine primary rays of a pixel (sub-sample index (tx+1)*3+(ty+1), -1 = miss).
+ * Host buffers in, host buffers out; the copies are part of the call. */
+int rt_whitted_render(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int h,
+                      rt_uchar4 *pixels_out, int32_t *hit_id_out);
+
+/* The same frame split into its three steps, so that a caller (bench.py) can keep the scene and
+ * the framebuffer resident in HBM: upload = clCreateBuffer + clEnqueueWriteBuffer
+ * (R323/raytracer.c:303-345), launch = clEnqueueNDRangeKernel (:561-570, asynchronous on the
+ * context's stream), download = clEnqueueReadBuffer (:600-609, blocking). */
+int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int h, int want_hit_ids);
+int rt_whitted_launch(rt_ctx *ctx);
+int rt_whitted_download(rt_ctx *ctx, rt_uchar4 *pixels_out, int32_t *hit_id_out);
+
+/* ------------------------------------------------------------------ smallpt path tracer
+ *
+ * Replaces the RadianceGPU kernel (SPT/rendering_kernel.cl:53-97 and rendering_kernel_dl.cl) and
+ * the host glue around it.  Seed <-> pixel mapping is the CPU twin's: pixel (x,y) uses
+ * seeds[2*i], seeds[2*i+1] and colors[i] with i = (h-1-y)*w + x (SPT/smallptCPU.cpp:86-90),
+ * and writes pixels[y*w + x]. */
+
+/* Replaces AllocateBuffers (SPT/smallptGPU.cpp:100-167): sizes the colour / seed / pixel buffers
+ * and uploads the caller's seeds (2*w*h u32, each >= 2 by the reference's rule at :106-110; seeds
+ * are never generated inside the library).  Resets the sample counter. */
+int rt_pt_resize(rt_ctx *ctx, int w, int h, const uint32_t *seeds);
+/* Replaces the sphere upload of SetUpOpenCL / ReInitSceneGPU (SPT/smallptGPU.cpp:489-498, 784-803).
+ * Resets the sample counter. */
+int rt_pt_set_scene(rt_ctx *ctx, const rt_sphere *spheres, uint32_t n);
+/* Replaces the camera upload of ReInitGPU (SPT/smallptGPU.cpp:805-830); `cam` must already hold
+ * dir/x/y as computed by UpdateCamera (SPT/displayfunc.cpp:182-195; rt_update_camera below).
+ * Resets the sample counter. */
+int rt_pt_set_camera(rt_ctx *ctx, const rt_camera *cam);
+/* Replaces UpdateRenderingGPU (SPT/smallptGPU.cpp:642-782): runs n_passes more sample passes
+ * (the reference launches one kernel per pass; here the pass loop is inside one kernel) starting
+ * at the context's currentSample, then copies back what is asked for:
+ * pixels_out w*h u32 (r | g<<8 | b<<16), colors_out 3*w*h float, seeds_out 2*w*h u32; any may be NULL.
+ * integrator: 0 = RadiancePathTracing (SPT/geomfunc.h:167), 1 = RadianceDirectLighting (:340). */
+int rt_pt_render(rt_ctx *ctx, int integrator, int n_passes,
+                 uint32_t *pixels_out, float *colors_out, uint32_t *seeds_out);
+/* Asynchronous launch only (state stays in HBM), and the matching blocking read-back. */
+int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes);
+int rt_pt_download(rt_ctx *ctx, uint32_t *pixels_out, float *colors_out, uint32_t *seeds_out);
+/* currentSample of the reference (SPT/smallptGPU.cpp:60): passes accumulated so far. */
+int rt_pt_current_sample(const rt_ctx *ctx);
+/* Sample-sharded progressive mode: colors hold running SUMS instead of running
+ * means, so that per-rank buffers can be added with ncclAllReduce; rt_pt_resolve_sums() then
+ * divides by total_samples and writes the 8-bit pixels.  Not bit-identical to the reference's
+ * sequential running mean; judged by RMSE only. */
+int rt_pt_set_accumulate_sums(rt_ctx *ctx, int enabled);
+int rt_pt_resolve_sums(rt_ctx *ctx, int total_samples);
+
+/* ------------------------------------------------------------------ timing and raw access */
+
+int rt_sync(rt_ctx *ctx);
+/* CUDA events on the context's stream: begin/end bracket any number of *_launch calls. */
+int rt_timer_begin(rt_ctx *ctx);
+int rt_timer_end(rt_ctx *ctx, float *elapsed_ms);   /* synchronises on the end event */
+/* Kernels launched by this context so far. */
+uint64_t rt_launch_count(const rt_ctx *ctx);
+/* Device addresses of the context's buffers, for collectives issued by the caller (NCCL through
+ * torch.distributed in bench.py) -- returns NULL if not allocated.  which: */
+enum { RT_BUF_WHITTED_PIXELS = 0, RT_BUF_WHITTED_HITS = 1, RT_BUF_PT_PIXELS = 2, RT_BUF_PT_COLORS = 3, RT_BUF_PT_SEEDS = 4 };
+void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes);
+/* The context's cudaStream_t as an opaque pointer (for callers that order their own work after it). */
+void *rt_stream(rt_ctx *ctx);
+
+/* ------------------------------------------------------------------ host-side scene helpers
+ * (kept from the reference's host code; pure CPU, no device needed) */
+
+/* UpdateCamera (SPT/displayfunc.cpp:182-195): derives dir, x, y from orig, target and the image size. */
+void rt_update_camera(rt_camera *cam, int w, int h);
+/* ReadScene (SPT/displayfunc.cpp:120-180): parses a .scn file.  *spheres_out is malloc'd
+ * (free with rt_free); cam_out receives orig/target only.  Returns RT_OK or RT_ERR_IO. */
+int rt_read_scene(const char *path, rt_camera *cam_out, rt_sphere **spheres_out, uint32_t *n_out);
+/* Writes what `perl SPT/scene_build_complex.pl` prints for the given $maxDepth, preceded by the
+ * camera / size / light / floor header of SPT/scenes/complex.scn (lines 1-4). */
+int rt_write_complex_scene(const char *path, int max_depth);
+/* create_scene + the Primitive -> Primitive_2 copy (R323/scene.c:48-128, R323/raytracer.c:721-746).
+ * which = CHOOSE_SCENE (0: 17 slots, 1: 64 slots).  Returns the primitive count, or <0. */
+int rt_whitted_create_scene(int which, rt_primitive *out, int cap);
+/* write_bmp_file (R323/bitmap.c:8-75): 24-bit BMP, bottom row first, BGR. */
+int rt_write_bmp(const char *path, const rt_uchar4 *pixels, int w, int h);
+/* The 'p' key of the reference viewer (SPT/displayfunc.cpp:254-271): P3 PPM, bottom row first. */
+int rt_write_ppm(const char *path, const uint32_t *pixels, int w, int h);
+void rt_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

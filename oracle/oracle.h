@@ -84,6 +84,12 @@ void oracle_pt_render(int integrator, const op_sphere *sph, uint32_t n, const op
                       int w, int h, int pass0, int n_passes,
                       float *colors, uint32_t *seeds, uint32_t *pixels, int threads, op_counters *ctr);
 
+/* Host libm taps (sinf/cosf/expf/powf as the reference's C++ build binds them), for the math parity tests. */
+void oracle_libm_sincosf(const float *in, float *sin_out, float *cos_out, long n);
+void oracle_libm_expf(const float *in, float *out, long n);
+void oracle_libm_to_int_gamma(const float *in, int *out, long n);
+double oracle_libm_pow20(float v);
+
 #ifdef __cplusplus
 }
 #endif

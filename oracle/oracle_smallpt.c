@@ -283,3 +283,11 @@ void oracle_pt_render(int integrator, const op_sphere *sph, uint32_t n, const op
         }
     free(t); free(jobs);
 }
+
+/* Host libm taps for tests/test_math_parity.py: the float functions the reference's C++ build binds to. */
+void oracle_libm_sincosf(const float *in, float *sin_out, float *cos_out, long n) {
+    for (long i = 0; i < n; i++) { sin_out[i] = sinf(in[i]); cos_out[i] = cosf(in[i]); }
+}
+void oracle_libm_expf(const float *in, float *out, long n) { for (long i = 0; i < n; i++) out[i] = expf(in[i]); }
+void oracle_libm_to_int_gamma(const float *in, int *out, long n) { for (long i = 0; i < n; i++) out[i] = to_byte(in[i]); }
+double oracle_libm_pow20(float v) { return pow((double)v, 20.0); }

@@ -1,0 +1,314 @@
+"""ctypes binding of librt_b200.so -- the reference-side stub a Python caller would use.
+
+The product is the shared library (CUDA kernels for sm_100a behind the C ABI of
+``include/rt_b200.h``); this module only declares its entry points for ``ctypes`` and wraps them in
+a thin class whose method names and argument meaning mirror the reference's host entry points
+(``UpdateRenderingGPU`` -> :meth:`Renderer.pt_render`, ``raytracer_non_kernel`` ->
+:meth:`Renderer.whitted_render`, ``ReadScene``/``UpdateCamera``/``create_scene`` -> module
+functions).  There is no Python or CPU implementation of the rendering path here: if the library
+or a CUDA device is missing, loading / ``Renderer()`` raises.
+
+The directory name contains hyphens (it is the reference's repository name), so import it with
+``importlib`` -- see ``load()`` in ``__graft_entry__.py``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+
+# ----------------------------------------------------------------------------- POD layouts
+SPHERE_DTYPE = np.dtype([("rad", "<f4"), ("p", "<f4", 3), ("e", "<f4", 3), ("c", "<f4", 3), ("refl", "<i4")])
+CAMERA_DTYPE = np.dtype([("orig", "<f4", 3), ("target", "<f4", 3), ("dir", "<f4", 3), ("x", "<f4", 3), ("y", "<f4", 3)])
+PRIMITIVE_DTYPE = np.dtype([
+    ("m_color", "<f4", 4), ("m_refl", "<f4"), ("m_diff", "<f4"), ("m_refr", "<f4"), ("m_refr_index", "<f4"),
+    ("m_spec", "<f4"), ("dummy_3", "<f4"), ("type", "<i4"), ("is_light", "u1"), ("pad_", "u1", 3),
+    ("normal", "<f4", 4), ("center", "<f4", 4), ("depth", "<f4"), ("radius", "<f4"), ("sq_radius", "<f4"),
+    ("r_radius", "<f4")])
+assert SPHERE_DTYPE.itemsize == 44 and CAMERA_DTYPE.itemsize == 60 and PRIMITIVE_DTYPE.itemsize == 96
+
+
+class Counters(C.Structure):
+    _fields_ = [("nearest_queries", C.c_uint64), ("shadow_queries", C.c_uint64), ("sphere_tests", C.c_uint64),
+                ("plane_tests", C.c_uint64), ("samples", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
+
+RT_OK, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_ARG, RT_ERR_STATE, RT_ERR_CAPACITY, RT_ERR_IO = 0, -1, -2, -3, -4, -5, -6
+TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM = 0, 1, 2
+BUF_WHITTED_PIXELS, BUF_WHITTED_HITS, BUF_PT_PIXELS, BUF_PT_COLORS, BUF_PT_SEEDS = 0, 1, 2, 3, 4
+
+# Every symbol include/rt_b200.h declares: name -> (restype, argtypes).
+_VP, _I, _U32, _U64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64
+SYMBOLS = {
+    "rt_init": (_I, [C.POINTER(_VP), _I]),
+    "rt_destroy": (None, [_VP]),
+    "rt_last_error": (C.c_char_p, [_VP]),
+    "rt_device_info": (_I, [_VP, C.POINTER(_I), C.POINTER(_I), C.c_char_p, _I]),
+    "rt_set_shard": (_I, [_VP, _I, _I, _I]),
+    "rt_set_counting": (_I, [_VP, _I]),
+    "rt_get_counters": (_I, [_VP, C.POINTER(Counters)]),
+    "rt_set_tuning": (_I, [_VP, _I, _I]),
+    "rt_whitted_render": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
+    "rt_whitted_upload": (_I, [_VP, _VP, _I, _I, _I, _I]),
+    "rt_whitted_launch": (_I, [_VP]),
+    "rt_whitted_download": (_I, [_VP, _VP, _VP]),
+    "rt_pt_resize": (_I, [_VP, _I, _I, _VP]),
+    "rt_pt_set_scene": (_I, [_VP, _VP, _U32]),
+    "rt_pt_set_camera": (_I, [_VP, _VP]),
+    "rt_pt_render": (_I, [_VP, _I, _I, _VP, _VP, _VP]),
+    "rt_pt_launch": (_I, [_VP, _I, _I]),
+    "rt_pt_download": (_I, [_VP, _VP, _VP, _VP]),
+    "rt_pt_current_sample": (_I, [_VP]),
+    "rt_pt_set_accumulate_sums": (_I, [_VP, _I]),
+    "rt_pt_resolve_sums": (_I, [_VP, _I]),
+    "rt_sync": (_I, [_VP]),
+    "rt_timer_begin": (_I, [_VP]),
+    "rt_timer_end": (_I, [_VP, C.POINTER(C.c_float)]),
+    "rt_launch_count": (_U64, [_VP]),
+    "rt_device_buffer": (_VP, [_VP, _I, C.POINTER(_U64)]),
+    "rt_stream": (_VP, [_VP]),
+    "rt_update_camera": (None, [_VP, _I, _I]),
+    "rt_read_scene": (_I, [C.c_char_p, _VP, C.POINTER(_VP), C.POINTER(_U32)]),
+    "rt_write_complex_scene": (_I, [C.c_char_p, _I]),
+    "rt_whitted_create_scene": (_I, [_I, _VP, _I]),
+    "rt_write_bmp": (_I, [C.c_char_p, _VP, _I, _I]),
+    "rt_write_ppm": (_I, [C.c_char_p, _VP, _I, _I]),
+    "rt_free": (None, [_VP]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads librt_b200.so (once).  Raises if it has not been built -- there is no other path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(or `make -C se-195-project-ray-tracer_b200`). The renderer has no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+class RtError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"rt_b200 error {code}: {message}")
+        self.code = code
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------------------- host-side scene helpers
+def update_camera(cam, w, h):
+    """UpdateCamera (SPT/displayfunc.cpp:182-195) on a CAMERA_DTYPE record array of length 1."""
+    assert cam.dtype == CAMERA_DTYPE and cam.size == 1
+    lib().rt_update_camera(_ptr(cam), w, h)
+    return cam
+
+
+def read_scene(path, w, h):
+    """ReadScene + UpdateCamera (SPT/displayfunc.cpp:120-195): returns (spheres, camera)."""
+    cam = np.zeros(1, CAMERA_DTYPE)
+    sp, n = C.c_void_p(), C.c_uint32()
+    rc = lib().rt_read_scene(os.fsencode(path), _ptr(cam), C.byref(sp), C.byref(n))
+    if rc != RT_OK:
+        raise RtError(rc, f"cannot read scene {path}")
+    try:
+        spheres = np.frombuffer(C.string_at(sp.value, n.value * 44), dtype=SPHERE_DTYPE).copy()
+    finally:
+        lib().rt_free(sp)
+    update_camera(cam, w, h)
+    return spheres, cam
+
+
+def write_complex_scene(path, max_depth):
+    rc = lib().rt_write_complex_scene(os.fsencode(path), max_depth)
+    if rc != RT_OK:
+        raise RtError(rc, f"cannot write {path}")
+
+
+def whitted_create_scene(which=0):
+    """create_scene of R323/scene.c:48-128 as flat Primitive_2 records."""
+    out = np.zeros(64, PRIMITIVE_DTYPE)
+    n = lib().rt_whitted_create_scene(which, _ptr(out), out.size)
+    if n < 0:
+        raise RtError(n, "rt_whitted_create_scene")
+    return out[:n].copy()
+
+
+def write_bmp(path, pixels):
+    h, w = pixels.shape[:2]
+    rc = lib().rt_write_bmp(os.fsencode(path), _ptr(np.ascontiguousarray(pixels)), w, h)
+    if rc != RT_OK:
+        raise RtError(rc, f"cannot write {path}")
+
+
+def write_ppm(path, pixels_u32):
+    h, w = pixels_u32.shape
+    rc = lib().rt_write_ppm(os.fsencode(path), _ptr(np.ascontiguousarray(pixels_u32)), w, h)
+    if rc != RT_OK:
+        raise RtError(rc, f"cannot write {path}")
+
+
+def reference_seeds(w, h, seed=1):
+    """The reference's seed rule (SPT/smallptGPU.cpp:105-110): 2*w*h draws, each clamped to >= 2.
+    The reference draws from libc rand(); the C ABI takes seeds as an INPUT, so any generator will do --
+    numpy's is used here so that fixtures do not depend on a libc."""
+    s = np.random.RandomState(seed).randint(0, 2 ** 31 - 1, size=2 * w * h, dtype=np.int64).astype(np.uint32)
+    return np.maximum(s, 2).astype(np.uint32)
+
+
+# ----------------------------------------------------------------------------- the renderer
+class Renderer:
+    """One context = one GPU.  Method names follow the reference's host entry points."""
+
+    def __init__(self, device=0):
+        self._lib = lib()
+        self._ctx = C.c_void_p()
+        rc = self._lib.rt_init(C.byref(self._ctx), device)
+        if rc != RT_OK:
+            msg = self._lib.rt_last_error(None).decode()
+            self._ctx = None
+            raise RtError(rc, msg)
+        self.pt_size = None
+        self.whitted_size = None
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.rt_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != RT_OK:
+            raise RtError(rc, self._lib.rt_last_error(self._ctx).decode())
+
+    # -- context
+    def device_info(self):
+        sm, khz = C.c_int(), C.c_int()
+        name = C.create_string_buffer(256)
+        self._ck(self._lib.rt_device_info(self._ctx, C.byref(sm), C.byref(khz), name, 256))
+        return {"sm_count": sm.value, "sm_clock_khz": khz.value, "name": name.value.decode()}
+
+    def set_shard(self, rank, world, tile_rows=8):
+        self._ck(self._lib.rt_set_shard(self._ctx, rank, world, tile_rows))
+
+    def set_counting(self, enabled):
+        self._ck(self._lib.rt_set_counting(self._ctx, int(bool(enabled))))
+
+    def counters(self):
+        c = Counters()
+        self._ck(self._lib.rt_get_counters(self._ctx, C.byref(c)))
+        return c.as_dict()
+
+    def set_tuning(self, key, value):
+        self._ck(self._lib.rt_set_tuning(self._ctx, key, value))
+
+    def sync(self):
+        self._ck(self._lib.rt_sync(self._ctx))
+
+    def timer_begin(self):
+        self._ck(self._lib.rt_timer_begin(self._ctx))
+
+    def timer_end(self):
+        ms = C.c_float()
+        self._ck(self._lib.rt_timer_end(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return int(self._lib.rt_launch_count(self._ctx))
+
+    def device_buffer(self, which):
+        n = C.c_uint64()
+        p = self._lib.rt_device_buffer(self._ctx, which, C.byref(n))
+        return p, n.value
+
+    # -- Whitted (raytracer_non_kernel(pixels, width, height, primitives, n_primitives))
+    def whitted_render(self, prims, w, h, want_hit_ids=False, pixels_out=None, hits_out=None):
+        prims = np.ascontiguousarray(prims)
+        assert prims.dtype == PRIMITIVE_DTYPE
+        pixels = pixels_out if pixels_out is not None else np.zeros((h, w, 4), np.uint8)
+        hits = None
+        if want_hit_ids:
+            hits = hits_out if hits_out is not None else np.zeros((h, w, 9), np.int32)
+        self._ck(self._lib.rt_whitted_render(self._ctx, _ptr(prims), prims.size, w, h, _ptr(pixels), _ptr(hits)))
+        self.whitted_size = (w, h)
+        return (pixels, hits) if want_hit_ids else pixels
+
+    def whitted_upload(self, prims, w, h, want_hit_ids=False):
+        prims = np.ascontiguousarray(prims)
+        assert prims.dtype == PRIMITIVE_DTYPE
+        self._ck(self._lib.rt_whitted_upload(self._ctx, _ptr(prims), prims.size, w, h, int(want_hit_ids)))
+        self.whitted_size = (w, h)
+
+    def whitted_launch(self):
+        self._ck(self._lib.rt_whitted_launch(self._ctx))
+
+    def whitted_download(self, want_hit_ids=False, pixels_out=None):
+        w, h = self.whitted_size
+        pixels = pixels_out if pixels_out is not None else np.zeros((h, w, 4), np.uint8)
+        hits = np.zeros((h, w, 9), np.int32) if want_hit_ids else None
+        self._ck(self._lib.rt_whitted_download(self._ctx, _ptr(pixels), _ptr(hits)))
+        return (pixels, hits) if want_hit_ids else pixels
+
+    # -- smallpt (AllocateBuffers / ReInitSceneGPU / ReInitGPU / UpdateRenderingGPU)
+    def pt_resize(self, w, h, seeds):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        assert seeds.size == 2 * w * h
+        self._ck(self._lib.rt_pt_resize(self._ctx, w, h, _ptr(seeds)))
+        self.pt_size = (w, h)
+
+    def pt_set_scene(self, spheres):
+        spheres = np.ascontiguousarray(spheres)
+        assert spheres.dtype == SPHERE_DTYPE
+        self._ck(self._lib.rt_pt_set_scene(self._ctx, _ptr(spheres), spheres.size))
+
+    def pt_set_camera(self, cam):
+        assert cam.dtype == CAMERA_DTYPE and cam.size == 1
+        self._ck(self._lib.rt_pt_set_camera(self._ctx, _ptr(cam)))
+
+    def pt_render(self, integrator, n_passes, want=("pixels", "colors", "seeds"), pixels_out=None):
+        w, h = self.pt_size
+        pixels = (pixels_out if pixels_out is not None else np.zeros((h, w), np.uint32)) if "pixels" in want else None
+        colors = np.zeros((h, w, 3), np.float32) if "colors" in want else None
+        seeds = np.zeros(2 * w * h, np.uint32) if "seeds" in want else None
+        self._ck(self._lib.rt_pt_render(self._ctx, integrator, n_passes, _ptr(pixels), _ptr(colors), _ptr(seeds)))
+        return {"pixels": pixels, "colors": colors, "seeds": seeds}
+
+    def pt_launch(self, integrator, n_passes):
+        self._ck(self._lib.rt_pt_launch(self._ctx, integrator, n_passes))
+
+    def pt_download(self, want=("pixels", "colors", "seeds")):
+        w, h = self.pt_size
+        pixels = np.zeros((h, w), np.uint32) if "pixels" in want else None
+        colors = np.zeros((h, w, 3), np.float32) if "colors" in want else None
+        seeds = np.zeros(2 * w * h, np.uint32) if "seeds" in want else None
+        self._ck(self._lib.rt_pt_download(self._ctx, _ptr(pixels), _ptr(colors), _ptr(seeds)))
+        return {"pixels": pixels, "colors": colors, "seeds": seeds}
+
+    def pt_current_sample(self):
+        return int(self._lib.rt_pt_current_sample(self._ctx))
+
+    def pt_set_accumulate_sums(self, enabled):
+        self._ck(self._lib.rt_pt_set_accumulate_sums(self._ctx, int(bool(enabled))))
+
+    def pt_resolve_sums(self, total_samples):
+        self._ck(self._lib.rt_pt_resolve_sums(self._ctx, total_samples))

@@ -1,0 +1,415 @@
+// rt_api.cu -- the C ABI declared in include/rt_b200.h: context, device buffers, launches, copies.
+//
+// This layer is what replaces the reference's OpenCL host glue (SPT/smallptGPU.cpp:100-830,
+// R323/raytracer.c:84-684).  There is deliberately no CPU path in it: every render entry point
+// either launches the sm_100a kernels of rt_kernels.cu or returns an error code.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include "../../include/rt_b200.h"
+#include "scene_soa.h"
+#include "rt_kernels.h"
+
+using namespace rtb;
+
+struct rt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0, clock_khz = 0, max_smem_optin = 0;
+    char name[256] = {0};
+    char err[512] = {0};
+    int shard_rank = 0, shard_world = 1, tile_rows = 8;
+    int counting = 0;
+    unsigned *d_work = nullptr;                    // one work counter per launch slot (zeroed before each launch)
+    unsigned long long *d_counters = nullptr;      // 5 x u64
+    uint64_t launches = 0;
+    // tuning
+    int pt_max_resident_bytes = 96 * 1024;
+    int pt_chunk_spheres = 3072;                   // 48 KB of (p, rad^2) per chunk
+    int max_blocks_per_sm = 0;
+    // Whitted
+    int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_want_hits = 0;
+    f4 *d_wgeom = nullptr, *d_wma = nullptr, *d_wmb = nullptr;
+    int *d_wflags = nullptr, *d_wlights = nullptr;
+    float *d_wrrad = nullptr;
+    uint32_t *d_wpixels = nullptr;
+    int32_t *d_whits = nullptr;
+    size_t w_pixels_cap = 0, w_hits_cap = 0;
+    int w_scene_cap = 0;
+    // path tracer
+    int p_w = 0, p_h = 0, p_n = 0, p_nl = 0;
+    float *d_colors = nullptr;
+    uint32_t *d_seeds = nullptr, *d_ppixels = nullptr;
+    f4 *d_pgeom = nullptr, *d_pemis = nullptr, *d_pcolr = nullptr;
+    int *d_plights = nullptr;
+    rt_camera cam;
+    bool have_cam = false, have_scene = false, have_size = false;
+    int current_sample = 0, sum_mode = 0;
+};
+
+static thread_local char g_init_err[512] = "";
+
+static int fail(rt_ctx *c, int code, const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(c ? c->err : g_init_err, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+static cudaError_t upload_vec(T **dptr, const std::vector<T> &v, cudaStream_t s) {
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    const size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)dptr, bytes);
+    if (e != cudaSuccess) return e;
+    if (v.size()) e = cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    return e;
+}
+
+extern "C" {
+
+int rt_init(rt_ctx **out, int device) {
+    rt_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, RT_ERR_ARG, "rt_init: ctx is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, RT_ERR_NO_DEVICE, "rt_init: no CUDA device (%s); this renderer has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, RT_ERR_ARG, "rt_init: device %d out of range (0..%d)", device, count - 1);
+    ctx = new rt_ctx();
+    ctx->device = device;
+    memset(&ctx->cam, 0, sizeof ctx->cam);
+    auto bail = [&](cudaError_t err, const char *what) {
+        fail(nullptr, RT_ERR_CUDA, "rt_init: %s failed: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return (int)RT_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device);
+    snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc((void **)&ctx->d_work, sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_counters, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->d_counters, 0, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_destroy(rt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights,
+                     ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
+                     ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
+    for (void *b : bufs) if (b) cudaFree(b);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *rt_last_error(const rt_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
+
+int rt_device_info(const rt_ctx *ctx, int *sm_count, int *sm_clock_khz, char *name, int name_cap) {
+    if (!ctx) return RT_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (sm_clock_khz) *sm_clock_khz = ctx->clock_khz;
+    if (name && name_cap > 0) snprintf(name, name_cap, "%s", ctx->name);
+    return RT_OK;
+}
+
+int rt_set_shard(rt_ctx *ctx, int rank, int world, int tile_rows) {
+    if (!ctx) return RT_ERR_ARG;
+    if (world < 1 || rank < 0 || rank >= world || tile_rows < 1)
+        return fail(ctx, RT_ERR_ARG, "rt_set_shard: need 0 <= rank < world and tile_rows >= 1 (got %d, %d, %d)", rank, world, tile_rows);
+    ctx->shard_rank = rank; ctx->shard_world = world; ctx->tile_rows = tile_rows;
+    return RT_OK;
+}
+
+int rt_set_counting(rt_ctx *ctx, int enabled) {
+    if (!ctx) return RT_ERR_ARG;
+    ctx->counting = enabled ? 1 : 0;
+    return RT_OK;
+}
+
+int rt_get_counters(rt_ctx *ctx, rt_counters *out) {
+    if (!ctx || !out) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long h[5];
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(h, ctx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    out->nearest_queries = h[0]; out->shadow_queries = h[1]; out->sphere_tests = h[2]; out->plane_tests = h[3]; out->samples = h[4];
+    return RT_OK;
+}
+
+int rt_set_tuning(rt_ctx *ctx, int key, int value) {
+    if (!ctx) return RT_ERR_ARG;
+    switch (key) {
+        case RT_TUNE_PT_MAX_RESIDENT_BYTES: if (value < 0) break; ctx->pt_max_resident_bytes = value; return RT_OK;
+        case RT_TUNE_PT_CHUNK_SPHERES: if (value < 1) break; ctx->pt_chunk_spheres = value; return RT_OK;
+        case RT_TUNE_MAX_BLOCKS_PER_SM: if (value < 0) break; ctx->max_blocks_per_sm = value; return RT_OK;
+        default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
+    }
+    return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
+}
+
+// ------------------------------------------------------------------------------------------------ Whitted
+
+int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int h, int want_hit_ids) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!prims || n < 1 || w < 1 || h < 1) return fail(ctx, RT_ERR_ARG, "rt_whitted_upload: need prims, n >= 1, w >= 1, h >= 1");
+    CK(cudaSetDevice(ctx->device));
+    WSoA soa;
+    build_w_soa(prims, n, soa);
+    if (rtk_whitted_smem_bytes(n, (int)soa.lights.size(), 0) > (size_t)ctx->max_smem_optin)
+        return fail(ctx, RT_ERR_CAPACITY, "rt_whitted_upload: %d primitives exceed the %d-byte shared-memory staging of this build", n, ctx->max_smem_optin);
+    CK(upload_vec(&ctx->d_wgeom, soa.geom, ctx->stream));
+    CK(upload_vec(&ctx->d_wma, soa.mat_a, ctx->stream));
+    CK(upload_vec(&ctx->d_wmb, soa.mat_b, ctx->stream));
+    CK(upload_vec(&ctx->d_wflags, soa.flags, ctx->stream));
+    CK(upload_vec(&ctx->d_wlights, soa.lights, ctx->stream));
+    CK(upload_vec(&ctx->d_wrrad, soa.rrad, ctx->stream));
+    const size_t px = (size_t)w * h;
+    if (px > ctx->w_pixels_cap) {
+        if (ctx->d_wpixels) cudaFree(ctx->d_wpixels);
+        ctx->d_wpixels = nullptr; ctx->w_pixels_cap = 0;
+        CK(cudaMalloc((void **)&ctx->d_wpixels, px * sizeof(uint32_t)));
+        ctx->w_pixels_cap = px;
+    }
+    if (want_hit_ids && px * 9 > ctx->w_hits_cap) {
+        if (ctx->d_whits) cudaFree(ctx->d_whits);
+        ctx->d_whits = nullptr; ctx->w_hits_cap = 0;
+        CK(cudaMalloc((void **)&ctx->d_whits, px * 9 * sizeof(int32_t)));
+        ctx->w_hits_cap = px * 9;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));      // the SoA vectors go out of scope
+    ctx->w_w = w; ctx->w_h = h; ctx->w_n = n; ctx->w_nl = (int)soa.lights.size();
+    ctx->w_ns = soa.n_spheres; ctx->w_np = soa.n_planes; ctx->w_want_hits = want_hit_ids ? 1 : 0;
+    return RT_OK;
+}
+
+int rt_whitted_launch(rt_ctx *ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->d_wgeom || !ctx->d_wpixels) return fail(ctx, RT_ERR_STATE, "rt_whitted_launch: call rt_whitted_upload first");
+    CK(cudaSetDevice(ctx->device));
+    WLaunch p;
+    WFrame &F = p.frame;
+    F.geom = ctx->d_wgeom; F.mat_a = ctx->d_wma; F.mat_b = ctx->d_wmb; F.flags = ctx->d_wflags; F.lights = ctx->d_wlights;
+    F.rrad = ctx->d_wrrad; F.n = ctx->w_n; F.n_lights = ctx->w_nl; F.n_spheres = ctx->w_ns; F.n_planes = ctx->w_np;
+    F.w = ctx->w_w; F.h = ctx->w_h;
+    // R323/raytracer_non_OpenCL.c:291-296: DX = (WX2 - WX1) / width with float operands.
+    const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
+    F.DX = (WX2 - WX1) / ctx->w_w; F.DY = (WY2 - WY1) / ctx->w_h;
+    F.hit_ids = ctx->w_want_hits ? ctx->d_whits : nullptr;
+    p.shard = make_shard(ctx->w_w, ctx->w_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
+    p.pixels = ctx->d_wpixels; p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
+    p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
+    p.stage_materials = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, 1) <= 32 * 1024 ? 1 : 0;
+    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
+    if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
+    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches++; }
+    return RT_OK;
+}
+
+int rt_whitted_download(rt_ctx *ctx, rt_uchar4 *pixels_out, int32_t *hit_id_out) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->d_wpixels) return fail(ctx, RT_ERR_STATE, "rt_whitted_download: nothing rendered yet");
+    if (hit_id_out && !ctx->w_want_hits) return fail(ctx, RT_ERR_STATE, "rt_whitted_download: hit IDs were not requested at upload");
+    CK(cudaSetDevice(ctx->device));
+    const size_t px = (size_t)ctx->w_w * ctx->w_h;
+    if (pixels_out) CK(cudaMemcpyAsync(pixels_out, ctx->d_wpixels, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hit_id_out) CK(cudaMemcpyAsync(hit_id_out, ctx->d_whits, px * 9 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_whitted_render(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int h, rt_uchar4 *pixels_out, int32_t *hit_id_out) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!pixels_out) return fail(ctx, RT_ERR_ARG, "rt_whitted_render: pixels_out is NULL");
+    int rc = rt_whitted_upload(ctx, prims, n, w, h, hit_id_out != nullptr);
+    if (rc) return rc;
+    if ((rc = rt_whitted_launch(ctx))) return rc;
+    return rt_whitted_download(ctx, pixels_out, hit_id_out);
+}
+
+// ------------------------------------------------------------------------------------------------ smallpt
+
+int rt_pt_resize(rt_ctx *ctx, int w, int h, const uint32_t *seeds) {
+    if (!ctx) return RT_ERR_ARG;
+    if (w < 1 || h < 1 || !seeds) return fail(ctx, RT_ERR_ARG, "rt_pt_resize: need w >= 1, h >= 1 and a seed array of 2*w*h values");
+    CK(cudaSetDevice(ctx->device));
+    const size_t px = (size_t)w * h;
+    if (ctx->d_colors) cudaFree(ctx->d_colors);
+    if (ctx->d_seeds) cudaFree(ctx->d_seeds);
+    if (ctx->d_ppixels) cudaFree(ctx->d_ppixels);
+    ctx->d_colors = nullptr; ctx->d_seeds = nullptr; ctx->d_ppixels = nullptr; ctx->have_size = false;
+    CK(cudaMalloc((void **)&ctx->d_colors, px * 3 * sizeof(float)));
+    CK(cudaMalloc((void **)&ctx->d_seeds, px * 2 * sizeof(uint32_t)));
+    CK(cudaMalloc((void **)&ctx->d_ppixels, px * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(ctx->d_colors, 0, px * 3 * sizeof(float), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ppixels, 0, px * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_seeds, seeds, px * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->p_w = w; ctx->p_h = h; ctx->have_size = true; ctx->current_sample = 0;
+    return RT_OK;
+}
+
+int rt_pt_set_scene(rt_ctx *ctx, const rt_sphere *spheres, uint32_t n) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!spheres || n < 1) return fail(ctx, RT_ERR_ARG, "rt_pt_set_scene: need at least one sphere");
+    for (uint32_t i = 0; i < n; i++)
+        if (spheres[i].refl < 0 || spheres[i].refl > 2)
+            return fail(ctx, RT_ERR_ARG, "rt_pt_set_scene: sphere %u has material %d (expected 0, 1 or 2)", i, spheres[i].refl);
+    CK(cudaSetDevice(ctx->device));
+    PtSoA soa;
+    build_pt_soa(spheres, n, soa);
+    CK(upload_vec(&ctx->d_pgeom, soa.geom, ctx->stream));
+    CK(upload_vec(&ctx->d_pemis, soa.emis, ctx->stream));
+    CK(upload_vec(&ctx->d_pcolr, soa.colr, ctx->stream));
+    CK(upload_vec(&ctx->d_plights, soa.lights, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->p_n = (int)n; ctx->p_nl = (int)soa.lights.size(); ctx->have_scene = true; ctx->current_sample = 0;
+    return RT_OK;
+}
+
+int rt_pt_set_camera(rt_ctx *ctx, const rt_camera *cam) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!cam) return fail(ctx, RT_ERR_ARG, "rt_pt_set_camera: cam is NULL");
+    ctx->cam = *cam; ctx->have_cam = true; ctx->current_sample = 0;
+    return RT_OK;
+}
+
+int rt_pt_set_accumulate_sums(rt_ctx *ctx, int enabled) {
+    if (!ctx) return RT_ERR_ARG;
+    ctx->sum_mode = enabled ? 1 : 0;
+    return RT_OK;
+}
+
+int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
+    if (!ctx) return RT_ERR_ARG;
+    if (integrator != 0 && integrator != 1) return fail(ctx, RT_ERR_ARG, "rt_pt_launch: integrator must be 0 (path tracing) or 1 (direct lighting)");
+    if (n_passes < 1) return fail(ctx, RT_ERR_ARG, "rt_pt_launch: n_passes must be >= 1");
+    if (!ctx->have_size || !ctx->have_scene || !ctx->have_cam)
+        return fail(ctx, RT_ERR_STATE, "rt_pt_launch: rt_pt_resize, rt_pt_set_scene and rt_pt_set_camera must be called first");
+    CK(cudaSetDevice(ctx->device));
+    PtLaunch p;
+    PtFrame &F = p.frame;
+    F.emis = ctx->d_pemis; F.colr = ctx->d_pcolr; F.geom_global = ctx->d_pgeom; F.lights = ctx->d_plights;
+    F.n = ctx->p_n; F.n_lights = ctx->p_nl;
+    const rt_camera &c = ctx->cam;
+    F.cam_ox = c.orig.x; F.cam_oy = c.orig.y; F.cam_oz = c.orig.z;
+    F.cam_dx = c.dir.x; F.cam_dy = c.dir.y; F.cam_dz = c.dir.z;
+    F.cam_xx = c.x.x; F.cam_xy = c.x.y; F.cam_xz = c.x.z;
+    F.cam_yx = c.y.x; F.cam_yy = c.y.y; F.cam_yz = c.y.z;
+    F.w = ctx->p_w; F.h = ctx->p_h;
+    F.inv_w = 1.f / ctx->p_w; F.inv_h = 1.f / ctx->p_h;          // SPT/smallptCPU.cpp:80-81
+    F.pass0 = ctx->current_sample; F.n_passes = n_passes;
+    F.direct_only = integrator; F.sum_mode = ctx->sum_mode;
+    p.shard = make_shard(ctx->p_w, ctx->p_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
+    p.colors = ctx->d_colors; p.seeds = ctx->d_seeds; p.pixels = ctx->d_ppixels;
+    p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
+    p.count = ctx->counting; p.sm_count = ctx->sm_count;
+    p.max_smem_geom = ctx->pt_max_resident_bytes < ctx->max_smem_optin ? ctx->pt_max_resident_bytes : ctx->max_smem_optin;
+    p.chunk_spheres = ctx->pt_chunk_spheres;
+    p.max_blocks_per_sm = ctx->max_blocks_per_sm;
+    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
+    if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
+    if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches++; }
+    ctx->current_sample += n_passes;
+    return RT_OK;
+}
+
+int rt_pt_resolve_sums(rt_ctx *ctx, int total_samples) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->have_size || total_samples < 1) return fail(ctx, RT_ERR_STATE, "rt_pt_resolve_sums: nothing to resolve");
+    CK(cudaSetDevice(ctx->device));
+    CK(rtk_launch_pt_resolve(ctx->d_colors, ctx->d_ppixels, ctx->p_w, ctx->p_h, 1.f / (float)total_samples, ctx->sm_count, ctx->stream));
+    ctx->launches++;
+    return RT_OK;
+}
+
+int rt_pt_download(rt_ctx *ctx, uint32_t *pixels_out, float *colors_out, uint32_t *seeds_out) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->have_size) return fail(ctx, RT_ERR_STATE, "rt_pt_download: rt_pt_resize has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const size_t px = (size_t)ctx->p_w * ctx->p_h;
+    if (pixels_out) CK(cudaMemcpyAsync(pixels_out, ctx->d_ppixels, px * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (colors_out) CK(cudaMemcpyAsync(colors_out, ctx->d_colors, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (seeds_out) CK(cudaMemcpyAsync(seeds_out, ctx->d_seeds, px * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_pt_render(rt_ctx *ctx, int integrator, int n_passes, uint32_t *pixels_out, float *colors_out, uint32_t *seeds_out) {
+    int rc = rt_pt_launch(ctx, integrator, n_passes);
+    if (rc) return rc;
+    return rt_pt_download(ctx, pixels_out, colors_out, seeds_out);
+}
+
+int rt_pt_current_sample(const rt_ctx *ctx) { return ctx ? ctx->current_sample : RT_ERR_ARG; }
+
+// ------------------------------------------------------------------------------------------------ timing / raw access
+
+int rt_sync(rt_ctx *ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_timer_begin(rt_ctx *ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return RT_OK;
+}
+
+int rt_timer_end(rt_ctx *ctx, float *elapsed_ms) {
+    if (!ctx || !elapsed_ms) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(elapsed_ms, ctx->ev0, ctx->ev1));
+    return RT_OK;
+}
+
+uint64_t rt_launch_count(const rt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes) {
+    if (!ctx) return nullptr;
+    const uint64_t wpx = (uint64_t)ctx->w_w * ctx->w_h, ppx = (uint64_t)ctx->p_w * ctx->p_h;
+    void *p = nullptr; uint64_t b = 0;
+    switch (which) {
+        case RT_BUF_WHITTED_PIXELS: p = ctx->d_wpixels; b = wpx * 4; break;
+        case RT_BUF_WHITTED_HITS: p = ctx->w_want_hits ? ctx->d_whits : nullptr; b = wpx * 36; break;
+        case RT_BUF_PT_PIXELS: p = ctx->d_ppixels; b = ppx * 4; break;
+        case RT_BUF_PT_COLORS: p = ctx->d_colors; b = ppx * 12; break;
+        case RT_BUF_PT_SEEDS: p = ctx->d_seeds; b = ppx * 8; break;
+        default: break;
+    }
+    if (bytes) *bytes = p ? b : 0;
+    return p;
+}
+
+void *rt_stream(rt_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+// rt_kernels.cu -- the two sm_100a kernels of librt_b200.so.
+//
+// Both kernels have the same shape (DESIGN.md "Kernel design"):
+//   * persistent CTAs: the grid is (SM count x resident CTAs per SM); every warp pulls work items
+//     (pixels, walked in 8x4 screen blocks of the rows this rank owns) from one global counter with a
+//     warp-aggregated atomicAdd -- one atomic per refill, not per lane;
+//   * one lane = one pixel for its whole life (all sample passes / all nine sub-samples), because the
+//     reference's per-pixel RNG stream and float accumulation order are sequential;
+//   * the loop body is "one ray query, then advance": every lane that has work tests its current ray
+//     (nearest-hit or shadow) against the SAME primitive at the same time, so the primitive record is
+//     one broadcast LDS.128 from the structure-of-arrays copy staged in shared memory, and lanes at
+//     different bounces / passes / pixels still share the intersection loop.  Shadow lanes drop out
+//     at their first blocker; a warp vote ends the loop early once every lane is done;
+//   * a lane that finishes its pixel refills on the next iteration, so divergence in path length
+//     costs idle lanes only at the very end of the frame;
+//   * no tensor cores: the work is branchy FP32 with single-rounded (un-fused) arithmetic, which is
+//     what makes hit IDs and RNG streams bit-identical to the reference's CPU path.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pt_lane.cuh"
+#include "whitted_lane.cuh"
+#include "rt_kernels.h"
+
+namespace rtb {
+
+#define FULL_MASK 0xffffffffu
+
+// Warp-aggregated work fetch: lanes with `need` set receive consecutive item numbers.
+__device__ __forceinline__ uint32_t fetch_items(unsigned *counter, bool need, uint32_t lane) {
+    const uint32_t m = __ballot_sync(FULL_MASK, need);
+    if (m == 0) return 0xffffffffu;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+__device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL_MASK, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// smallpt: replaces RadianceGPU (SPT/rendering_kernel.cl:53-97, rendering_kernel_dl.cl) with the pass
+// loop inside the kernel.  CHUNKED = the (p, rad^2) array does not fit in shared memory: the CTA walks
+// it in chunks, all warps in lock-step (one __syncthreads pair per chunk per query round).
+template <bool COUNT, bool CHUNKED>
+__global__ void __launch_bounds__(PT_THREADS)
+pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, uint32_t *pixels,
+          unsigned *work_counter, unsigned long long *counters, int chunk) {
+    extern __shared__ f4 s_geom[];
+    const uint32_t lane = threadIdx.x & 31u;
+
+    if (!CHUNKED) {
+        for (int i = threadIdx.x; i < F.n; i += blockDim.x) s_geom[i] = F.geom_global[i];
+        __syncthreads();
+        F.geom_global = s_geom;     // shading reads of (p, rad^2) also come from the staged copy
+    }
+
+    PtLane L;
+    L.phase = PH_IDLE;
+    L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_tests = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        const bool need = (L.phase == PH_IDLE) && !exhausted;
+        const uint32_t item = fetch_items(work_counter, need, lane);
+        if (need) {
+            if (item < n_items) {
+                int x, y;
+                if (item_to_pixel(S, F.w, item, x, y)) pt_begin_pixel(L, F, x, y, colors, seeds);
+            } else exhausted = true;
+        }
+        const bool active = L.phase != PH_IDLE;
+        const bool more = active || !exhausted;
+        if (CHUNKED) { if (!__syncthreads_or(more)) break; }
+        else         { if (!__any_sync(FULL_MASK, more)) break; }
+
+        bool done = !active;
+        if (!CHUNKED) {
+            int i = F.n - 1;
+            for (; i >= 3; i -= 4) {
+                const f4 g0 = s_geom[i], g1 = s_geom[i - 1], g2 = s_geom[i - 2], g3 = s_geom[i - 3];
+                if (!done) done = pt_test<COUNT>(L, g0, i);
+                if (!done) done = pt_test<COUNT>(L, g1, i - 1);
+                if (!done) done = pt_test<COUNT>(L, g2, i - 2);
+                if (!done) done = pt_test<COUNT>(L, g3, i - 3);
+                if ((i & 12) == 0 && __all_sync(FULL_MASK, done)) { i = -1; break; }
+            }
+            for (; i >= 0; --i) {
+                const f4 g = s_geom[i];
+                if (!done) done = pt_test<COUNT>(L, g, i);
+            }
+        } else {
+            for (int hi = F.n; hi > 0; hi -= chunk) {          // descending index, chunk by chunk
+                const int lo = hi > chunk ? hi - chunk : 0;
+                __syncthreads();
+                for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) s_geom[i - lo] = F.geom_global[i];
+                __syncthreads();
+                if (!__any_sync(FULL_MASK, !done)) continue;    // this warp has nothing left in this round
+                for (int i = hi - 1; i >= lo; --i) {
+                    const f4 g = s_geom[i - lo];
+                    if (!done) done = pt_test<COUNT>(L, g, i);
+                }
+            }
+        }
+
+        if (active && pt_advance<COUNT>(L, F)) {
+            const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
+            colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
+            seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
+            if (!F.sum_mode) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
+        }
+    }
+
+    if (COUNT) {
+        const uint64_t a = warp_sum(L.c_nearest), b = warp_sum(L.c_shadow), c = warp_sum(L.c_tests), d = warp_sum(L.c_samples);
+        if (lane == 0) {
+            atomicAdd(&counters[0], (unsigned long long)a); atomicAdd(&counters[1], (unsigned long long)b);
+            atomicAdd(&counters[2], (unsigned long long)c); atomicAdd(&counters[4], (unsigned long long)d);
+        }
+    }
+}
+
+// Sample-sharded mode: colors hold sums; divide and write the 8-bit pixels.
+__global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, int h, float inv_total) {
+    const size_t n = (size_t)w * h;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const int y = (int)(p / w), x = (int)(p % w);
+        const size_t i = (size_t)(h - y - 1) * w + x;
+        pixels[p] = pt_pack_pixel(f_mul(colors[3 * i], inv_total), f_mul(colors[3 * i + 1], inv_total), f_mul(colors[3 * i + 2], inv_total));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whitted: replaces raytracer_kernel (R323/raytracer_kernel.cl:246-383) with the numerics of its CPU
+// twin.  The reference copies the 96-byte AoS primitives to local memory (:254-258) and keeps a
+// 64-slot x 80-byte ray queue in private memory; here the primitives are SoA float4 in shared memory
+// and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
+template <bool COUNT>
+__global__ void __launch_bounds__(W_THREADS)
+whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *work_counter,
+               unsigned long long *counters, int stage_materials) {
+    extern __shared__ f4 s_raw[];
+    // layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | rrad[n] (optional) | lights[n_lights] (optional)
+    f4 *s_geom = s_raw;
+    int *s_flags;
+    const uint32_t lane = threadIdx.x & 31u;
+    {
+        const int n = F.n;
+        f4 *s_ma = s_geom + n, *s_mb = s_ma + n;
+        int *ibase = stage_materials ? (int *)(s_mb + n) : (int *)(s_geom + n);
+        s_flags = ibase;
+        float *s_rr = (float *)(ibase + n);
+        int *s_li = (int *)(s_rr + n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            s_geom[i] = F.geom[i];
+            s_flags[i] = F.flags[i];
+            if (stage_materials) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; }
+        }
+        if (stage_materials)
+            for (int i = threadIdx.x; i < F.n_lights; i += blockDim.x) s_li[i] = F.lights[i];
+        __syncthreads();
+        F.geom = s_geom; F.flags = s_flags;
+        if (stage_materials) { F.mat_a = s_ma; F.mat_b = s_mb; F.rrad = s_rr; F.lights = s_li; }
+    }
+
+    f4 queue[3 * W_QUEUE_SLOTS];
+    WLane L;
+    L.phase = PH_IDLE;
+    L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_sphere_tests = L.c_plane_tests = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        const bool need = (L.phase == PH_IDLE) && !exhausted;
+        const uint32_t item = fetch_items(work_counter, need, lane);
+        if (need) {
+            if (item < n_items) {
+                int x, y;
+                if (item_to_pixel(S, F.w, item, x, y)) w_begin_pixel(L, F, x, y);
+            } else exhausted = true;
+        }
+        const bool active = L.phase != PH_IDLE;
+        if (!__any_sync(FULL_MASK, active || !exhausted)) break;
+
+        bool done = !active;
+        for (int s = 0; s < F.n; ++s) {                         // ascending index, RNO:185
+            const f4 g = s_geom[s];
+            const int fl = s_flags[s];
+            if (!done) done = w_test<COUNT>(L, g, fl, s);
+            if ((s & 7) == 7 && __all_sync(FULL_MASK, done)) break;
+        }
+
+        if (active && w_advance<COUNT>(L, F, queue))
+            pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(L.ar, L.ag, L.ab);
+    }
+
+    if (COUNT) {
+        const uint64_t a = warp_sum(L.c_nearest), b = warp_sum(L.c_shadow), c = warp_sum(L.c_sphere_tests),
+                       d = warp_sum(L.c_plane_tests), e = warp_sum(L.c_samples);
+        if (lane == 0) {
+            atomicAdd(&counters[0], (unsigned long long)a); atomicAdd(&counters[1], (unsigned long long)b);
+            atomicAdd(&counters[2], (unsigned long long)c); atomicAdd(&counters[3], (unsigned long long)d);
+            atomicAdd(&counters[4], (unsigned long long)e);
+        }
+    }
+}
+
+}  // namespace rtb
+
+// ------------------------------------------------------------------------------------------------ launchers
+using namespace rtb;
+
+template <typename K>
+static int blocks_per_sm(K kernel, int threads, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess) return 0;
+    return nb;
+}
+
+cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
+    const size_t geom_bytes = (size_t)p.frame.n * sizeof(f4);
+    const bool chunked = geom_bytes > (size_t)p.max_smem_geom;
+    int chunk = p.frame.n;
+    size_t smem = geom_bytes;
+    if (chunked) {
+        chunk = p.chunk_spheres;
+        smem = (size_t)chunk * sizeof(f4);
+    }
+    if (smem < 16) smem = 16;
+    typedef void (*kern_t)(PtFrame, Shard, uint32_t, float *, uint32_t *, uint32_t *, unsigned *, unsigned long long *, int);
+    kern_t k = chunked ? (p.count ? pt_kernel<true, true> : pt_kernel<false, true>)
+                       : (p.count ? pt_kernel<true, false> : pt_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int nb = blocks_per_sm(k, PT_THREADS, smem);
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    if (p.max_blocks_per_sm > 0 && nb > p.max_blocks_per_sm) nb = p.max_blocks_per_sm;
+    long grid = (long)nb * p.sm_count;
+    const long need = ((long)p.n_items + PT_THREADS - 1) / PT_THREADS;
+    if (grid > need) grid = need > 0 ? need : 1;
+    k<<<(unsigned)grid, PT_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, p.colors, p.seeds, p.pixels,
+                                                   p.work_counter, p.counters, chunk);
+    return cudaGetLastError();
+}
+
+cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream) {
+    pt_resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(colors, pixels, w, h, inv_total);
+    return cudaGetLastError();
+}
+
+size_t rtk_whitted_smem_bytes(int n, int n_lights, int stage_materials) {
+    size_t b = (size_t)n * (sizeof(f4) + sizeof(int));
+    if (stage_materials) b += (size_t)n * (2 * sizeof(f4) + sizeof(float)) + (size_t)n_lights * sizeof(int);
+    return b < 16 ? 16 : b;
+}
+
+cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
+    const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.stage_materials);
+    typedef void (*kern_t)(WFrame, Shard, uint32_t, uint32_t *, unsigned *, unsigned long long *, int);
+    kern_t k = p.count ? whitted_kernel<true> : whitted_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int nb = blocks_per_sm(k, W_THREADS, smem);
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    if (p.max_blocks_per_sm > 0 && nb > p.max_blocks_per_sm) nb = p.max_blocks_per_sm;
+    long grid = (long)nb * p.sm_count;
+    const long need = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
+    if (grid > need) grid = need > 0 ? need : 1;
+    k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, p.pixels, p.work_counter, p.counters,
+                                                  p.stage_materials);
+    return cudaGetLastError();
+}

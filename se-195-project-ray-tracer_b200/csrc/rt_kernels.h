@@ -1,0 +1,36 @@
+// rt_kernels.h -- launch descriptors shared by rt_kernels.cu (device) and rt_api.cu (C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pt_lane.cuh"
+#include "whitted_lane.cuh"
+
+#define PT_THREADS 256
+#define W_THREADS 128
+
+struct PtLaunch {
+    rtb::PtFrame frame;
+    rtb::Shard shard;
+    uint32_t n_items;
+    float *colors; uint32_t *seeds; uint32_t *pixels;
+    unsigned *work_counter; unsigned long long *counters;
+    int count;                  // 1: counting build of the kernel
+    int sm_count;
+    int max_smem_geom;          // (p, rad^2) arrays larger than this many bytes are streamed in chunks
+    int chunk_spheres;          // spheres per chunk in that case
+    int max_blocks_per_sm;      // 0 = whatever fits
+};
+
+struct WLaunch {
+    rtb::WFrame frame;
+    rtb::Shard shard;
+    uint32_t n_items;
+    uint32_t *pixels;
+    unsigned *work_counter; unsigned long long *counters;
+    int count, sm_count, stage_materials, max_blocks_per_sm;
+};
+
+cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream);
+cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream);
+cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);
+size_t rtk_whitted_smem_bytes(int n, int n_lights, int stage_materials);

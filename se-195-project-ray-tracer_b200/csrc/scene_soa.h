@@ -1,0 +1,86 @@
+// scene_soa.h -- host-side conversion of the reference's array-of-structs scene tables into the
+// structure-of-arrays float4 layout the kernels stage into shared memory.  Pure host C++.
+#pragma once
+#include <vector>
+#include <stdint.h>
+#include <string.h>
+#include "../../include/rt_b200.h"
+#include "pt_lane.cuh"
+#include "whitted_lane.cuh"
+
+namespace rtb {
+
+static_assert(sizeof(rt_sphere) == 44, "rt_sphere must match the reference Sphere (SPT/geom.h:43-47)");
+static_assert(sizeof(rt_camera) == 60, "rt_camera must match the reference Camera (SPT/camera.h:29-34)");
+static_assert(sizeof(rt_primitive) == 96, "rt_primitive must match the reference Primitive_2 (R323/common.h:49-63)");
+static_assert(sizeof(rt_uchar4) == 4 && sizeof(rt_float4) == 16 && sizeof(f4) == 16, "vector PODs");
+
+struct PtSoA {
+    std::vector<f4> geom, emis, colr;
+    std::vector<int> lights;
+};
+
+inline void build_pt_soa(const rt_sphere *s, uint32_t n, PtSoA &out) {
+    out.geom.resize(n); out.emis.resize(n); out.colr.resize(n); out.lights.clear();
+    for (uint32_t i = 0; i < n; i++) {
+        const float rad2 = s[i].rad * s[i].rad;                 // `s->rad * s->rad`, SPT/geomfunc.h:42 (one rounding)
+        f4 g = { s[i].p.x, s[i].p.y, s[i].p.z, rad2 };
+        uint32_t refl_bits = (uint32_t)s[i].refl; float refl_as_float; memcpy(&refl_as_float, &refl_bits, 4);
+        f4 e = { s[i].e.x, s[i].e.y, s[i].e.z, refl_as_float };
+        f4 c = { s[i].c.x, s[i].c.y, s[i].c.z, s[i].rad };
+        out.geom[i] = g; out.emis[i] = e; out.colr[i] = c;
+        // viszero() of SPT/vec.h:44 tests x, x and z -- never y.  Reproduced.
+        if (!(s[i].e.x == 0.f && s[i].e.z == 0.f)) out.lights.push_back((int)i);
+    }
+}
+
+struct WSoA {
+    std::vector<f4> geom, mat_a, mat_b;
+    std::vector<int> flags, lights;
+    std::vector<float> rrad;
+    int n_spheres = 0, n_planes = 0;
+};
+
+inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
+    out.geom.resize(n); out.mat_a.resize(n); out.mat_b.resize(n); out.flags.resize(n); out.rrad.resize(n);
+    out.lights.clear(); out.n_spheres = out.n_planes = 0;
+    for (int i = 0; i < n; i++) {
+        int fl = 0;
+        f4 g;
+        if (p[i].type == RT_SPHERE) {
+            fl |= W_FLAG_SPHERE; out.n_spheres++;
+            g.x = p[i].center.x; g.y = p[i].center.y; g.z = p[i].center.z; g.w = p[i].sq_radius;
+        } else if (p[i].type == RT_PLANE) {
+            out.n_planes++;
+            g.x = p[i].normal.x; g.y = p[i].normal.y; g.z = p[i].normal.z; g.w = p[i].depth;
+        } else {                       // intersect() returns MISS for any other type (RNO:150-160): a plane that is never hit
+            g.x = g.y = g.z = g.w = 0.f;
+        }
+        if (p[i].is_light) { fl |= W_FLAG_LIGHT; out.lights.push_back(i); }
+        f4 a = { p[i].m_color.x, p[i].m_color.y, p[i].m_color.z, p[i].m_refl };
+        f4 b = { p[i].m_diff, p[i].m_refr, p[i].m_refr_index, p[i].m_spec };
+        out.geom[i] = g; out.mat_a[i] = a; out.mat_b[i] = b; out.flags[i] = fl; out.rrad[i] = p[i].r_radius;
+    }
+}
+
+// Rows of an h-row frame owned by `rank` when tiles of tile_rows rows are dealt round-robin.
+inline int shard_local_rows(int h, int rank, int world, int tile_rows) {
+    int rows = 0;
+    for (int t = rank; t * tile_rows < h; t += world) {
+        const int r = h - t * tile_rows;
+        rows += r < tile_rows ? r : tile_rows;
+    }
+    return rows;
+}
+
+inline Shard make_shard(int w, int h, int rank, int world, int tile_rows, uint32_t *n_items) {
+    Shard s;
+    s.rank = rank; s.world = world; s.tile_rows = tile_rows;
+    s.local_rows = shard_local_rows(h, rank, world, tile_rows);
+    s.blocks_x = (w + 7) / 8;
+    const int blocks_y = (s.local_rows + 3) / 4;
+    *n_items = (uint32_t)s.blocks_x * (uint32_t)blocks_y * 32u;
+    return s;
+}
+
+}  // namespace rtb

@@ -1,0 +1,295 @@
+// whitted_lane.cuh -- per-lane state machine of the Whitted tracer (host/device).
+//
+// Follows R323/raytracer_non_OpenCL.c ("RNO:") -- the CPU twin of R323/raytracer_kernel.cl that
+// release 3.2.03 actually runs and whose output is the golden test.bmp.  One lane owns one pixel:
+// nine sub-samples in the reference's order (tx outer, ty inner), each expanded breadth-first
+// through a FIFO of secondary rays (RNO:30-40, 330-433), because the float accumulation order
+// inside a pixel is part of the result.  As in pt_lane.cuh the control flow is cut into RAY QUERIES:
+// a nearest-hit query over all primitives (RNO:185-193) or a hard-shadow query over the non-light
+// primitives that stops at the first blocker (RNO:232-240).  w_advance() runs everything between two
+// queries: shading, accumulation, spawning of the reflected / refracted children, next sub-sample.
+#pragma once
+#include "rt_math.cuh"
+#include "pt_lane.cuh"   // f4, PH_*, Shard
+
+namespace rtb {
+
+#define W_EPS 0.001f             /* RNO:26 */
+#define W_FAR 10000000.0f        /* RNO:181 */
+#define W_TRACEDEPTH 5           /* RNO:4   */
+#define W_QUEUE_SLOTS 32         /* a breadth-first queue over a depth-5 binary ray tree never holds more */
+#define W_FLAG_SPHERE 1
+#define W_FLAG_LIGHT 2
+enum { W_PRIMARY = 0, W_REFLECTED = 1, W_REFRACTED = 2 };   /* RNO:59-63 */
+
+// Scene in structure-of-arrays form (built once per frame from the 96-byte Primitive_2 records):
+//   geom[i]  sphere: (center.xyz, sq_radius)   plane: (normal.xyz, depth)    <- all a test reads
+//   flags[i] bit0 = sphere, bit1 = is_light
+//   mat_a[i] (color.xyz, refl)     mat_b[i] (diff, refr, refr_index, spec)    rrad[i] = r_radius
+struct WFrame {
+    const f4 *geom, *mat_a, *mat_b;
+    const int *flags, *lights;
+    const float *rrad;
+    int n, n_lights, n_spheres, n_planes;
+    int w, h;
+    float DX, DY;               // (WX2-WX1)/w, (WY2-WY1)/h computed on the host exactly as RNO:295-296
+    int32_t *hit_ids;           // NULL or int[w*h*9]
+};
+
+struct WLane {
+    int x, y, sub;
+    float ar, ag, ab;                               // pixel accumulator
+    int head, tail;                                 // FIFO cursors of the current sub-sample
+    float dx, dy, dz;                               // direction of the ray being processed
+    float weight, r_index, tr, tg, tb;              // its weight, medium index, transparency
+    int depth, kind, from;
+    float qox, qoy, qoz, qdx, qdy, qdz;             // ray of the query in flight
+    float cumu;                                     // nearest distance so far / distance to the light
+    int qhit, qkind;                                // nearest: primitive + HIT(1)/INPRIM(-1); shadow: qhit = blocked
+    float dist; int hit, hkind;                     // result of the nearest query while lights are processed
+    float px, py, pz;                               // intersection point
+    float cr, cg, cb;                               // colour gathered for this ray
+    int li, phase;
+    uint32_t c_nearest, c_shadow, c_samples;
+    uint64_t c_sphere_tests, c_plane_tests;
+};
+
+// plane_intersect RNO:95-109 / sphere_intersect RNO:111-148 against the lane's query ray.
+// Return HIT(1) / INPRIM(-1) / MISS(0) and shrink L.cumu on a hit.
+RT_HD int w_plane(WLane &L, const f4 g) {
+    const float d = dot3(g.x, g.y, g.z, L.qdx, L.qdy, L.qdz);
+    if (d != 0.f) {
+        const float dist = f_div(-f_add(dot3(g.x, g.y, g.z, L.qox, L.qoy, L.qoz), g.w), d);
+        if (dist > 0.f && dist < L.cumu) { L.cumu = dist; return 1; }
+    }
+    return 0;
+}
+RT_HD int w_sphere(WLane &L, const f4 g) {
+    const float vx = f_sub(L.qox, g.x), vy = f_sub(L.qoy, g.y), vz = f_sub(L.qoz, g.z);
+    const float b = -dot3(vx, vy, vz, L.qdx, L.qdy, L.qdz);
+    float det = f_add(f_sub(f_mul(b, b), dot3(vx, vy, vz, vx, vy, vz)), g.w);
+    if (det > 0.f) {
+        det = f_sqrt(det);
+        const float i1 = f_sub(b, det), i2 = f_add(b, det);
+        if (i2 > 0.f) {
+            if (i1 < 0.f) { if (i2 < L.cumu) { L.cumu = i2; return -1; } }
+            else if (i1 < L.cumu) { L.cumu = i1; return 1; }
+        }
+    }
+    return 0;
+}
+
+// One primitive against the lane's query; returns true when a shadow query found its blocker.
+// Ascending index + strict '<' => the lowest index keeps an exact tie (RNO:185-193).
+template <bool COUNT>
+RT_HD bool w_test(WLane &L, const f4 g, int flag, int i) {
+    if (L.phase == PH_SHADOW && (flag & W_FLAG_LIGHT)) return false;     // RNO:234: lights cast no shadow
+    int k;
+    if (flag & W_FLAG_SPHERE) { if (COUNT && L.phase == PH_SHADOW) L.c_sphere_tests++; k = w_sphere(L, g); }
+    else                      { if (COUNT && L.phase == PH_SHADOW) L.c_plane_tests++;  k = w_plane(L, g); }
+    if (k) {
+        if (L.phase == PH_NEAREST) { L.qhit = i; L.qkind = k; }
+        else { L.qhit = 1; return true; }
+    }
+    return false;
+}
+
+RT_HD void w_normal(const WFrame &F, int prim, float px, float py, float pz, float &nx, float &ny, float &nz) {   // RNO:162-177
+    const f4 g = F.geom[prim];
+    if (F.flags[prim] & W_FLAG_SPHERE) {
+        const float rr = F.rrad[prim];
+        nx = f_mul(f_sub(px, g.x), rr); ny = f_mul(f_sub(py, g.y), rr); nz = f_mul(f_sub(pz, g.z), rr);
+    } else { nx = g.x; ny = g.y; nz = g.z; }
+}
+
+RT_HD void w_set_nearest_query(WLane &L, float ox, float oy, float oz) {
+    L.qox = ox; L.qoy = oy; L.qoz = oz; L.qdx = L.dx; L.qdy = L.dy; L.qdz = L.dz;
+    L.cumu = W_FAR; L.qhit = -1; L.qkind = 0; L.phase = PH_NEAREST;
+}
+
+// Primary ray of sub-sample L.sub: RNO:299-328.
+RT_HD void w_start_subsample(WLane &L, const WFrame &F) {
+    const int tx = L.sub / 3 - 1, ty = L.sub % 3 - 1;
+    const float SY = f_add(2.25f, f_mul((float)L.y, F.DY));
+    const float SX = f_add(-3.0f, f_mul((float)L.x, F.DX));
+    float dx = f_sub(f_add(SX, f_mul(F.DX, f_div((float)tx, 2.0f))), 0.f);
+    float dy = f_sub(f_add(SY, f_mul(F.DY, f_div((float)ty, 2.0f))), 0.25f);
+    float dz = f_sub(0.f, -7.0f);
+    const float len = f_div(1.0f, f_sqrt(f_add(f_add(f_mul(dx, dx), f_mul(dy, dy)), f_mul(dz, dz))));
+    L.dx = f_mul(dx, len); L.dy = f_mul(dy, len); L.dz = f_mul(dz, len);
+    L.weight = 1.0f; L.depth = 0; L.from = -1; L.kind = W_PRIMARY; L.r_index = 1.0f;
+    L.tr = L.tg = L.tb = 1.0f;
+    L.head = L.tail = 0;
+    w_set_nearest_query(L, 0.f, 0.25f, -7.0f);
+}
+
+RT_HD void w_begin_pixel(WLane &L, const WFrame &F, int x, int y) {
+    L.x = x; L.y = y; L.sub = 0; L.ar = L.ag = L.ab = 0.f;
+    w_start_subsample(L, F);
+}
+
+// FIFO record: 12 words = three f4.
+RT_HD void w_push(f4 *q, WLane &L, float ox, float oy, float oz, float dx, float dy, float dz,
+                  float weight, float r_index, float tr, float tg, float tb, int depth, int kind, int from) {
+    f4 *slot = q + 3 * (L.tail & (W_QUEUE_SLOTS - 1));
+    L.tail++;
+    f4 a = { ox, oy, oz, dx }, b = { dy, dz, weight, r_index }, c = { tr, tg, tb, bits_f((uint32_t)(depth | (kind << 4) | ((from + 1) << 8))) };
+    slot[0] = a; slot[1] = b; slot[2] = c;
+}
+RT_HD void w_pop(const f4 *q, WLane &L) {
+    const f4 *slot = q + 3 * (L.head & (W_QUEUE_SLOTS - 1));
+    L.head++;
+    const f4 a = slot[0], b = slot[1], c = slot[2];
+    L.dx = a.w; L.dy = b.x; L.dz = b.y; L.weight = b.z; L.r_index = b.w;
+    L.tr = c.x; L.tg = c.y; L.tb = c.z;
+    const uint32_t pk = f_bits(c.w);
+    L.depth = (int)(pk & 15u); L.kind = (int)((pk >> 4) & 15u); L.from = (int)(pk >> 8) - 1;
+    w_set_nearest_query(L, a.x, a.y, a.z);
+}
+
+// Diffuse + specular contribution of light `l` (RNO:242-276); Lx.. is the unit vector to the light.
+RT_HD void w_shade(WLane &L, const WFrame &F, int l, float Lx, float Ly, float Lz, float lit) {
+    const f4 ma = F.mat_a[L.hit], mb = F.mat_b[L.hit], lc = F.mat_a[l];
+    float nx, ny, nz;
+    w_normal(F, L.hit, L.px, L.py, L.pz, nx, ny, nz);
+    if (mb.x > 0.f) {
+        const float nl = dot3(nx, ny, nz, Lx, Ly, Lz);
+        if (nl > 0.f) {
+            const float k = f_mul(f_mul(nl, mb.x), lit);
+            L.cr = f_add(L.cr, f_mul(f_mul(k, ma.x), lc.x));
+            L.cg = f_add(L.cg, f_mul(f_mul(k, ma.y), lc.y));
+            L.cb = f_add(L.cb, f_mul(f_mul(k, ma.z), lc.z));
+        }
+    }
+    if (mb.w > 0.f) {
+        const float ln = dot3(Lx, Ly, Lz, nx, ny, nz);
+        const float k2 = f_mul(2.0f, ln);
+        const float rx = f_sub(Lx, f_mul(k2, nx)), ry = f_sub(Ly, f_mul(k2, ny)), rz = f_sub(Lz, f_mul(k2, nz));
+        const float vr = dot3(L.dx, L.dy, L.dz, rx, ry, rz);
+        if (vr > 0.f) {
+            // pow(float,int) binds to the double overload in the reference's C++ build; the product with
+            // m_spec and shade stays in double and is rounded to float once (RNO:270).
+            const float k = (float)d_mul(d_mul(pow20_double(vr), (double)mb.w), (double)lit);
+            L.cr = f_add(L.cr, f_mul(k, lc.x));
+            L.cg = f_add(L.cg, f_mul(k, lc.y));
+            L.cb = f_add(L.cb, f_mul(k, lc.z));
+        }
+    }
+}
+
+// Runs everything between two queries.  Returns true when the pixel is finished (L.ar/ag/ab final).
+template <bool COUNT>
+RT_HD bool w_advance(WLane &L, const WFrame &F, f4 *q) {
+    bool to_lights;
+    if (L.phase == PH_NEAREST) {
+        if (COUNT) { L.c_nearest++; L.c_sphere_tests += (uint32_t)F.n_spheres; L.c_plane_tests += (uint32_t)F.n_planes; }
+        L.dist = L.cumu; L.hit = L.qhit; L.hkind = L.qkind;
+        L.cr = L.cg = L.cb = 0.f;
+        to_lights = false;
+        if (L.hit >= 0) {
+            if (F.flags[L.hit] & W_FLAG_LIGHT) {                       // RNO:197-200
+                const f4 ma = F.mat_a[L.hit];
+                L.cr = ma.x; L.cg = ma.y; L.cb = ma.z;
+            } else {
+                L.px = f_add(L.qox, f_mul(L.qdx, L.dist));
+                L.py = f_add(L.qoy, f_mul(L.qdy, L.dist));
+                L.pz = f_add(L.qoz, f_mul(L.qdz, L.dist));
+                L.li = 0;
+                to_lights = true;
+            }
+        }
+    } else {                                                           // shadow query finished
+        if (COUNT) L.c_shadow++;
+        if (!L.qhit) w_shade(L, F, F.lights[L.li], L.qdx, L.qdy, L.qdz, 1.0f);   // a blocked light adds exactly 0
+        L.li++;
+        to_lights = true;
+    }
+
+    if (to_lights) {
+        for (; L.li < F.n_lights; L.li++) {                            // RNO:206-277
+            const int l = F.lights[L.li];
+            const f4 lg = F.geom[l];
+            const float ex = f_sub(lg.x, L.px), ey = f_sub(lg.y, L.py), ez = f_sub(lg.z, L.pz);
+            const float reach = f_sqrt(f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(ez, ez)));
+            const float inv = f_div(1.0f, reach);
+            const float Lx = f_mul(inv, ex), Ly = f_mul(inv, ey), Lz = f_mul(inv, ez);
+            if (F.flags[l] & W_FLAG_SPHERE) {                          // only sphere lights cast shadows (RNO:223)
+                L.qox = f_add(L.px, f_mul(Lx, W_EPS)); L.qoy = f_add(L.py, f_mul(Ly, W_EPS)); L.qoz = f_add(L.pz, f_mul(Lz, W_EPS));
+                L.qdx = Lx; L.qdy = Ly; L.qdz = Lz;
+                L.cumu = reach; L.qhit = 0; L.phase = PH_SHADOW;
+                return false;
+            }
+            w_shade(L, F, l, Lx, Ly, Lz, 1.0f);
+        }
+    }
+
+    // The ray is finished: fold its colour into the pixel (RNO:351-368).
+    if (L.kind == W_PRIMARY) {
+        if (COUNT) L.c_samples++;
+        if (F.hit_ids) F.hit_ids[((size_t)L.y * F.w + L.x) * 9 + L.sub] = L.hit;
+        L.ar = f_add(L.ar, f_mul(L.cr, L.weight));
+        L.ag = f_add(L.ag, f_mul(L.cg, L.weight));
+        L.ab = f_add(L.ab, f_mul(L.cb, L.weight));
+    } else if (L.kind == W_REFLECTED) {
+        const f4 fa = F.mat_a[L.from];
+        L.ar = f_add(L.ar, f_mul(f_mul(f_mul(L.cr, L.weight), fa.x), L.tr));
+        L.ag = f_add(L.ag, f_mul(f_mul(f_mul(L.cg, L.weight), fa.y), L.tg));
+        L.ab = f_add(L.ab, f_mul(f_mul(f_mul(L.cb, L.weight), fa.z), L.tb));
+    } else {
+        L.ar = f_add(L.ar, f_mul(f_mul(L.cr, L.weight), L.tr));
+        L.ag = f_add(L.ag, f_mul(f_mul(L.cg, L.weight), L.tg));
+        L.ab = f_add(L.ab, f_mul(f_mul(L.cb, L.weight), L.tb));
+    }
+    // Children (RNO:370-432).  A miss spawns nothing (the reference reads prims[-1] there; its shipped
+    // scenes are closed boxes, so it never happens -- SURVEY.md 2.3).
+    if (L.hit >= 0 && L.depth < W_TRACEDEPTH) {
+        const f4 ma = F.mat_a[L.hit], mb = F.mat_b[L.hit];
+        if (ma.w > 0.0f) {                                             // reflection
+            float nx, ny, nz;
+            w_normal(F, L.hit, L.px, L.py, L.pz, nx, ny, nz);
+            const float k2 = f_mul(2.0f, dot3(L.dx, L.dy, L.dz, nx, ny, nz));
+            const float rx = f_sub(L.dx, f_mul(k2, nx)), ry = f_sub(L.dy, f_mul(k2, ny)), rz = f_sub(L.dz, f_mul(k2, nz));
+            w_push(q, L, f_add(L.px, f_mul(rx, W_EPS)), f_add(L.py, f_mul(ry, W_EPS)), f_add(L.pz, f_mul(rz, W_EPS)), rx, ry, rz,
+                   f_mul(ma.w, L.weight), L.r_index, L.tr, L.tg, L.tb, L.depth + 1, W_REFLECTED, L.hit);
+        }
+        if (mb.y > 0.0f) {                                             // refraction
+            const float m_rindex = mb.z;
+            const float nn = f_div(L.r_index, m_rindex);
+            float gx, gy, gz;
+            w_normal(F, L.hit, L.px, L.py, L.pz, gx, gy, gz);
+            const float sgn = (float)L.hkind;
+            const float nx = f_mul(gx, sgn), ny = f_mul(gy, sgn), nz = f_mul(gz, sgn);
+            const float cosI = -dot3(nx, ny, nz, L.dx, L.dy, L.dz);
+            const float cosT2 = f_sub(1.0f, f_mul(f_mul(nn, nn), f_sub(1.0f, f_mul(cosI, cosI))));
+            if (cosT2 > 0.0f) {
+                const float kk = f_sub(f_mul(nn, cosI), f_sqrt(cosT2));
+                const float tx = f_add(f_mul(nn, L.dx), f_mul(kk, nx));
+                const float ty = f_add(f_mul(nn, L.dy), f_mul(kk, ny));
+                const float tz = f_add(f_mul(nn, L.dz), f_mul(kk, nz));
+                const float nd = -L.dist;
+                w_push(q, L, f_add(L.px, f_mul(tx, W_EPS)), f_add(L.py, f_mul(ty, W_EPS)), f_add(L.pz, f_mul(tz, W_EPS)), tx, ty, tz,
+                       L.weight, m_rindex,
+                       f_mul(L.tr, expf_glibc(f_mul(f_mul(ma.x, 0.15f), nd))),     // Beer's law, RNO:424-426
+                       f_mul(L.tg, expf_glibc(f_mul(f_mul(ma.y, 0.15f), nd))),
+                       f_mul(L.tb, expf_glibc(f_mul(f_mul(ma.z, 0.15f), nd))),
+                       L.depth + 1, W_REFRACTED, L.hit);
+            }
+        }
+    }
+    if (L.head < L.tail) { w_pop(q, L); return false; }
+    L.sub++;
+    if (L.sub < 9) { w_start_subsample(L, F); return false; }
+    L.phase = PH_IDLE;
+    return true;
+}
+
+// RNO:436-447: min(255, (int)(acc * (256/9))), alpha 0.
+RT_HD uint32_t w_pack_pixel(float r, float g, float b) {
+    int ir = (int)f_mul(r, 28.0f), ig = (int)f_mul(g, 28.0f), ib = (int)f_mul(b, 28.0f);
+    if (ir > 255) ir = 255;
+    if (ig > 255) ig = 255;
+    if (ib > 255) ib = 255;
+    return (uint32_t)(ir & 255) | ((uint32_t)(ig & 255) << 8) | ((uint32_t)(ib & 255) << 16);
+}
+
+}  // namespace rtb

@@ -1,0 +1,110 @@
+// tests/devsim/devsim.cpp -- TEST-ONLY host build of the device lane code.
+//
+// Compiles the very headers the CUDA kernels are made of (rt_math.cuh, pt_lane.cuh, whitted_lane.cuh,
+// scene_soa.h) with g++ and drives one lane at a time through "query, then advance" -- the loop body
+// of the kernels in csrc/rt_kernels.cu -- so that the per-lane state machines, the work-item -> pixel
+// mapping and the FP64 replicas of glibc's float functions can be checked against the oracle on a
+// machine without a GPU.  It is not part of librt_b200.so, is never loaded by the product, and is not
+// a fallback: the product has none (rt_init fails without a CUDA device).
+#include <vector>
+#include <stdint.h>
+#include <string.h>
+#include "../../se-195-project-ray-tracer_b200/csrc/scene_soa.h"
+
+using namespace rtb;
+
+extern "C" {
+
+void devsim_sincos(const float *in, float *sin_out, float *cos_out, long n) {
+    for (long i = 0; i < n; i++) sincos_glibc(in[i], &sin_out[i], &cos_out[i]);
+}
+void devsim_expf(const float *in, float *out, long n) { for (long i = 0; i < n; i++) out[i] = expf_glibc(in[i]); }
+void devsim_to_int_gamma(const float *in, int *out, long n) { for (long i = 0; i < n; i++) out[i] = to_int_gamma(in[i]); }
+double devsim_pow20(float v) { return pow20_double(v); }
+float devsim_get_random(uint32_t *s0, uint32_t *s1) { return get_random(*s0, *s1); }
+
+// Item -> pixel coverage: marks every pixel that (rank, world, tile_rows) visits; returns the item count.
+uint32_t devsim_cover(int w, int h, int rank, int world, int tile_rows, int32_t *visits /* w*h, incremented */) {
+    uint32_t n_items;
+    Shard S = make_shard(w, h, rank, world, tile_rows, &n_items);
+    for (uint32_t it = 0; it < n_items; it++) {
+        int x, y;
+        if (item_to_pixel(S, w, it, x, y)) visits[(size_t)y * w + x]++;
+    }
+    return n_items;
+}
+
+// Whitted frame through the lane state machine (rows owned by rank/world/tile_rows only).
+void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_primitive *prims, int n,
+                    int rank, int world, int tile_rows, uint64_t *counters5) {
+    WSoA soa;
+    build_w_soa(prims, n, soa);
+    WFrame F;
+    F.geom = soa.geom.data(); F.mat_a = soa.mat_a.data(); F.mat_b = soa.mat_b.data();
+    F.flags = soa.flags.data(); F.lights = soa.lights.data(); F.rrad = soa.rrad.data();
+    F.n = n; F.n_lights = (int)soa.lights.size(); F.n_spheres = soa.n_spheres; F.n_planes = soa.n_planes;
+    F.w = w; F.h = h;
+    const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
+    F.DX = (WX2 - WX1) / w; F.DY = (WY2 - WY1) / h;
+    F.hit_ids = hit_ids;
+    uint32_t n_items;
+    Shard S = make_shard(w, h, rank, world, tile_rows, &n_items);
+    f4 queue[3 * W_QUEUE_SLOTS];
+    uint64_t c[5] = {0, 0, 0, 0, 0};
+    for (uint32_t it = 0; it < n_items; it++) {
+        int x, y;
+        if (!item_to_pixel(S, w, it, x, y)) continue;
+        WLane L;
+        memset(&L, 0, sizeof L);
+        w_begin_pixel(L, F, x, y);
+        for (;;) {
+            bool done = false;
+            for (int s = 0; s < F.n && !done; ++s) done = w_test<true>(L, F.geom[s], F.flags[s], s);
+            if (w_advance<true>(L, F, queue)) break;
+        }
+        const uint32_t p = w_pack_pixel(L.ar, L.ag, L.ab);
+        memcpy(pixels + ((size_t)y * w + x) * 4, &p, 4);
+        c[0] += L.c_nearest; c[1] += L.c_shadow; c[2] += L.c_sphere_tests; c[3] += L.c_plane_tests; c[4] += L.c_samples;
+    }
+    if (counters5) for (int k = 0; k < 5; k++) counters5[k] += c[k];
+}
+
+// smallpt passes through the lane state machine.  colors/seeds updated in place (CPU-twin indexing).
+void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera *cam, int w, int h,
+               int pass0, int n_passes, int sum_mode, float *colors, uint32_t *seeds, uint32_t *pixels,
+               int rank, int world, int tile_rows, uint64_t *counters5) {
+    PtSoA soa;
+    build_pt_soa(sph, n, soa);
+    PtFrame F;
+    F.emis = soa.emis.data(); F.colr = soa.colr.data(); F.geom_global = soa.geom.data(); F.lights = soa.lights.data();
+    F.n = (int)n; F.n_lights = (int)soa.lights.size();
+    F.cam_ox = cam->orig.x; F.cam_oy = cam->orig.y; F.cam_oz = cam->orig.z;
+    F.cam_dx = cam->dir.x; F.cam_dy = cam->dir.y; F.cam_dz = cam->dir.z;
+    F.cam_xx = cam->x.x; F.cam_xy = cam->x.y; F.cam_xz = cam->x.z;
+    F.cam_yx = cam->y.x; F.cam_yy = cam->y.y; F.cam_yz = cam->y.z;
+    F.w = w; F.h = h; F.inv_w = 1.f / w; F.inv_h = 1.f / h;
+    F.pass0 = pass0; F.n_passes = n_passes; F.direct_only = integrator; F.sum_mode = sum_mode;
+    uint32_t n_items;
+    Shard S = make_shard(w, h, rank, world, tile_rows, &n_items);
+    uint64_t c[5] = {0, 0, 0, 0, 0};
+    for (uint32_t it = 0; it < n_items; it++) {
+        int x, y;
+        if (!item_to_pixel(S, w, it, x, y)) continue;
+        PtLane L;
+        memset(&L, 0, sizeof L);
+        pt_begin_pixel(L, F, x, y, colors, seeds);
+        for (;;) {
+            bool done = false;
+            for (int i = F.n - 1; i >= 0 && !done; --i) done = pt_test<true>(L, soa.geom[i], i);
+            if (pt_advance<true>(L, F)) break;
+        }
+        const size_t i = (size_t)(h - y - 1) * w + x;
+        colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
+        seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
+        if (!sum_mode && pixels) pixels[(size_t)y * w + x] = pt_pack_pixel(L.cr, L.cg, L.cb);
+        c[0] += L.c_nearest; c[1] += L.c_shadow; c[2] += L.c_tests; c[4] += L.c_samples;
+    }
+    if (counters5) for (int k = 0; k < 5; k++) counters5[k] += c[k];
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""The device lane code (csrc/*.cuh), compiled for the host by tests/devsim, against the oracle.
+CPU only.  This checks the state machines the CUDA kernels are built from -- not the product path;
+the GPU parity tests (test_gpu_parity.py) are the ones that call librt_b200.so."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import vp, load_smallpt_golden
+
+
+def test_sincos_bit_exact_on_the_whole_input_domain(devsim, orc):
+    """Every argument the path can pass to sin/cos is 2*pi*GetRandom(): 2^23 values.  All of them."""
+    i = np.arange(1 << 23, dtype=np.uint32)
+    u = ((i | 0x40000000).view(np.float32) - np.float32(2)) / np.float32(2)
+    a = (np.float32(2.0) * np.float32(3.14159265358979323846) * u).astype(np.float32)
+    s, c, s2, c2 = (np.zeros_like(a) for _ in range(4))
+    devsim.devsim_sincos(vp(a), vp(s), vp(c), ctypes.c_long(a.size))
+    orc.oracle_libm_sincosf(vp(a), vp(s2), vp(c2), ctypes.c_long(a.size))
+    assert np.array_equal(s.view(np.uint32), s2.view(np.uint32))
+    assert np.array_equal(c.view(np.uint32), c2.view(np.uint32))
+
+
+def test_expf_and_gamma_match_host_libm(devsim, orc):
+    rs = np.random.RandomState(0)
+    x = np.concatenate([-(rs.rand(2_000_000) * 70), -np.logspace(-6, 2, 20000), [0.0, -0.0, -100, -104, -200]]).astype(np.float32)
+    a, b = np.zeros_like(x), np.zeros_like(x)
+    devsim.devsim_expf(vp(x), vp(a), ctypes.c_long(x.size))
+    orc.oracle_libm_expf(vp(x), vp(b), ctypes.c_long(x.size))
+    assert np.count_nonzero(a.view(np.uint32) != b.view(np.uint32)) <= 2     # documented: < 1e-8 of inputs may differ by 1 ulp
+    v = np.concatenate([rs.rand(2_000_000) * 1.2 - 0.1, np.logspace(-30, 0, 20000), [0, 1, 1e-40, 2, -1, 0.5]]).astype(np.float32)
+    g1, g2 = np.zeros(v.size, np.int32), np.zeros(v.size, np.int32)
+    devsim.devsim_to_int_gamma(vp(v), vp(g1), ctypes.c_long(v.size))
+    orc.oracle_libm_to_int_gamma(vp(v), vp(g2), ctypes.c_long(v.size))
+    assert np.array_equal(g1, g2)
+
+
+def test_pow20_close_to_libm_pow(devsim, orc):
+    for v in np.random.RandomState(1).rand(2000).astype(np.float32):
+        a, b = devsim.devsim_pow20(float(v)), orc.oracle_libm_pow20(float(v))
+        assert a == b or abs(a - b) <= 12 * np.spacing(b)
+
+
+def test_whitted_lanes_equal_oracle(devsim, orc, rt):
+    prims = rt.whitted_create_scene(0)
+    for (w, h) in [(120, 90), (37, 29)]:
+        px, hits, ctr = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32), np.zeros(5, np.uint64)
+        devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, vp(ctr))
+        px_o, hits_o, ctr_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32), np.zeros(5, np.uint64)
+        orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, vp(ctr_o))
+        assert np.array_equal(px, px_o) and np.array_equal(hits, hits_o)
+        assert list(ctr[:4]) == list(ctr_o[:4]) and ctr[4] == w * h * 9
+
+
+def test_whitted_lanes_sharded_equal_unsharded(devsim, rt):
+    prims = rt.whitted_create_scene(0)
+    w, h = 50, 41
+    full = np.zeros((h, w, 4), np.uint8)
+    devsim.devsim_whitted(vp(full), None, w, h, vp(prims), prims.size, 0, 1, 8, None)
+    parts = np.zeros((h, w, 4), np.uint8)
+    for rank in range(3):
+        devsim.devsim_whitted(vp(parts), None, w, h, vp(prims), prims.size, rank, 3, 4, None)
+    assert np.array_equal(full, parts)
+
+
+@pytest.mark.parametrize("scene", ["cornell", "caustic3", "simple", "complex"])
+def test_smallpt_lanes_equal_reference_fixture(devsim, rt, scene):
+    g = load_smallpt_golden(rt, scene)
+    w, h = g["w"], g["h"]
+    for integ, tag in [(0, "pt"), (1, "dl")]:
+        col, sd, pix = np.zeros(3 * w * h, np.float32), g["seeds_in"].copy(), np.zeros(w * h, np.uint32)
+        devsim.devsim_pt(integ, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, g["passes"], 0,
+                         vp(col), vp(sd), vp(pix), 0, 1, 8, None)
+        assert np.array_equal(col.view(np.uint32), g[tag + "_colors"]), (scene, tag)
+        assert np.array_equal(sd, g[tag + "_seeds"]) and np.array_equal(pix, g[tag + "_pixels"]), (scene, tag)
+
+
+def test_smallpt_lane_counters_equal_oracle(devsim, orc, rt):
+    g = load_smallpt_golden(rt, "cornell")
+    w, h = g["w"], g["h"]
+    col, sd, ctr = np.zeros(3 * w * h, np.float32), g["seeds_in"].copy(), np.zeros(5, np.uint64)
+    devsim.devsim_pt(0, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, 3, 0, vp(col), vp(sd), None, 0, 1, 8, vp(ctr))
+    col_o, sd_o, ctr_o = np.zeros(3 * w * h, np.float32), g["seeds_in"].copy(), np.zeros(4, np.uint64)
+    orc.oracle_pt_render(0, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, 3, vp(col_o), vp(sd_o), None, 2, vp(ctr_o))
+    assert (ctr[4], ctr[0], ctr[1], ctr[2]) == tuple(ctr_o)
