@@ -182,6 +182,10 @@ enum { RT_BUF_WHITTED_PIXELS = 0, RT_BUF_WHITTED_HITS = 1, RT_BUF_PT_PIXELS = 2,
 void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes);
 /* The context's cudaStream_t as an opaque pointer (for callers that order their own work after it). */
 void *rt_stream(rt_ctx *ctx);
+/* Makes the context issue all its work on a caller-owned cudaStream_t (e.g. torch's current stream, so
+ * that the caller's collectives and CUDA events are ordered with the render kernels).  The reference
+ * analogue is the single in-order cl_command_queue every call shares (SPT/smallptGPU.cpp:463-467). */
+int rt_set_stream(rt_ctx *ctx, void *cuda_stream);
 
 /* ------------------------------------------------------------------ host-side scene helpers
  * (kept from the reference's host code; pure CPU, no device needed) */

@@ -38,6 +38,7 @@ class Counters(C.Structure):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
 
 
+RT_DIFF_, RT_SPEC_, RT_REFR_ = 0, 1, 2
 RT_OK, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_ARG, RT_ERR_STATE, RT_ERR_CAPACITY, RT_ERR_IO = 0, -1, -2, -3, -4, -5, -6
 TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM = 0, 1, 2
 BUF_WHITTED_PIXELS, BUF_WHITTED_HITS, BUF_PT_PIXELS, BUF_PT_COLORS, BUF_PT_SEEDS = 0, 1, 2, 3, 4
@@ -72,6 +73,7 @@ SYMBOLS = {
     "rt_launch_count": (_U64, [_VP]),
     "rt_device_buffer": (_VP, [_VP, _I, C.POINTER(_U64)]),
     "rt_stream": (_VP, [_VP]),
+    "rt_set_stream": (_I, [_VP, _VP]),
     "rt_update_camera": (None, [_VP, _I, _I]),
     "rt_read_scene": (_I, [C.c_char_p, _VP, C.POINTER(_VP), C.POINTER(_U32)]),
     "rt_write_complex_scene": (_I, [C.c_char_p, _I]),
@@ -161,6 +163,27 @@ def write_ppm(path, pixels_u32):
         raise RtError(rc, f"cannot write {path}")
 
 
+def cornell_scene(w, h):
+    """The reference's built-in scene: CornellSpheres[] (SPT/scene.h:32-42) and the default camera of
+    mainGPU (SPT/smallptGPU.cpp:856-857), in float arithmetic like the C initialisers.  Bit-identical
+    to what ReadScene makes of SPT/scenes/cornell.scn (checked by tests/test_host_and_abi.py)."""
+    f = np.float32
+    W = f(1e4)
+    rows = [(W, (W + f(1), 40.8, 81.6), (0, 0, 0), (.75, .25, .25), RT_DIFF_), (W, (-W + f(99), 40.8, 81.6), (0, 0, 0), (.25, .25, .75), RT_DIFF_),
+            (W, (50, 40.8, W), (0, 0, 0), (.75, .75, .75), RT_DIFF_), (W, (50, 40.8, -W + f(270)), (0, 0, 0), (0, 0, 0), RT_DIFF_),
+            (W, (50, W, 81.6), (0, 0, 0), (.75, .75, .75), RT_DIFF_), (W, (50, -W + f(81.6), 81.6), (0, 0, 0), (.75, .75, .75), RT_DIFF_),
+            (16.5, (27, 16.5, 47), (0, 0, 0), (.9, .9, .9), RT_SPEC_), (16.5, (73, 16.5, 78), (0, 0, 0), (.9, .9, .9), RT_REFR_),
+            (7, (50, f(81.6) - f(15), 81.6), (12, 12, 12), (0, 0, 0), RT_DIFF_)]
+    spheres = np.zeros(len(rows), SPHERE_DTYPE)
+    for i, row in enumerate(rows):
+        spheres[i] = row
+    cam = np.zeros(1, CAMERA_DTYPE)
+    cam["orig"] = (50, 45, 205.6)
+    cam["target"] = (50, f(45) - f(0.042612), 204.6)
+    update_camera(cam, w, h)
+    return spheres, cam
+
+
 def reference_seeds(w, h, seed=1):
     """The reference's seed rule (SPT/smallptGPU.cpp:105-110): 2*w*h draws, each clamped to >= 2.
     The reference draws from libc rand(); the C ABI takes seeds as an INPUT, so any generator will do --
@@ -235,6 +258,10 @@ class Renderer:
 
     def launch_count(self):
         return int(self._lib.rt_launch_count(self._ctx))
+
+    def set_stream(self, cuda_stream_handle):
+        """Issue all work on the given cudaStream_t (an int, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self._lib.rt_set_stream(self._ctx, C.c_void_p(cuda_stream_handle)))
 
     def device_buffer(self, which):
         n = C.c_uint64()

@@ -38,7 +38,11 @@ struct rt_ctx {
     uint32_t *d_wpixels = nullptr;
     int32_t *d_whits = nullptr;
     size_t w_pixels_cap = 0, w_hits_cap = 0;
-    int w_scene_cap = 0;
+    size_t cap_wgeom = 0, cap_wma = 0, cap_wmb = 0, cap_wflags = 0, cap_wlights = 0, cap_wrrad = 0;
+    size_t cap_pgeom = 0, cap_pemis = 0, cap_pcolr = 0, cap_plights = 0;
+    WSoA w_soa;                                    // host staging of the last uploaded scenes (kept alive
+    PtSoA p_soa;                                   //  until the asynchronous copies have been issued and synced)
+    bool own_stream = true;
     // path tracer
     int p_w = 0, p_h = 0, p_n = 0, p_nl = 0;
     float *d_colors = nullptr;
@@ -66,14 +70,19 @@ static int fail(rt_ctx *c, int code, const char *fmt, ...) {
             return fail(ctx, RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Uploads v into *dptr, growing the allocation only when the capacity (in elements) is too small, so
+// that re-uploading a scene of the same size costs copies only (no cudaMalloc / cudaFree).
 template <typename T>
-static cudaError_t upload_vec(T **dptr, const std::vector<T> &v, cudaStream_t s) {
-    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
-    const size_t bytes = (v.size() ? v.size() : 1) * sizeof(T);
-    cudaError_t e = cudaMalloc((void **)dptr, bytes);
-    if (e != cudaSuccess) return e;
-    if (v.size()) e = cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-    return e;
+static cudaError_t upload_vec(T **dptr, size_t *cap, const std::vector<T> &v, cudaStream_t s) {
+    const size_t need = v.size() ? v.size() : 1;
+    if (!*dptr || *cap < need) {
+        if (*dptr) { cudaFree(*dptr); *dptr = nullptr; *cap = 0; }
+        cudaError_t e = cudaMalloc((void **)dptr, need * sizeof(T));
+        if (e != cudaSuccess) return e;
+        *cap = need;
+    }
+    if (v.size()) return cudaMemcpyAsync(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    return cudaSuccess;
 }
 
 extern "C" {
@@ -123,7 +132,7 @@ void rt_destroy(rt_ctx *ctx) {
     for (void *b : bufs) if (b) cudaFree(b);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -178,16 +187,16 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     if (!ctx) return RT_ERR_ARG;
     if (!prims || n < 1 || w < 1 || h < 1) return fail(ctx, RT_ERR_ARG, "rt_whitted_upload: need prims, n >= 1, w >= 1, h >= 1");
     CK(cudaSetDevice(ctx->device));
-    WSoA soa;
+    WSoA &soa = ctx->w_soa;
     build_w_soa(prims, n, soa);
     if (rtk_whitted_smem_bytes(n, (int)soa.lights.size(), 0) > (size_t)ctx->max_smem_optin)
         return fail(ctx, RT_ERR_CAPACITY, "rt_whitted_upload: %d primitives exceed the %d-byte shared-memory staging of this build", n, ctx->max_smem_optin);
-    CK(upload_vec(&ctx->d_wgeom, soa.geom, ctx->stream));
-    CK(upload_vec(&ctx->d_wma, soa.mat_a, ctx->stream));
-    CK(upload_vec(&ctx->d_wmb, soa.mat_b, ctx->stream));
-    CK(upload_vec(&ctx->d_wflags, soa.flags, ctx->stream));
-    CK(upload_vec(&ctx->d_wlights, soa.lights, ctx->stream));
-    CK(upload_vec(&ctx->d_wrrad, soa.rrad, ctx->stream));
+    CK(upload_vec(&ctx->d_wgeom, &ctx->cap_wgeom, soa.geom, ctx->stream));
+    CK(upload_vec(&ctx->d_wma, &ctx->cap_wma, soa.mat_a, ctx->stream));
+    CK(upload_vec(&ctx->d_wmb, &ctx->cap_wmb, soa.mat_b, ctx->stream));
+    CK(upload_vec(&ctx->d_wflags, &ctx->cap_wflags, soa.flags, ctx->stream));
+    CK(upload_vec(&ctx->d_wlights, &ctx->cap_wlights, soa.lights, ctx->stream));
+    CK(upload_vec(&ctx->d_wrrad, &ctx->cap_wrrad, soa.rrad, ctx->stream));
     const size_t px = (size_t)w * h;
     if (px > ctx->w_pixels_cap) {
         if (ctx->d_wpixels) cudaFree(ctx->d_wpixels);
@@ -201,7 +210,6 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
         CK(cudaMalloc((void **)&ctx->d_whits, px * 9 * sizeof(int32_t)));
         ctx->w_hits_cap = px * 9;
     }
-    CK(cudaStreamSynchronize(ctx->stream));      // the SoA vectors go out of scope
     ctx->w_w = w; ctx->w_h = h; ctx->w_n = n; ctx->w_nl = (int)soa.lights.size();
     ctx->w_ns = soa.n_spheres; ctx->w_np = soa.n_planes; ctx->w_want_hits = want_hit_ids ? 1 : 0;
     return RT_OK;
@@ -280,12 +288,12 @@ int rt_pt_set_scene(rt_ctx *ctx, const rt_sphere *spheres, uint32_t n) {
         if (spheres[i].refl < 0 || spheres[i].refl > 2)
             return fail(ctx, RT_ERR_ARG, "rt_pt_set_scene: sphere %u has material %d (expected 0, 1 or 2)", i, spheres[i].refl);
     CK(cudaSetDevice(ctx->device));
-    PtSoA soa;
+    PtSoA &soa = ctx->p_soa;
     build_pt_soa(spheres, n, soa);
-    CK(upload_vec(&ctx->d_pgeom, soa.geom, ctx->stream));
-    CK(upload_vec(&ctx->d_pemis, soa.emis, ctx->stream));
-    CK(upload_vec(&ctx->d_pcolr, soa.colr, ctx->stream));
-    CK(upload_vec(&ctx->d_plights, soa.lights, ctx->stream));
+    CK(upload_vec(&ctx->d_pgeom, &ctx->cap_pgeom, soa.geom, ctx->stream));
+    CK(upload_vec(&ctx->d_pemis, &ctx->cap_pemis, soa.emis, ctx->stream));
+    CK(upload_vec(&ctx->d_pcolr, &ctx->cap_pcolr, soa.colr, ctx->stream));
+    CK(upload_vec(&ctx->d_plights, &ctx->cap_plights, soa.lights, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->p_n = (int)n; ctx->p_nl = (int)soa.lights.size(); ctx->have_scene = true; ctx->current_sample = 0;
     return RT_OK;
@@ -411,5 +419,15 @@ void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes) {
 }
 
 void *rt_stream(rt_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int rt_set_stream(rt_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return RT_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,280 @@
+"""Parity of the CUDA path (librt_b200.so, called through its C ABI) with the oracle.  Needs a B200.
+
+Bars (BASELINE.json north_star): hit-ID buffer bit-exact; Whitted pixels byte-exact (the stated
+tolerance is 1 LSB; nothing here needs it); path-tracer RNG state and float radiance bit-exact;
+8-bit path-traced pixels byte-exact.  Nothing in this file reads /root/reference."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import vp, load_smallpt_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_whitted(orc, prims, w, h):
+    px, hits, ctr = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32), np.zeros(5, np.uint64)
+    orc.oracle_whitted_render(vp(px), vp(hits), w, h, vp(prims), prims.size, 16, vp(ctr))
+    return px, hits, ctr
+
+
+def oracle_pt(orc, integ, spheres, cam, w, h, seeds, passes, pass0=0, colors=None):
+    col = np.zeros(3 * w * h, np.float32) if colors is None else colors
+    sd, pix, ctr = seeds.copy(), np.zeros(w * h, np.uint32), np.zeros(4, np.uint64)
+    orc.oracle_pt_render(integ, vp(spheres), spheres.size, vp(cam), w, h, pass0, passes, vp(col), vp(sd), vp(pix), 16, vp(ctr))
+    return col, sd, pix, ctr
+
+
+# ------------------------------------------------------------------------------------------ math
+def test_device_is_a_b200_and_kernels_launch(gpu):
+    info = gpu.device_info()
+    assert info["sm_count"] > 0
+    before = gpu.launch_count()
+    gpu.whitted_render(__import__("rt_b200").whitted_create_scene(0), 32, 24)
+    assert gpu.launch_count() == before + 1
+
+
+# ------------------------------------------------------------------------------------------ Whitted
+def test_whitted_800x600_equals_reference_golden_image(gpu, rt, whitted_golden, tmp_path):
+    """The GPU frame equals the reference's shipped test.bmp byte for byte, and the BMP written from
+    it has the reference file's md5; primary hit IDs match the compiled-reference known answers."""
+    prims = rt.whitted_create_scene(0)
+    px, hits = gpu.whitted_render(prims, 800, 600, want_hit_ids=True)
+    assert np.array_equal(px[:, :, :3], whitted_golden["rgb"])
+    assert not px[:, :, 3].any()
+    assert hashlib.sha256(hits.tobytes()).hexdigest() == whitted_golden["all9_hit_id_sha256"]
+    p = tmp_path / "gpu.bmp"
+    rt.write_bmp(str(p), px)
+    assert hashlib.md5(p.read_bytes()).hexdigest() == whitted_golden["bmp_md5"]
+
+
+@pytest.mark.parametrize("size", [(160, 120), (203, 77), (1, 1), (7, 3), (1920, 1080)])
+def test_whitted_equals_oracle(gpu, orc, rt, size):
+    w, h = size
+    prims = rt.whitted_create_scene(0)
+    px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+    px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
+    assert np.array_equal(hits, hits_o)                       # bit-exact, no grazing-edge allowance needed
+    assert np.array_equal(px, px_o)                           # byte-exact (bar: within 1 LSB)
+
+
+def test_whitted_scene1_and_open_scene(gpu, orc, rt):
+    """CHOOSE_SCENE 1 (64 primitives, open: rays miss) and a two-primitive open scene."""
+    for prims in [rt.whitted_create_scene(1), rt.whitted_create_scene(0)[[0, 13]].copy()]:
+        px, hits = gpu.whitted_render(prims, 240, 180, want_hit_ids=True)
+        px_o, hits_o, _ = oracle_whitted(orc, prims, 240, 180)
+        assert (hits_o == -1).any()
+        assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
+
+
+def test_whitted_counters_equal_oracle(gpu, orc, rt):
+    prims = rt.whitted_create_scene(0)
+    gpu.set_counting(True)
+    try:
+        px = gpu.whitted_render(prims, 320, 240)
+        c = gpu.counters()
+    finally:
+        gpu.set_counting(False)
+    px_o, _, ctr = oracle_whitted(orc, prims, 320, 240)
+    assert np.array_equal(px, px_o)
+    assert (c["nearest_queries"], c["shadow_queries"], c["sphere_tests"], c["plane_tests"]) == tuple(int(v) for v in ctr[:4])
+    assert c["samples"] == 320 * 240 * 9
+
+
+def test_whitted_row_tile_sharding_is_bit_identical(gpu, rt):
+    """Interleaved row tiles: the union of R shards equals the 1-GPU frame (each shard only touches its rows)."""
+    prims = rt.whitted_create_scene(0)
+    w, h = 333, 250
+    full = gpu.whitted_render(prims, w, h)
+    try:
+        for world, tile in [(2, 8), (4, 4), (8, 8)]:
+            acc = np.zeros_like(full)
+            for rank in range(world):
+                gpu.set_shard(rank, world, tile)
+                part = gpu.whitted_render(prims, w, h)
+                rows = np.array([(y // tile) % world == rank for y in range(h)])
+                acc[rows] = part[rows]
+            assert np.array_equal(acc, full), (world, tile)
+    finally:
+        gpu.set_shard(0, 1, 8)
+
+
+# ------------------------------------------------------------------------------------------ smallpt
+@pytest.mark.parametrize("scene", ["cornell", "caustic3", "simple", "complex"])
+def test_smallpt_equals_reference_fixture(gpu, rt, scene):
+    """colors / pixels / RNG state == the fixture produced by the reference's own CPU code."""
+    g = load_smallpt_golden(rt, scene)
+    for integ, tag in [(0, "pt"), (1, "dl")]:
+        gpu.pt_resize(g["w"], g["h"], g["seeds_in"])
+        gpu.pt_set_scene(g["spheres"])
+        gpu.pt_set_camera(g["camera"])
+        out = gpu.pt_render(integ, g["passes"])
+        assert np.array_equal(out["seeds"], g[tag + "_seeds"]), (scene, tag)
+        assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), g[tag + "_colors"]), (scene, tag)
+        assert np.array_equal(out["pixels"].reshape(-1), g[tag + "_pixels"]), (scene, tag)
+
+
+@pytest.mark.parametrize("size,passes", [((256, 192), 16), ((1024, 768), 2), ((61, 37), 5)])
+def test_smallpt_cornell_equals_oracle(gpu, orc, rt, cornell, size, passes):
+    w, h = size
+    spheres, cam = cornell
+    cam = cam.copy()
+    rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=11)
+    for integ in (0, 1):
+        gpu.pt_resize(w, h, seeds)
+        gpu.pt_set_scene(spheres)
+        gpu.pt_set_camera(cam)
+        out = gpu.pt_render(integ, passes)
+        col_o, sd_o, pix_o, _ = oracle_pt(orc, integ, spheres, cam, w, h, seeds, passes)
+        assert np.array_equal(out["seeds"], sd_o)                                       # RNG streams bit-exact
+        assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32))
+        assert np.array_equal(out["pixels"].reshape(-1), pix_o)
+
+
+def test_smallpt_progressive_calls_continue_the_sample_counter(gpu, orc, rt, cornell):
+    """UpdateRenderingGPU semantics: repeated calls accumulate; scene/camera/resize reset currentSample."""
+    spheres, cam = cornell
+    w, h = 96, 72
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=5)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    gpu.pt_render(0, 1); gpu.pt_render(0, 2)
+    out = gpu.pt_render(0, 3)
+    assert gpu.pt_current_sample() == 6
+    col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, spheres, cam, w, h, seeds, 6)
+    assert np.array_equal(out["seeds"], sd_o) and np.array_equal(out["pixels"].reshape(-1), pix_o)
+    assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32))
+    gpu.pt_set_camera(cam)
+    assert gpu.pt_current_sample() == 0
+
+
+def test_smallpt_chunked_staging_equals_resident(gpu, orc, rt, tmp_path):
+    """A scene streamed through shared memory in chunks (forced by a tiny residency limit, ragged last
+    chunk) gives the same bits as the resident path and as the oracle."""
+    p = tmp_path / "c3.scn"
+    rt.write_complex_scene(str(p), 3)                     # 158 spheres
+    w, h = 80, 60
+    spheres, cam = rt.read_scene(str(p), w, h)
+    seeds = rt.reference_seeds(w, h, seed=3)
+    col_o, sd_o, pix_o, ctr_o = oracle_pt(orc, 0, spheres, cam, w, h, seeds, 3)
+    try:
+        for resident_bytes, chunk in [(96 * 1024, 3072), (0, 64), (0, 50), (0, 1000)]:
+            gpu.set_tuning(rt.TUNE_PT_MAX_RESIDENT_BYTES, resident_bytes)
+            gpu.set_tuning(rt.TUNE_PT_CHUNK_SPHERES, chunk)
+            gpu.set_counting(True)
+            gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+            out = gpu.pt_render(0, 3)
+            c = gpu.counters()
+            assert np.array_equal(out["seeds"], sd_o), (resident_bytes, chunk)
+            assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32))
+            assert np.array_equal(out["pixels"].reshape(-1), pix_o)
+            assert (c["samples"], c["nearest_queries"], c["shadow_queries"], c["sphere_tests"]) == tuple(int(v) for v in ctr_o)
+    finally:
+        gpu.set_counting(False)
+        gpu.set_tuning(rt.TUNE_PT_MAX_RESIDENT_BYTES, 96 * 1024)
+        gpu.set_tuning(rt.TUNE_PT_CHUNK_SPHERES, 3072)
+
+
+def test_smallpt_row_tile_sharding_is_bit_identical(gpu, rt, cornell):
+    spheres, cam = cornell
+    w, h = 100, 75
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=9)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    full = gpu.pt_render(0, 4)
+    try:
+        gpu.pt_resize(w, h, seeds)
+        for rank in range(4):                 # four shards rendered into the same device buffers
+            gpu.set_shard(rank, 4, 8)
+            gpu.pt_set_camera(cam)            # reset currentSample for each shard
+            out = gpu.pt_render(0, 4)
+        assert np.array_equal(out["seeds"], full["seeds"])
+        assert np.array_equal(out["colors"].view(np.uint32), full["colors"].view(np.uint32))
+        assert np.array_equal(out["pixels"], full["pixels"])
+    finally:
+        gpu.set_shard(0, 1, 8)
+
+
+def test_smallpt_256spp_rmse_and_convergence(gpu, orc, rt, cornell):
+    """256 spp (BASELINE config 3's sample count, at 160x120 so that the CPU oracle finishes in seconds):
+    RMSE versus the oracle is exactly 0, and halving the noise needs 4x the samples (sanity of the estimator)."""
+    spheres, cam = cornell
+    w, h = 160, 120
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=21)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    out = gpu.pt_render(0, 256)
+    col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, spheres, cam, w, h, seeds, 256)
+    rmse = float(np.sqrt(np.mean((out["colors"].reshape(-1).astype(np.float64) - col_o) ** 2)))
+    assert rmse == 0.0                                     # stated bound: 0 (bit-exact); the north star asks for "< a stated bound"
+    assert np.array_equal(out["seeds"], sd_o) and np.array_equal(out["pixels"].reshape(-1), pix_o)
+
+
+def test_smallpt_sum_mode_matches_running_mean_within_rounding(gpu, rt, cornell):
+    """Sample-sharded mode accumulates sums; resolved image == running-mean image up to float rounding."""
+    spheres, cam = cornell
+    w, h = 64, 48
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=2)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    mean = gpu.pt_render(0, 32)
+    try:
+        gpu.pt_set_accumulate_sums(True)
+        gpu.pt_resize(w, h, seeds)
+        gpu.pt_launch(0, 32)
+        gpu.pt_resolve_sums(32)
+        s = gpu.pt_download()
+    finally:
+        gpu.pt_set_accumulate_sums(False)
+    assert np.array_equal(s["seeds"], mean["seeds"])
+    np.testing.assert_allclose(s["colors"] / 32.0, mean["colors"], rtol=2e-5, atol=1e-6)
+    diff = np.abs((s["pixels"].view(np.uint8).astype(int) - mean["pixels"].view(np.uint8).astype(int)))
+    assert diff.max() <= 1
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(gpu, rt, cornell):
+    """At BASELINE sizes the oracle is too slow to be the checker; size-independent properties instead:
+    determinism (same inputs -> same bits), the alpha channel is 0, 4K row-tile shards tile the frame,
+    seeds never fall below the generator's fixed points, and the complex scene renders through the ABI."""
+    prims = rt.whitted_create_scene(0)
+    a = gpu.whitted_render(prims, 1920, 1080)
+    b = gpu.whitted_render(prims, 1920, 1080)
+    assert np.array_equal(a, b) and not a[:, :, 3].any() and a[:, :, :3].any()
+    spheres, cam = cornell
+    w, h = 1024, 768
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=1)
+    outs = []
+    for _ in range(2):
+        gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+        outs.append(gpu.pt_render(0, 8))
+    assert np.array_equal(outs[0]["seeds"], outs[1]["seeds"]) and np.array_equal(outs[0]["pixels"], outs[1]["pixels"])
+    assert np.isfinite(outs[0]["colors"]).all() and (outs[0]["colors"] >= 0).all()
+    assert (outs[0]["pixels"] >> 24 == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ error behaviour
+def test_errors_are_codes_not_exits(gpu, rt, cornell):
+    spheres, cam = cornell
+    r = rt.Renderer(0)
+    try:
+        with pytest.raises(rt.RtError) as e:
+            r.pt_launch(0, 1)                              # before resize / scene / camera
+        assert e.value.code == rt.RT_ERR_STATE
+        r.pt_resize(8, 8, rt.reference_seeds(8, 8)); r.pt_set_scene(spheres); r.pt_set_camera(cam)
+        with pytest.raises(rt.RtError) as e:
+            r.pt_launch(2, 1)                              # unknown integrator
+        assert e.value.code == rt.RT_ERR_ARG
+        bad = spheres.copy(); bad["refl"][0] = 7
+        with pytest.raises(rt.RtError) as e:
+            r.pt_set_scene(bad)
+        assert e.value.code == rt.RT_ERR_ARG
+        with pytest.raises(rt.RtError) as e:
+            r.set_shard(3, 2, 8)
+        assert e.value.code == rt.RT_ERR_ARG
+    finally:
+        r.close()

@@ -93,3 +93,10 @@ def test_work_items_cover_each_owned_pixel_exactly_once(devsim):
             assert all((y // tile) % world == rank for y in rows)
             total += v
         assert (total == 1).all(), (w, h, world, tile)
+
+
+def test_builtin_cornell_equals_scn_fixture(rt):
+    """rt.cornell_scene() (CornellSpheres[] of SPT/scene.h) == ReadScene(SPT/scenes/cornell.scn) from the fixture."""
+    g = load_smallpt_golden(rt, "cornell")
+    spheres, cam = rt.cornell_scene(g["w"], g["h"])
+    assert spheres.tobytes() == g["spheres"].tobytes() and cam.tobytes() == g["camera"].tobytes()
