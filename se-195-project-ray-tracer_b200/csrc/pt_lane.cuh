@@ -51,7 +51,7 @@ struct PtLane {
     float lr, lg, lb;               // direct light gathered at the current diffuse hit
     float lscale;                   // geometric term of the light sample whose shadow query is in flight
     float cumu;                     // nearest distance so far / shadow max-t
-    int hit;                        // nearest: sphere index (-1 none); shadow: 1 if occluded
+    int hit;                        // sphere index of the accepted hit, -1 none (shadow query: >= 0 means occluded)
     int li;                         // cursor into lights[]
     int depth, after_spec, phase;
     // work counters (only maintained by counting builds)
@@ -59,35 +59,79 @@ struct PtLane {
     uint64_t c_tests;
 };
 
-// SphereIntersect, SPT/geomfunc.h:32-59, on the staged (p, rad^2) record.
-RT_HD float pt_sphere_hit(const f4 g, float ox, float oy, float oz, float dx, float dy, float dz) {
-    const float opx = f_sub(g.x, ox), opy = f_sub(g.y, oy), opz = f_sub(g.z, oz);
-    const float b = dot3(opx, opy, opz, dx, dy, dz);
-    float det = f_add(f_sub(f_mul(b, b), dot3(opx, opy, opz, opx, opy, opz)), g.w);
-    if (det < 0.f) return 0.f;
-    det = f_sqrt(det);
-    float t = f_sub(b, det);
-    if (t > PT_EPS) return t;
-    t = f_add(b, det);
-    return t > PT_EPS ? t : 0.f;
+// One sphere against the lane's query: SphereIntersect (SPT/geomfunc.h:32-59) on the staged (p, rad^2)
+// record, followed by the acceptance test shared by Intersect (:80-88) and IntersectP (:102-109):
+// `d != 0 && d < limit`.  Written without per-lane branches -- every lane of the warp evaluates the same
+// instruction stream and the update is a predicated select -- because the loop index is warp-uniform; the
+// square root (only needed when some lane has det >= 0) sits behind a warp vote.  `live` masks lanes that
+// have no query in flight.  A nearest query keeps the closest hit (scanning i = n-1 .. 0 with a strict '<'
+// leaves the HIGHER index on an exact tie, as the reference does); a shadow query only needs "any hit", so
+// recording the index there too (hit >= 0 means occluded) lets both kinds share the update.
+template <bool COUNT>
+RT_HD void pt_test(PtLane &L, const f4 g, int i, bool live) {
+    if (COUNT && live && L.phase == PH_SHADOW && L.hit < 0) L.c_tests++;   // IntersectP stops at its first hit
+    const float opx = f_sub(g.x, L.ox), opy = f_sub(g.y, L.oy), opz = f_sub(g.z, L.oz);
+    const float b = dot3(opx, opy, opz, L.dx, L.dy, L.dz);
+    const float det = f_add(f_sub(f_mul(b, b), dot3(opx, opy, opz, opx, opy, opz)), g.w);
+    const bool cand = live && !(det < 0.f);
+    if (warp_any(cand)) {
+        const float sq = f_sqrt(det);
+        const float t1 = f_sub(b, sq), t2 = f_add(b, sq);
+        const float t = t1 > PT_EPS ? t1 : t2;                 // first root if beyond EPSILON, else the second
+        if (cand && t > PT_EPS && t < L.cumu) { L.cumu = t; L.hit = i; }
+    }
 }
 
-// One sphere against the lane's query.  Returns true when the lane's query is finished early
-// (shadow ray found an occluder).  Intersect keeps a strictly closer hit, so scanning i = n-1 .. 0
-// leaves the HIGHER index on an exact tie (SPT/geomfunc.h:80-88).
+// Four consecutive spheres (indices i, i-1, i-2, i-3; g points at sphere i-3) in one go: the four
+// discriminants are independent instruction chains (ILP), one warp vote covers the four square roots, and
+// the four acceptance tests are applied in the reference's descending index order.
 template <bool COUNT>
-RT_HD bool pt_test(PtLane &L, const f4 g, int i) {
-    if (COUNT && L.phase == PH_SHADOW) L.c_tests++;
-    const float k = pt_sphere_hit(g, L.ox, L.oy, L.oz, L.dx, L.dy, L.dz);
-    if (k != 0.f && k < L.cumu) {
-        if (L.phase == PH_NEAREST) { L.cumu = k; L.hit = i; }
-        else { L.hit = 1; return true; }
+RT_HD void pt_test4(PtLane &L, const f4 *g, int i, bool live) {
+    float b[4], det[4];
+    bool cand[4];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const f4 s = g[3 - k];
+        const float opx = f_sub(s.x, L.ox), opy = f_sub(s.y, L.oy), opz = f_sub(s.z, L.oz);
+        b[k] = dot3(opx, opy, opz, L.dx, L.dy, L.dz);
+        det[k] = f_add(f_sub(f_mul(b[k], b[k]), dot3(opx, opy, opz, opx, opy, opz)), s.w);
+        cand[k] = live && !(det[k] < 0.f);
+        any = any || cand[k];
     }
-    return false;
+    if (warp_any(any)) {
+        float t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float sq = f_sqrt(det[k]);
+            const float t1 = f_sub(b[k], sq), t2 = f_add(b[k], sq);
+            t[k] = t1 > PT_EPS ? t1 : t2;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (COUNT && live && L.phase == PH_SHADOW && L.hit < 0) L.c_tests++;
+            if (cand[k] && t[k] > PT_EPS && t[k] < L.cumu) { L.cumu = t[k]; L.hit = i - k; }
+        }
+    } else if (COUNT && live && L.phase == PH_SHADOW && L.hit < 0) L.c_tests += 4;
+}
+
+// The sphere loop of one query round over spheres [lo, hi), descending (geom[0] is sphere `lo`): groups of
+// four, then the ragged rest.  Every 16 spheres a warp vote ends the loop once no lane can change any more
+// (all idle, or all shadow queries already occluded) -- the any-hit early-out of IntersectP at warp level.
+template <bool COUNT>
+RT_HD void pt_query_range(PtLane &L, const f4 *geom, int lo, int hi, bool active) {
+    int i = hi - 1;
+    while (i >= lo) {
+        const bool live = active && !(L.phase == PH_SHADOW && L.hit >= 0);
+        if (!warp_any(live)) return;
+        int stop = i - 15 > lo ? i - 15 : lo;           // this vote covers spheres i .. stop
+        for (; i - 3 >= stop; i -= 4) pt_test4<COUNT>(L, geom + (i - 3 - lo), i, live);
+        for (; i >= stop; --i) pt_test<COUNT>(L, geom[i - lo], i, live);
+    }
 }
 
 RT_HD void pt_unit(float &x, float &y, float &z) {     // vnorm, SPT/vec.h:41
-    const float l = f_div(1.f, f_sqrt(dot3(x, y, z, x, y, z)));
+    const float l = f_rcp(f_sqrt(dot3(x, y, z, x, y, z)));
     x = f_mul(l, x); y = f_mul(l, y); z = f_mul(l, z);
 }
 
@@ -168,7 +212,7 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
                         L.dx = mx; L.dy = my; L.dz = mz;
                     } else {                                          // REFR: SPT/geomfunc.h:289-336
                         const bool into = dot3(nx, ny, nz, nlx, nly, nlz) > 0.f;
-                        const float nnt = into ? f_div(1.f, 1.5f) : f_div(1.5f, 1.f);
+                        const float nnt = into ? 0x1.555556p-1f : 1.5f;       // nc / nt = fl(1.f / 1.5f), nt / nc = 1.5f
                         const float ddn = dot3(L.dx, L.dy, L.dz, nlx, nly, nlz);
                         const float cos2t = f_sub(1.f, f_mul(f_mul(nnt, nnt), f_sub(1.f, f_mul(ddn, ddn))));
                         if (cos2t < 0.f) {                            // total internal reflection
@@ -180,8 +224,7 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
                             float ty = f_sub(f_mul(nnt, L.dy), f_mul(kk, ny));
                             float tz = f_sub(f_mul(nnt, L.dz), f_mul(kk, nz));
                             pt_unit(tx, ty, tz);
-                            const float ea = f_sub(1.5f, 1.f), eb = f_add(1.5f, 1.f);
-                            const float R0 = f_div(f_mul(ea, ea), f_mul(eb, eb));
+                            const float R0 = 0.04f;                           // a*a/(b*b) = fl(0.25f / 6.25f), a = nt-nc, b = nt+nc
                             const float c = f_sub(1.f, into ? -ddn : dot3(tx, ty, tz, nx, ny, nz));
                             const float Re = f_add(R0, f_mul(f_mul(f_mul(f_mul(f_mul(f_sub(1.f, R0), c), c), c), c), c));
                             const float Tr = f_sub(1.f, Re);
@@ -203,7 +246,7 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
         }
     } else {                                                          // a shadow query has just finished
         if (COUNT) L.c_shadow++;
-        if (!L.hit) {                                                 // light visible: SPT/geomfunc.h:157-162
+        if (L.hit < 0) {                                              // light visible: SPT/geomfunc.h:157-162
             const f4 le = F.emis[F.lights[L.li]];
             L.lr = f_add(L.lr, f_mul(L.lscale, le.x));
             L.lg = f_add(L.lg, f_mul(L.lscale, le.y));
@@ -232,7 +275,7 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
             const float spx = f_add(f_mul(lrad, ux), lg.x), spy = f_add(f_mul(lrad, uy), lg.y), spz = f_add(f_mul(lrad, uz), lg.z);
             float sx = f_sub(spx, L.ox), sy = f_sub(spy, L.oy), sz = f_sub(spz, L.oz);
             const float len = f_sqrt(dot3(sx, sy, sz, sx, sy, sz));
-            const float inv = f_div(1.f, len);
+            const float inv = f_rcp(len);
             sx = f_mul(inv, sx); sy = f_mul(inv, sy); sz = f_mul(inv, sz);
             float wo = dot3(sx, sy, sz, ux, uy, uz);
             if (wo > 0.f) continue;                                   // sample on the far half of the light
@@ -242,7 +285,7 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
                 L.lscale = f_div(f_mul(f_mul(f_mul(f_mul(f_mul(4.f, PT_PI), lrad), lrad), wi), wo), f_mul(len, len));
                 L.dx = sx; L.dy = sy; L.dz = sz;
                 L.cumu = f_sub(len, PT_EPS);
-                L.hit = 0;
+                L.hit = -1;
                 L.phase = PH_SHADOW;
                 return false;
             }
@@ -289,7 +332,7 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
         L.cr = L.rr; L.cg = L.rg; L.cb = L.rb;
     } else {
         const float k1 = (float)L.pass;
-        const float k2 = f_div(1.f, f_add(k1, 1.f));
+        const float k2 = f_rcp(f_add(k1, 1.f));
         L.cr = f_mul(f_add(f_mul(L.cr, k1), L.rr), k2);
         L.cg = f_mul(f_add(f_mul(L.cg, k1), L.rg), k2);
         L.cb = f_mul(f_add(f_mul(L.cb, k1), L.rb), k2);

@@ -31,14 +31,14 @@ struct rt_ctx {
     int pt_chunk_spheres = 3072;                   // 48 KB of (p, rad^2) per chunk
     int max_blocks_per_sm = 0;
     // Whitted
-    int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_want_hits = 0;
+    int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_nr = 0, w_want_hits = 0;
     f4 *d_wgeom = nullptr, *d_wma = nullptr, *d_wmb = nullptr;
-    int *d_wflags = nullptr, *d_wlights = nullptr;
+    int *d_wflags = nullptr, *d_wlights = nullptr, *d_wruns = nullptr;
     float *d_wrrad = nullptr;
     uint32_t *d_wpixels = nullptr;
     int32_t *d_whits = nullptr;
     size_t w_pixels_cap = 0, w_hits_cap = 0;
-    size_t cap_wgeom = 0, cap_wma = 0, cap_wmb = 0, cap_wflags = 0, cap_wlights = 0, cap_wrrad = 0;
+    size_t cap_wgeom = 0, cap_wma = 0, cap_wmb = 0, cap_wflags = 0, cap_wlights = 0, cap_wrrad = 0, cap_wruns = 0;
     size_t cap_pgeom = 0, cap_pemis = 0, cap_pcolr = 0, cap_plights = 0;
     WSoA w_soa;                                    // host staging of the last uploaded scenes (kept alive
     PtSoA p_soa;                                   //  until the asynchronous copies have been issued and synced)
@@ -126,7 +126,7 @@ void rt_destroy(rt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights,
+    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
     for (void *b : bufs) if (b) cudaFree(b);
@@ -189,7 +189,7 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(cudaSetDevice(ctx->device));
     WSoA &soa = ctx->w_soa;
     build_w_soa(prims, n, soa);
-    if (rtk_whitted_smem_bytes(n, (int)soa.lights.size(), 0) > (size_t)ctx->max_smem_optin)
+    if (rtk_whitted_smem_bytes(n, (int)soa.lights.size(), (int)soa.runs.size() / 3, 0) > (size_t)ctx->max_smem_optin)
         return fail(ctx, RT_ERR_CAPACITY, "rt_whitted_upload: %d primitives exceed the %d-byte shared-memory staging of this build", n, ctx->max_smem_optin);
     CK(upload_vec(&ctx->d_wgeom, &ctx->cap_wgeom, soa.geom, ctx->stream));
     CK(upload_vec(&ctx->d_wma, &ctx->cap_wma, soa.mat_a, ctx->stream));
@@ -197,6 +197,7 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(upload_vec(&ctx->d_wflags, &ctx->cap_wflags, soa.flags, ctx->stream));
     CK(upload_vec(&ctx->d_wlights, &ctx->cap_wlights, soa.lights, ctx->stream));
     CK(upload_vec(&ctx->d_wrrad, &ctx->cap_wrrad, soa.rrad, ctx->stream));
+    CK(upload_vec(&ctx->d_wruns, &ctx->cap_wruns, soa.runs, ctx->stream));
     const size_t px = (size_t)w * h;
     if (px > ctx->w_pixels_cap) {
         if (ctx->d_wpixels) cudaFree(ctx->d_wpixels);
@@ -211,7 +212,7 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
         ctx->w_hits_cap = px * 9;
     }
     ctx->w_w = w; ctx->w_h = h; ctx->w_n = n; ctx->w_nl = (int)soa.lights.size();
-    ctx->w_ns = soa.n_spheres; ctx->w_np = soa.n_planes; ctx->w_want_hits = want_hit_ids ? 1 : 0;
+    ctx->w_ns = soa.n_spheres; ctx->w_np = soa.n_planes; ctx->w_nr = (int)soa.runs.size() / 3; ctx->w_want_hits = want_hit_ids ? 1 : 0;
     return RT_OK;
 }
 
@@ -222,6 +223,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
     WLaunch p;
     WFrame &F = p.frame;
     F.geom = ctx->d_wgeom; F.mat_a = ctx->d_wma; F.mat_b = ctx->d_wmb; F.flags = ctx->d_wflags; F.lights = ctx->d_wlights;
+    F.runs = ctx->d_wruns; F.n_runs = ctx->w_nr;
     F.rrad = ctx->d_wrrad; F.n = ctx->w_n; F.n_lights = ctx->w_nl; F.n_spheres = ctx->w_ns; F.n_planes = ctx->w_np;
     F.w = ctx->w_w; F.h = ctx->w_h;
     // R323/raytracer_non_OpenCL.c:291-296: DX = (WX2 - WX1) / width with float operands.
@@ -231,7 +233,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
     p.shard = make_shard(ctx->w_w, ctx->w_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.pixels = ctx->d_wpixels; p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
     p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
-    p.stage_materials = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, 1) <= 32 * 1024 ? 1 : 0;
+    p.stage_materials = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 1) <= 32 * 1024 ? 1 : 0;
     CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches++; }

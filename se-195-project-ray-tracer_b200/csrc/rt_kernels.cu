@@ -77,32 +77,15 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
         if (CHUNKED) { if (!__syncthreads_or(more)) break; }
         else         { if (!__any_sync(FULL_MASK, more)) break; }
 
-        bool done = !active;
         if (!CHUNKED) {
-            int i = F.n - 1;
-            for (; i >= 3; i -= 4) {
-                const f4 g0 = s_geom[i], g1 = s_geom[i - 1], g2 = s_geom[i - 2], g3 = s_geom[i - 3];
-                if (!done) done = pt_test<COUNT>(L, g0, i);
-                if (!done) done = pt_test<COUNT>(L, g1, i - 1);
-                if (!done) done = pt_test<COUNT>(L, g2, i - 2);
-                if (!done) done = pt_test<COUNT>(L, g3, i - 3);
-                if ((i & 12) == 0 && __all_sync(FULL_MASK, done)) { i = -1; break; }
-            }
-            for (; i >= 0; --i) {
-                const f4 g = s_geom[i];
-                if (!done) done = pt_test<COUNT>(L, g, i);
-            }
+            pt_query_range<COUNT>(L, s_geom, 0, F.n, active);
         } else {
             for (int hi = F.n; hi > 0; hi -= chunk) {          // descending index, chunk by chunk
                 const int lo = hi > chunk ? hi - chunk : 0;
                 __syncthreads();
                 for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) s_geom[i - lo] = F.geom_global[i];
                 __syncthreads();
-                if (!__any_sync(FULL_MASK, !done)) continue;    // this warp has nothing left in this round
-                for (int i = hi - 1; i >= lo; --i) {
-                    const f4 g = s_geom[i - lo];
-                    if (!done) done = pt_test<COUNT>(L, g, i);
-                }
+                pt_query_range<COUNT>(L, s_geom, lo, hi, active);
             }
         }
 
@@ -143,22 +126,24 @@ __global__ void __launch_bounds__(W_THREADS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *work_counter,
                unsigned long long *counters, int stage_materials) {
     extern __shared__ f4 s_raw[];
-    // layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | rrad[n] (optional) | lights[n_lights] (optional)
+    // layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | runs[3*n_runs] | rrad[n] (optional) | lights[n_lights] (optional)
     f4 *s_geom = s_raw;
-    int *s_flags;
+    int *s_flags, *s_runs;
     const uint32_t lane = threadIdx.x & 31u;
     {
         const int n = F.n;
         f4 *s_ma = s_geom + n, *s_mb = s_ma + n;
         int *ibase = stage_materials ? (int *)(s_mb + n) : (int *)(s_geom + n);
         s_flags = ibase;
-        float *s_rr = (float *)(ibase + n);
+        s_runs = ibase + n;
+        float *s_rr = (float *)(s_runs + 3 * F.n_runs);
         int *s_li = (int *)(s_rr + n);
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             s_geom[i] = F.geom[i];
             s_flags[i] = F.flags[i];
             if (stage_materials) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; }
         }
+        for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) s_runs[i] = F.runs[i];
         if (stage_materials)
             for (int i = threadIdx.x; i < F.n_lights; i += blockDim.x) s_li[i] = F.lights[i];
         __syncthreads();
@@ -184,13 +169,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *
         const bool active = L.phase != PH_IDLE;
         if (!__any_sync(FULL_MASK, active || !exhausted)) break;
 
-        bool done = !active;
-        for (int s = 0; s < F.n; ++s) {                         // ascending index, RNO:185
-            const f4 g = s_geom[s];
-            const int fl = s_flags[s];
-            if (!done) done = w_test<COUNT>(L, g, fl, s);
-            if ((s & 7) == 7 && __all_sync(FULL_MASK, done)) break;
-        }
+        w_query<COUNT>(L, s_geom, s_runs, F.n_runs, active);
 
         if (active && w_advance<COUNT>(L, F, queue))
             pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(L.ar, L.ag, L.ab);
@@ -250,14 +229,14 @@ cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, 
     return cudaGetLastError();
 }
 
-size_t rtk_whitted_smem_bytes(int n, int n_lights, int stage_materials) {
-    size_t b = (size_t)n * (sizeof(f4) + sizeof(int));
+size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_materials) {
+    size_t b = (size_t)n * (sizeof(f4) + sizeof(int)) + (size_t)n_runs * 3 * sizeof(int);
     if (stage_materials) b += (size_t)n * (2 * sizeof(f4) + sizeof(float)) + (size_t)n_lights * sizeof(int);
     return b < 16 ? 16 : b;
 }
 
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
-    const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.stage_materials);
+    const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_materials);
     typedef void (*kern_t)(WFrame, Shard, uint32_t, uint32_t *, unsigned *, unsigned long long *, int);
     kern_t k = p.count ? whitted_kernel<true> : whitted_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

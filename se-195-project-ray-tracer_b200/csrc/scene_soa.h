@@ -36,7 +36,7 @@ inline void build_pt_soa(const rt_sphere *s, uint32_t n, PtSoA &out) {
 
 struct WSoA {
     std::vector<f4> geom, mat_a, mat_b;
-    std::vector<int> flags, lights;
+    std::vector<int> flags, lights, runs;
     std::vector<float> rrad;
     int n_spheres = 0, n_planes = 0;
 };
@@ -60,6 +60,15 @@ inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
         f4 a = { p[i].m_color.x, p[i].m_color.y, p[i].m_color.z, p[i].m_refl };
         f4 b = { p[i].m_diff, p[i].m_refr, p[i].m_refr_index, p[i].m_spec };
         out.geom[i] = g; out.mat_a[i] = a; out.mat_b[i] = b; out.flags[i] = fl; out.rrad[i] = p[i].r_radius;
+    }
+    // Index order is part of the result (ties), so the kernel walks the primitives in order -- but as runs
+    // of equal (type, is_light), which takes the type dispatch out of the inner loop.
+    out.runs.clear();
+    for (int i = 0; i < n;) {
+        int j = i;
+        while (j < n && out.flags[j] == out.flags[i] && j - i < 32) j++;   // <= 32 per run: the kernel re-votes per run
+        out.runs.push_back(i); out.runs.push_back(j - i); out.runs.push_back(out.flags[i]);
+        i = j;
     }
 }
 

@@ -29,8 +29,9 @@ enum { W_PRIMARY = 0, W_REFLECTED = 1, W_REFRACTED = 2 };   /* RNO:59-63 */
 struct WFrame {
     const f4 *geom, *mat_a, *mat_b;
     const int *flags, *lights;
+    const int *runs;            // maximal index runs of equal (type, is_light): triples (start, count, flags)
     const float *rrad;
-    int n, n_lights, n_spheres, n_planes;
+    int n, n_lights, n_spheres, n_planes, n_runs;
     int w, h;
     float DX, DY;               // (WX2-WX1)/w, (WY2-WY1)/h computed on the host exactly as RNO:295-296
     int32_t *hit_ids;           // NULL or int[w*h*9]
@@ -45,7 +46,7 @@ struct WLane {
     int depth, kind, from;
     float qox, qoy, qoz, qdx, qdy, qdz;             // ray of the query in flight
     float cumu;                                     // nearest distance so far / distance to the light
-    int qhit, qkind;                                // nearest: primitive + HIT(1)/INPRIM(-1); shadow: qhit = blocked
+    int qhit, qkind;                                // primitive of the accepted hit (-1 none) + HIT(1)/INPRIM(-1); shadow: qhit >= 0 = blocked
     float dist; int hit, hkind;                     // result of the nearest query while lights are processed
     float px, py, pz;                               // intersection point
     float cr, cg, cb;                               // colour gathered for this ray
@@ -54,44 +55,103 @@ struct WLane {
     uint64_t c_sphere_tests, c_plane_tests;
 };
 
-// plane_intersect RNO:95-109 / sphere_intersect RNO:111-148 against the lane's query ray.
-// Return HIT(1) / INPRIM(-1) / MISS(0) and shrink L.cumu on a hit.
-RT_HD int w_plane(WLane &L, const f4 g) {
+// plane_intersect (RNO:95-109) and sphere_intersect (RNO:111-148) against the lane's query ray, written
+// without per-lane branches: the primitive index is warp-uniform, so all 32 lanes run one instruction
+// stream and a hit is a predicated update of (cumu, qhit, qkind).  `live` masks lanes that take no part
+// (no query in flight, or a shadow query looking at a light).  The two expensive IEEE operations sit
+// behind warp votes: the square root is only evaluated when some lane has det > 0, the division only
+// when some lane can still be hit.  For a shadow query qhit >= 0 simply means "blocked"; the reference
+// stops at the first blocker, which changes nothing but the test count (kept exact in counting builds).
+//
+// Plane pre-filters (exact: they only discard tests the reference's own comparison would fail):
+//   A. dist = num/d with num = -(N.o + depth).  dist > 0 needs num and d non-zero and of equal sign.
+//   B. |num| > (cumu*|d|)*(1+2^-21), all factors rounded, implies |num|/|d| > cumu*(1+2^-22), hence the
+//      correctly rounded quotient is >= cumu + ulp and `dist < cumu` fails.  Skipped when the product is
+//      not comfortably normal (the error bound would not hold for subnormals; inf never rejects).
+template <bool COUNT>
+RT_HD void w_plane(WLane &L, const f4 g, int i, bool live) {
+    if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests++;
     const float d = dot3(g.x, g.y, g.z, L.qdx, L.qdy, L.qdz);
-    if (d != 0.f) {
-        const float dist = f_div(-f_add(dot3(g.x, g.y, g.z, L.qox, L.qoy, L.qoz), g.w), d);
-        if (dist > 0.f && dist < L.cumu) { L.cumu = dist; return 1; }
+    const float num = -f_add(dot3(g.x, g.y, g.z, L.qox, L.qoy, L.qoz), g.w);
+    const float bound = f_mul(f_mul(L.cumu, fabsf(d)), 1.000000476837158203125f);
+    const bool far_away = fabsf(num) > bound && bound > 1e-30f;
+    const bool cand = live && d != 0.f && num != 0.f && ((num > 0.f) == (d > 0.f)) && !far_away;
+    if (warp_any(cand)) {
+        const float dist = f_div(num, d);
+        if (cand && dist > 0.f && dist < L.cumu) { L.cumu = dist; L.qhit = i; L.qkind = 1; }
     }
-    return 0;
 }
-RT_HD int w_sphere(WLane &L, const f4 g) {
+template <bool COUNT>
+RT_HD void w_sphere(WLane &L, const f4 g, int i, bool live) {
+    if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests++;
     const float vx = f_sub(L.qox, g.x), vy = f_sub(L.qoy, g.y), vz = f_sub(L.qoz, g.z);
     const float b = -dot3(vx, vy, vz, L.qdx, L.qdy, L.qdz);
-    float det = f_add(f_sub(f_mul(b, b), dot3(vx, vy, vz, vx, vy, vz)), g.w);
-    if (det > 0.f) {
-        det = f_sqrt(det);
-        const float i1 = f_sub(b, det), i2 = f_add(b, det);
-        if (i2 > 0.f) {
-            if (i1 < 0.f) { if (i2 < L.cumu) { L.cumu = i2; return -1; } }
-            else if (i1 < L.cumu) { L.cumu = i1; return 1; }
-        }
+    const float det = f_add(f_sub(f_mul(b, b), dot3(vx, vy, vz, vx, vy, vz)), g.w);
+    const bool cand = live && det > 0.f;
+    if (warp_any(cand)) {
+        const float sq = f_sqrt(det);
+        const float i1 = f_sub(b, sq), i2 = f_add(b, sq);
+        const bool inside = i1 < 0.f;                           // ray starts inside: take the far root, INPRIM
+        const float t = inside ? i2 : i1;
+        if (cand && i2 > 0.f && t < L.cumu) { L.cumu = t; L.qhit = i; L.qkind = inside ? -1 : 1; }
     }
-    return 0;
 }
 
-// One primitive against the lane's query; returns true when a shadow query found its blocker.
-// Ascending index + strict '<' => the lowest index keeps an exact tie (RNO:185-193).
+// Two consecutive spheres (i, i+1) at once: two independent discriminant chains, one vote for both roots,
+// acceptance in ascending index order.
 template <bool COUNT>
-RT_HD bool w_test(WLane &L, const f4 g, int flag, int i) {
-    if (L.phase == PH_SHADOW && (flag & W_FLAG_LIGHT)) return false;     // RNO:234: lights cast no shadow
-    int k;
-    if (flag & W_FLAG_SPHERE) { if (COUNT && L.phase == PH_SHADOW) L.c_sphere_tests++; k = w_sphere(L, g); }
-    else                      { if (COUNT && L.phase == PH_SHADOW) L.c_plane_tests++;  k = w_plane(L, g); }
-    if (k) {
-        if (L.phase == PH_NEAREST) { L.qhit = i; L.qkind = k; }
-        else { L.qhit = 1; return true; }
+RT_HD void w_sphere2(WLane &L, const f4 *g, int i, bool live) {
+    float b[2], det[2];
+    bool cand[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const f4 s = g[k];
+        const float vx = f_sub(L.qox, s.x), vy = f_sub(L.qoy, s.y), vz = f_sub(L.qoz, s.z);
+        b[k] = -dot3(vx, vy, vz, L.qdx, L.qdy, L.qdz);
+        det[k] = f_add(f_sub(f_mul(b[k], b[k]), dot3(vx, vy, vz, vx, vy, vz)), s.w);
+        cand[k] = live && det[k] > 0.f;
     }
-    return false;
+    if (warp_any(cand[0] || cand[1])) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests++;
+            const float sq = f_sqrt(det[k]);
+            const float i1 = f_sub(b[k], sq), i2 = f_add(b[k], sq);
+            const bool inside = i1 < 0.f;
+            const float t = inside ? i2 : i1;
+            if (cand[k] && i2 > 0.f && t < L.cumu) { L.cumu = t; L.qhit = i + k; L.qkind = inside ? -1 : 1; }
+        }
+    } else if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests += 2;
+}
+
+// Host-side reference loop over all primitives (used by tests/devsim): ascending index, strict '<' => the
+// lowest index keeps an exact tie (RNO:185-193); a shadow query skips lights (RNO:234).
+template <bool COUNT>
+RT_HD void w_test(WLane &L, const f4 g, int flag, int i) {
+    const bool live = !(L.phase == PH_SHADOW && ((flag & W_FLAG_LIGHT) || L.qhit >= 0));
+    if (flag & W_FLAG_SPHERE) w_sphere<COUNT>(L, g, i, live);
+    else w_plane<COUNT>(L, g, i, live);
+}
+
+// The primitive loop of one query round: runs of equal (type, is_light) in ascending index order
+// (ties: the lowest index keeps an exact tie because the acceptance test is a strict '<', RNO:185-193).
+// A run is skipped when no lane of the warp can still be affected by it: idle lanes, shadow queries that
+// are already blocked, and shadow queries in front of a light run (RNO:234) take no part.
+template <bool COUNT>
+RT_HD void w_query(WLane &L, const f4 *geom, const int *runs, int n_runs, bool active) {
+    for (int r = 0; r < n_runs; ++r) {
+        const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
+        const bool live = active && !(L.phase == PH_SHADOW && ((fl & W_FLAG_LIGHT) || L.qhit >= 0));
+        if (!warp_any(live)) continue;
+        int i = start;
+        const int end = start + count;
+        if (fl & W_FLAG_SPHERE) {
+            for (; i + 1 < end; i += 2) w_sphere2<COUNT>(L, geom + i, i, live);
+            if (i < end) w_sphere<COUNT>(L, geom[i], i, live);
+        } else {
+            for (; i < end; ++i) w_plane<COUNT>(L, geom[i], i, live);
+        }
+    }
 }
 
 RT_HD void w_normal(const WFrame &F, int prim, float px, float py, float pz, float &nx, float &ny, float &nz) {   // RNO:162-177
@@ -112,10 +172,10 @@ RT_HD void w_start_subsample(WLane &L, const WFrame &F) {
     const int tx = L.sub / 3 - 1, ty = L.sub % 3 - 1;
     const float SY = f_add(2.25f, f_mul((float)L.y, F.DY));
     const float SX = f_add(-3.0f, f_mul((float)L.x, F.DX));
-    float dx = f_sub(f_add(SX, f_mul(F.DX, f_div((float)tx, 2.0f))), 0.f);
-    float dy = f_sub(f_add(SY, f_mul(F.DY, f_div((float)ty, 2.0f))), 0.25f);
+    float dx = f_sub(f_add(SX, f_mul(F.DX, f_mul((float)tx, 0.5f))), 0.f);
+    float dy = f_sub(f_add(SY, f_mul(F.DY, f_mul((float)ty, 0.5f))), 0.25f);
     float dz = f_sub(0.f, -7.0f);
-    const float len = f_div(1.0f, f_sqrt(f_add(f_add(f_mul(dx, dx), f_mul(dy, dy)), f_mul(dz, dz))));
+    const float len = f_rcp(f_sqrt(f_add(f_add(f_mul(dx, dx), f_mul(dy, dy)), f_mul(dz, dz))));
     L.dx = f_mul(dx, len); L.dy = f_mul(dy, len); L.dz = f_mul(dz, len);
     L.weight = 1.0f; L.depth = 0; L.from = -1; L.kind = W_PRIMARY; L.r_index = 1.0f;
     L.tr = L.tg = L.tb = 1.0f;
@@ -200,7 +260,7 @@ RT_HD bool w_advance(WLane &L, const WFrame &F, f4 *q) {
         }
     } else {                                                           // shadow query finished
         if (COUNT) L.c_shadow++;
-        if (!L.qhit) w_shade(L, F, F.lights[L.li], L.qdx, L.qdy, L.qdz, 1.0f);   // a blocked light adds exactly 0
+        if (L.qhit < 0) w_shade(L, F, F.lights[L.li], L.qdx, L.qdy, L.qdz, 1.0f);   // a blocked light adds exactly 0
         L.li++;
         to_lights = true;
     }
@@ -211,12 +271,12 @@ RT_HD bool w_advance(WLane &L, const WFrame &F, f4 *q) {
             const f4 lg = F.geom[l];
             const float ex = f_sub(lg.x, L.px), ey = f_sub(lg.y, L.py), ez = f_sub(lg.z, L.pz);
             const float reach = f_sqrt(f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(ez, ez)));
-            const float inv = f_div(1.0f, reach);
+            const float inv = f_rcp(reach);
             const float Lx = f_mul(inv, ex), Ly = f_mul(inv, ey), Lz = f_mul(inv, ez);
             if (F.flags[l] & W_FLAG_SPHERE) {                          // only sphere lights cast shadows (RNO:223)
                 L.qox = f_add(L.px, f_mul(Lx, W_EPS)); L.qoy = f_add(L.py, f_mul(Ly, W_EPS)); L.qoz = f_add(L.pz, f_mul(Lz, W_EPS));
                 L.qdx = Lx; L.qdy = Ly; L.qdz = Lz;
-                L.cumu = reach; L.qhit = 0; L.phase = PH_SHADOW;
+                L.cumu = reach; L.qhit = -1; L.phase = PH_SHADOW;
                 return false;
             }
             w_shade(L, F, l, Lx, Ly, Lz, 1.0f);
@@ -285,7 +345,10 @@ RT_HD bool w_advance(WLane &L, const WFrame &F, f4 *q) {
 
 // RNO:436-447: min(255, (int)(acc * (256/9))), alpha 0.
 RT_HD uint32_t w_pack_pixel(float r, float g, float b) {
-    int ir = (int)f_mul(r, 28.0f), ig = (int)f_mul(g, 28.0f), ib = (int)f_mul(b, 28.0f);
+    // The reference is x86 code: (int) of a float outside the int range (its tracer does blow up to ~1e13 on a
+    // few pixels inside the front glass sphere) or of a NaN is cvttss2si's "integer indefinite" 0x80000000,
+    // which then fails `> 255` and truncates to byte 0.  CUDA's cvt would saturate to 255 instead.
+    int ir = x86_float_to_int(f_mul(r, 28.0f)), ig = x86_float_to_int(f_mul(g, 28.0f)), ib = x86_float_to_int(f_mul(b, 28.0f));
     if (ir > 255) ir = 255;
     if (ig > 255) ig = 255;
     if (ib > 255) ib = 255;

@@ -36,12 +36,13 @@ uint32_t devsim_cover(int w, int h, int rank, int world, int tile_rows, int32_t 
 
 // Whitted frame through the lane state machine (rows owned by rank/world/tile_rows only).
 void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_primitive *prims, int n,
-                    int rank, int world, int tile_rows, uint64_t *counters5) {
+                    int rank, int world, int tile_rows, uint64_t *counters5, float *acc_out /* NULL or w*h*3 */, int use_runs) {
     WSoA soa;
     build_w_soa(prims, n, soa);
     WFrame F;
     F.geom = soa.geom.data(); F.mat_a = soa.mat_a.data(); F.mat_b = soa.mat_b.data();
     F.flags = soa.flags.data(); F.lights = soa.lights.data(); F.rrad = soa.rrad.data();
+    F.runs = soa.runs.data(); F.n_runs = (int)soa.runs.size() / 3;
     F.n = n; F.n_lights = (int)soa.lights.size(); F.n_spheres = soa.n_spheres; F.n_planes = soa.n_planes;
     F.w = w; F.h = h;
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
@@ -58,12 +59,13 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
         memset(&L, 0, sizeof L);
         w_begin_pixel(L, F, x, y);
         for (;;) {
-            bool done = false;
-            for (int s = 0; s < F.n && !done; ++s) done = w_test<true>(L, F.geom[s], F.flags[s], s);
+            if (use_runs) w_query<true>(L, F.geom, F.runs, F.n_runs, true);                  // the kernel's loop
+            else for (int s = 0; s < F.n; ++s) w_test<true>(L, F.geom[s], F.flags[s], s);    // plain per-primitive loop
             if (w_advance<true>(L, F, queue)) break;
         }
         const uint32_t p = w_pack_pixel(L.ar, L.ag, L.ab);
         memcpy(pixels + ((size_t)y * w + x) * 4, &p, 4);
+        if (acc_out) { float *a = acc_out + ((size_t)y * w + x) * 3; a[0] = L.ar; a[1] = L.ag; a[2] = L.ab; }
         c[0] += L.c_nearest; c[1] += L.c_shadow; c[2] += L.c_sphere_tests; c[3] += L.c_plane_tests; c[4] += L.c_samples;
     }
     if (counters5) for (int k = 0; k < 5; k++) counters5[k] += c[k];
@@ -72,7 +74,7 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
 // smallpt passes through the lane state machine.  colors/seeds updated in place (CPU-twin indexing).
 void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera *cam, int w, int h,
                int pass0, int n_passes, int sum_mode, float *colors, uint32_t *seeds, uint32_t *pixels,
-               int rank, int world, int tile_rows, uint64_t *counters5) {
+               int rank, int world, int tile_rows, uint64_t *counters5, int chunk /* <=0: plain per-sphere loop */) {
     PtSoA soa;
     build_pt_soa(sph, n, soa);
     PtFrame F;
@@ -94,8 +96,11 @@ void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera
         memset(&L, 0, sizeof L);
         pt_begin_pixel(L, F, x, y, colors, seeds);
         for (;;) {
-            bool done = false;
-            for (int i = F.n - 1; i >= 0 && !done; --i) done = pt_test<true>(L, soa.geom[i], i);
+            if (chunk <= 0) for (int i = F.n - 1; i >= 0; --i) pt_test<true>(L, soa.geom[i], i, true);   // plain loop
+            else for (int hi = F.n; hi > 0; hi -= chunk) {                                               // the kernel's loops
+                const int lo = hi > chunk ? hi - chunk : 0;
+                pt_query_range<true>(L, soa.geom.data() + lo, lo, hi, true);
+            }
             if (pt_advance<true>(L, F)) break;
         }
         const size_t i = (size_t)(h - y - 1) * w + x;

@@ -45,7 +45,7 @@ def test_whitted_lanes_equal_oracle(devsim, orc, rt):
     prims = rt.whitted_create_scene(0)
     for (w, h) in [(120, 90), (37, 29)]:
         px, hits, ctr = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32), np.zeros(5, np.uint64)
-        devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, vp(ctr))
+        devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, vp(ctr), None, 1)
         px_o, hits_o, ctr_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32), np.zeros(5, np.uint64)
         orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, vp(ctr_o))
         assert np.array_equal(px, px_o) and np.array_equal(hits, hits_o)
@@ -56,10 +56,10 @@ def test_whitted_lanes_sharded_equal_unsharded(devsim, rt):
     prims = rt.whitted_create_scene(0)
     w, h = 50, 41
     full = np.zeros((h, w, 4), np.uint8)
-    devsim.devsim_whitted(vp(full), None, w, h, vp(prims), prims.size, 0, 1, 8, None)
+    devsim.devsim_whitted(vp(full), None, w, h, vp(prims), prims.size, 0, 1, 8, None, None, 1)
     parts = np.zeros((h, w, 4), np.uint8)
     for rank in range(3):
-        devsim.devsim_whitted(vp(parts), None, w, h, vp(prims), prims.size, rank, 3, 4, None)
+        devsim.devsim_whitted(vp(parts), None, w, h, vp(prims), prims.size, rank, 3, 4, None, None, 1)
     assert np.array_equal(full, parts)
 
 
@@ -70,7 +70,7 @@ def test_smallpt_lanes_equal_reference_fixture(devsim, rt, scene):
     for integ, tag in [(0, "pt"), (1, "dl")]:
         col, sd, pix = np.zeros(3 * w * h, np.float32), g["seeds_in"].copy(), np.zeros(w * h, np.uint32)
         devsim.devsim_pt(integ, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, g["passes"], 0,
-                         vp(col), vp(sd), vp(pix), 0, 1, 8, None)
+                         vp(col), vp(sd), vp(pix), 0, 1, 8, None, 1 << 30)
         assert np.array_equal(col.view(np.uint32), g[tag + "_colors"]), (scene, tag)
         assert np.array_equal(sd, g[tag + "_seeds"]) and np.array_equal(pix, g[tag + "_pixels"]), (scene, tag)
 
@@ -79,7 +79,7 @@ def test_smallpt_lane_counters_equal_oracle(devsim, orc, rt):
     g = load_smallpt_golden(rt, "cornell")
     w, h = g["w"], g["h"]
     col, sd, ctr = np.zeros(3 * w * h, np.float32), g["seeds_in"].copy(), np.zeros(5, np.uint64)
-    devsim.devsim_pt(0, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, 3, 0, vp(col), vp(sd), None, 0, 1, 8, vp(ctr))
+    devsim.devsim_pt(0, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, 3, 0, vp(col), vp(sd), None, 0, 1, 8, vp(ctr), 1 << 30)
     col_o, sd_o, ctr_o = np.zeros(3 * w * h, np.float32), g["seeds_in"].copy(), np.zeros(4, np.uint64)
     orc.oracle_pt_render(0, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, 3, vp(col_o), vp(sd_o), None, 2, vp(ctr_o))
     assert (ctr[4], ctr[0], ctr[1], ctr[2]) == tuple(ctr_o)

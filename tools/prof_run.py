@@ -1,0 +1,21 @@
+"""Small fixed workload for ncu: one Whitted 1080p frame and one Cornell 1024x768 x 16 spp launch."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as g
+rt = g.load()
+r = rt.Renderer(0)
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+if which in ("both", "whitted"):
+    prims = rt.whitted_create_scene(0)
+    r.whitted_upload(prims, 1920, 1080)
+    for _ in range(2):
+        r.whitted_launch()
+    r.sync()
+if which in ("both", "pt"):
+    sph, cam = rt.cornell_scene(1024, 768)
+    r.pt_resize(1024, 768, rt.reference_seeds(1024, 768)); r.pt_set_scene(sph); r.pt_set_camera(cam)
+    for _ in range(2):
+        r.pt_launch(0, 16)
+    r.sync()
+r.close()
+print("prof_run ok")
