@@ -187,6 +187,15 @@ void *rt_stream(rt_ctx *ctx);
  * analogue is the single in-order cl_command_queue every call shares (SPT/smallptGPU.cpp:463-467). */
 int rt_set_stream(rt_ctx *ctx, void *cuda_stream);
 
+/* Evaluates, ON THE DEVICE, the elementary functions the kernels use in place of the reference's libm
+ * calls, so that a test can compare them with the host libm the reference's CPU path binds to.
+ * op: 0 sinf+cosf (out: float[2n], sin then cos; SPT/geomfunc.h:66-67, 261-262), 1 expf (float[n];
+ * R323/raytracer_non_OpenCL.c:424-426), 2 toInt = gamma + 8-bit quantisation (int[n]; SPT/vec.h:62),
+ * 3 square root (float[2n]: the loops' grouped fast path, then __fsqrt_rn), 4 x^20 in double (double[n];
+ * R323/raytracer_non_OpenCL.c:270).  Diagnostics only; host buffers in and out. */
+enum { RT_SELFTEST_SINCOS = 0, RT_SELFTEST_EXPF = 1, RT_SELFTEST_GAMMA = 2, RT_SELFTEST_SQRT = 3, RT_SELFTEST_POW20 = 4 };
+int rt_selftest_math(rt_ctx *ctx, int op, const float *in, void *out, uint64_t n);
+
 /* ------------------------------------------------------------------ host-side scene helpers
  * (kept from the reference's host code; pure CPU, no device needed) */
 

