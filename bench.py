@@ -158,13 +158,6 @@ def run_reference(args, rank):
 
 
 # --------------------------------------------------------------------------------------------- our arm
-class DevArray:
-    """Exposes a device pointer of the renderer to torch (plumbing for collectives)."""
-
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -178,7 +171,7 @@ def run_ours(args, rank, world, local_rank):
     info = r.device_info()
     peaks = measured_peaks()
     w, h = WEAK_SIZES.get(world, (BASE_W, BASE_H * world))
-    tile = next(t for t in (8, 4, 2, 1) if h % t == 0 and (h // t) % world == 0)
+    tile = rt.pick_tile_rows(h, world)
     prims = rt.whitted_create_scene(0)
     r.set_shard(rank, world, tile)
 
@@ -197,23 +190,12 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- device-resident steps
     ptr, nbytes = r.device_buffer(rt.BUF_WHITTED_PIXELS)
-    fb = torch.as_tensor(DevArray(ptr, (h // tile, tile * w), "<u4"), device="cuda")
-    my_tiles = fb[rank::world]
-    staging = [torch.empty_like(fb[q::world]) for q in range(world)] if (rank == 0 and world > 1) else None
+    fb = torch.as_tensor(rt.DeviceArray(ptr, (h, w), "<i4"), device="cuda")      # the context's framebuffer, as a torch view
+    staging = rt.gather_staging(fb, world, tile) if (rank == 0 and world > 1) else None
     flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
     def gather():
-        if world == 1:
-            return
-        if rank == 0:
-            ops = [dist.P2POp(dist.irecv, staging[q], q) for q in range(1, world)]
-            for w_ in dist.batch_isend_irecv(ops):
-                w_.wait()
-            for q in range(1, world):
-                fb[q::world] = staging[q]
-        else:
-            for w_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, my_tiles.contiguous(), 0)]):
-                w_.wait()
+        rt.gather_row_tiles(fb, rank, world, tile, staging)
 
     def step():
         r.whitted_launch()

@@ -193,6 +193,86 @@ def reference_seeds(w, h, seed=1):
     return np.maximum(s, 2).astype(np.uint32)
 
 
+# ----------------------------------------------------------------------------- multi-GPU plumbing
+# One process per GPU (torchrun); torch.distributed carries the only two exchanges the path has
+# (SURVEY.md 8e): the gather of the interleaved row tiles to rank 0, and the sum of the per-rank
+# accumulation buffers in the sample-sharded mode.  Works on CUDA tensors over NCCL/NVLink and on CPU
+# tensors over gloo (the world_size-2 tests).
+class DeviceArray:
+    """Wraps a device pointer handed out by rt_device_buffer for torch.as_tensor(..., device="cuda")."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def pick_tile_rows(h, world):
+    """Largest tile height of 8, 4, 2, 1 rows that deals the frame's tiles evenly over the ranks (else 8)."""
+    for t in (8, 4, 2, 1):
+        if h % t == 0 and (h // t) % world == 0:
+            return t
+    return 8
+
+
+def owned_rows(h, rank, world, tile_rows):
+    """Row indices rendered by `rank` under rt_set_shard(rank, world, tile_rows)."""
+    return [y for y in range(h) if (y // tile_rows) % world == rank]
+
+
+def _tile_views(frame, world, tile_rows):
+    """Per-rank (strided view of the full tiles, view of the ragged last tile or None)."""
+    h = frame.shape[0]
+    n_full = h // tile_rows
+    body = frame[:n_full * tile_rows].reshape(n_full, -1)           # [tile, tile_rows * row_elems], a view
+    tail_owner = n_full % world if h % tile_rows else -1
+    return [(body[q::world], frame[n_full * tile_rows:].reshape(-1) if q == tail_owner else None) for q in range(world)]
+
+
+def gather_row_tiles(frame, rank, world, tile_rows, staging=None):
+    """frame: contiguous [h, ...] tensor whose rows owned by this rank are valid.  After the call rank 0's
+    frame is complete.  Each rank sends only its own rows, as one message ((world-1)/world of the frame
+    crosses the links); rank 0 de-interleaves with strided copies."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return frame
+    if frame.dtype == torch.uint32:                                  # torch has few uint32 kernels
+        frame = frame.view(torch.int32)
+    views = _tile_views(frame, world, tile_rows)
+    sizes = [v.numel() + (t.numel() if t is not None else 0) for v, t in views]
+    if rank == 0:
+        if staging is None:
+            staging = [torch.empty(sizes[q], dtype=frame.dtype, device=frame.device) for q in range(world)]
+        for r_ in dist.batch_isend_irecv([dist.P2POp(dist.irecv, staging[q], q) for q in range(1, world)]):
+            r_.wait()
+        for q in range(1, world):
+            v, t = views[q]
+            v.copy_(staging[q][:v.numel()].view(v.shape))
+            if t is not None:
+                t.copy_(staging[q][v.numel():])
+    else:
+        v, t = views[rank]
+        mine = v.reshape(-1) if t is None else torch.cat([v.reshape(-1), t])
+        for r_ in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine.contiguous(), 0)]):
+            r_.wait()
+    return frame
+
+
+def gather_staging(frame, world, tile_rows):
+    """Pre-allocated receive buffers for gather_row_tiles on rank 0 (so timed steps do not allocate)."""
+    import torch
+    if frame.dtype == torch.uint32:
+        frame = frame.view(torch.int32)
+    views = _tile_views(frame, world, tile_rows)
+    return [torch.empty(v.numel() + (t.numel() if t is not None else 0), dtype=frame.dtype, device=frame.device) for v, t in views]
+
+
+def allreduce_sums(colors):
+    """Sample-sharded mode: adds the per-rank float accumulation buffers in place (ncclAllReduce, sum)."""
+    import torch.distributed as dist
+    dist.all_reduce(colors, op=dist.ReduceOp.SUM)
+    return colors
+
+
 # ----------------------------------------------------------------------------- the renderer
 class Renderer:
     """One context = one GPU.  Method names follow the reference's host entry points."""
