@@ -17,7 +17,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+# RT_B200_LIB lets tools/variants.sh point the binding at an A/B build; the default is the in-tree product.
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
 
 # ----------------------------------------------------------------------------- POD layouts
 SPHERE_DTYPE = np.dtype([("rad", "<f4"), ("p", "<f4", 3), ("e", "<f4", 3), ("c", "<f4", 3), ("refl", "<i4")])
@@ -40,7 +41,7 @@ class Counters(C.Structure):
 
 RT_DIFF_, RT_SPEC_, RT_REFR_ = 0, 1, 2
 RT_OK, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_ARG, RT_ERR_STATE, RT_ERR_CAPACITY, RT_ERR_IO = 0, -1, -2, -3, -4, -5, -6
-TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM = 0, 1, 2
+TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER = 0, 1, 2, 3
 BUF_WHITTED_PIXELS, BUF_WHITTED_HITS, BUF_PT_PIXELS, BUF_PT_COLORS, BUF_PT_SEEDS = 0, 1, 2, 3, 4
 
 # Every symbol include/rt_b200.h declares: name -> (restype, argtypes).

@@ -30,6 +30,9 @@ struct rt_ctx {
     int pt_max_resident_bytes = 96 * 1024;
     int pt_chunk_spheres = 3072;                   // 48 KB of (p, rad^2) per chunk
     int max_blocks_per_sm = 0;
+    int whitted_sort = 1;                          // cost-sorted work order (scheduling pre-pass)
+    uint32_t *d_worder = nullptr; size_t worder_cap = 0;
+    unsigned *d_wclass = nullptr;
     // Whitted
     int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_nr = 0, w_want_hits = 0;
     f4 *d_wgeom = nullptr, *d_wma = nullptr, *d_wmb = nullptr;
@@ -126,7 +129,7 @@ void rt_destroy(rt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns,
+    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
     for (void *b : bufs) if (b) cudaFree(b);
@@ -176,6 +179,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_PT_MAX_RESIDENT_BYTES: if (value < 0) break; ctx->pt_max_resident_bytes = value; return RT_OK;
         case RT_TUNE_PT_CHUNK_SPHERES: if (value < 1) break; ctx->pt_chunk_spheres = value; return RT_OK;
         case RT_TUNE_MAX_BLOCKS_PER_SM: if (value < 0) break; ctx->max_blocks_per_sm = value; return RT_OK;
+        case RT_TUNE_WHITTED_COST_ORDER: ctx->whitted_sort = value ? 1 : 0; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -234,9 +238,21 @@ int rt_whitted_launch(rt_ctx *ctx) {
     p.pixels = ctx->d_wpixels; p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
     p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
     p.stage_materials = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 1) <= 32 * 1024 ? 1 : 0;
+    p.order = nullptr; p.class_counts = nullptr;
+    p.n_valid = (uint32_t)p.shard.local_rows * (uint32_t)ctx->w_w;
+    if (ctx->whitted_sort && p.n_items) {
+        if (p.n_items > ctx->worder_cap) {
+            if (ctx->d_worder) cudaFree(ctx->d_worder);
+            ctx->d_worder = nullptr; ctx->worder_cap = 0;
+            CK(cudaMalloc((void **)&ctx->d_worder, 3 * (size_t)p.n_items * sizeof(uint32_t)));
+            ctx->worder_cap = p.n_items;
+        }
+        if (!ctx->d_wclass) CK(cudaMalloc((void **)&ctx->d_wclass, 4 * sizeof(unsigned)));
+        p.order = ctx->d_worder; p.class_counts = ctx->d_wclass;
+    }
     CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
-    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches++; }
+    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += p.order ? 2 : 1; }
     return RT_OK;
 }
 

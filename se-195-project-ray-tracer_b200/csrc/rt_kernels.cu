@@ -17,8 +17,6 @@
 //     what makes hit IDs and RNG streams bit-identical to the reference's CPU path.
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include "pt_lane.cuh"
-#include "whitted_lane.cuh"
 #include "rt_kernels.h"
 
 namespace rtb {
@@ -46,7 +44,7 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 // loop inside the kernel.  CHUNKED = the (p, rad^2) array does not fit in shared memory: the CTA walks
 // it in chunks, all warps in lock-step (one __syncthreads pair per chunk per query round).
 template <bool COUNT, bool CHUNKED>
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS)
 pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, uint32_t *pixels,
           unsigned *work_counter, unsigned long long *counters, int chunk) {
     extern __shared__ f4 s_geom[];
@@ -123,8 +121,8 @@ __global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, 
 // and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
 template <bool COUNT>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
-whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *work_counter,
-               unsigned long long *counters, int stage_materials) {
+whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
+               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, int stage_materials) {
     extern __shared__ f4 s_raw[];
     // layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | runs[3*n_runs] | rrad[n] (optional) | lights[n_lights] (optional)
     f4 *s_geom = s_raw;
@@ -163,7 +161,12 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *
         if (need) {
             if (item < n_items) {
                 int x, y;
-                if (item_to_pixel(S, F.w, item, x, y)) w_begin_pixel(L, F, x, y);
+                uint32_t it = item;
+                if (order) {                     // walk the cost classes in turn (see whitted_classify_kernel)
+                    const uint32_t n0 = class_counts[0], n1 = class_counts[1];
+                    it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
+                }
+                if (item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
             } else exhausted = true;
         }
         const bool active = L.phase != PH_IDLE;
@@ -182,6 +185,49 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *pixels, unsigned *
             atomicAdd(&counters[0], (unsigned long long)a); atomicAdd(&counters[1], (unsigned long long)b);
             atomicAdd(&counters[2], (unsigned long long)c); atomicAdd(&counters[3], (unsigned long long)d);
             atomicAdd(&counters[4], (unsigned long long)e);
+        }
+    }
+}
+
+// Scheduling pre-pass for the Whitted frame.  A pixel is one indivisible work unit (its float accumulation
+// order is fixed), and its cost varies by ~10x: a pixel that looks at a refracting sphere grows a ray tree
+// of up to 63 rays per sub-sample, a pixel that looks at a wall traces 9 + 27 rays.  With pixels handed out
+// in screen order the expensive ones (the spheres stand on the floor, bottom rows) come last and the frame
+// ends in a long tail of warps with one busy lane (ncu: SMs idle 25 % of the frame).  This kernel traces the
+// centre primary ray of every pixel (1/60 of the frame's work), classifies the pixel by the material it
+// hits -- 0: refracting, 1: reflecting, 2: neither / miss -- and appends it to that class's list.  The
+// render kernel then walks list 0, 1, 2: expensive pixels first, and warps that hold pixels of one class.
+// It changes WHEN a pixel is rendered, never what is computed for it.
+#define W_COST_CLASSES 3
+__global__ void __launch_bounds__(W_THREADS)
+whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* W_COST_CLASSES x n_items */, unsigned *class_counts) {
+    extern __shared__ f4 s_raw[];
+    f4 *s_geom = s_raw;
+    int *s_runs = (int *)(s_geom + F.n);
+    for (int i = threadIdx.x; i < F.n; i += blockDim.x) s_geom[i] = F.geom[i];
+    for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) s_runs[i] = F.runs[i];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t per_pass = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n_items; base += per_pass) {   // warp-uniform trip count
+        const uint32_t item = base + threadIdx.x;
+        int x = 0, y = 0;
+        const bool valid = item < n_items && item_to_pixel(S, F.w, item, x, y);
+        WLane L;
+        L.phase = PH_IDLE; L.qhit = -1; L.cumu = 0.f; L.qkind = 0;
+        L.qox = L.qoy = L.qoz = 0.f; L.qdx = L.qdy = L.qdz = 0.f;
+        if (valid) { L.x = x; L.y = y; L.sub = 4; w_start_subsample(L, F); }
+        w_query<false>(L, s_geom, s_runs, F.n_runs, valid);
+        int cls = W_COST_CLASSES - 1;
+        if (valid && L.qhit >= 0) cls = F.mat_b[L.qhit].y > 0.f ? 0 : (F.mat_a[L.qhit].w > 0.f ? 1 : 2);
+        const uint32_t below = (1u << lane) - 1u;
+#pragma unroll
+        for (int c = 0; c < W_COST_CLASSES; c++) {
+            const uint32_t m = __ballot_sync(FULL_MASK, valid && cls == c);
+            uint32_t b0 = 0;
+            if (lane == 0 && m) b0 = atomicAdd(&class_counts[c], (unsigned)__popc(m));
+            b0 = __shfl_sync(FULL_MASK, b0, 0);
+            if (valid && cls == c) lists[(size_t)c * n_items + b0 + __popc(m & below)] = item;
         }
     }
 }
@@ -259,7 +305,7 @@ size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_materia
 
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_materials);
-    typedef void (*kern_t)(WFrame, Shard, uint32_t, uint32_t *, unsigned *, unsigned long long *, int);
+    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *, int);
     kern_t k = p.count ? whitted_kernel<true> : whitted_kernel<false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -269,7 +315,22 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     long grid = (long)nb * p.sm_count;
     const long need = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
     if (grid > need) grid = need > 0 ? need : 1;
-    k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, p.pixels, p.work_counter, p.counters,
-                                                  p.stage_materials);
+    uint32_t n_work = p.n_items;
+    if (p.order) {
+        // scheduling pre-pass: order[] = expensive pixels first; the number of valid entries is known on the host
+        size_t csmem = (size_t)p.frame.n * sizeof(f4) + (size_t)p.frame.n_runs * 3 * sizeof(int);
+        if (csmem < 16) csmem = 16;
+        e = cudaFuncSetAttribute(whitted_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(p.class_counts, 0, W_COST_CLASSES * sizeof(unsigned), stream);
+        if (e != cudaSuccess) return e;
+        long cgrid = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
+        if (cgrid > (long)p.sm_count * 16) cgrid = (long)p.sm_count * 16;
+        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame, p.shard, p.n_items, p.order, p.class_counts);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        n_work = p.n_valid;
+    }
+    k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
+                                                  p.counters, p.stage_materials);
     return cudaGetLastError();
 }

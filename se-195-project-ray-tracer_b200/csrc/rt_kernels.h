@@ -5,9 +5,22 @@
 #include "pt_lane.cuh"
 #include "whitted_lane.cuh"
 
+// Launch shape (overridable with -D for the A/B builds of tools/variants.sh).
+#ifndef PT_THREADS
 #define PT_THREADS 256
+#endif
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 1
+#endif
+#ifndef W_THREADS
 #define W_THREADS 128
-#define W_MIN_BLOCKS 8      /* 64 registers per thread: 32 resident warps per SM */
+#endif
+#ifndef W_MIN_BLOCKS
+#define W_MIN_BLOCKS 1
+#endif
+#ifndef W_PLANE_PAIRS
+#define W_PLANE_PAIRS 1
+#endif
 
 struct PtLaunch {
     rtb::PtFrame frame;
@@ -29,6 +42,9 @@ struct WLaunch {
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
     int count, sm_count, stage_materials, max_blocks_per_sm;
+    uint32_t *order;            // NULL: screen order; else scratch of 3 x n_items entries: one work list per cost class
+    unsigned *class_counts;     // 3 x u32 scratch: entries in each list
+    uint32_t n_valid;           // pixels owned by this rank (n_items minus the padding of the 8x4 blocks)
 };
 
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream);

@@ -176,8 +176,10 @@ RT_HD void w_query(WLane &L, const f4 *geom, const int *runs, int n_runs, bool a
             for (; i + 1 < end; i += 2) w_sphere2<COUNT>(L, geom + i, i, live);
             if (i < end) w_sphere<COUNT>(L, geom[i], i, live);
         } else {
+#if !defined(W_PLANE_PAIRS) || W_PLANE_PAIRS
             for (; i + 1 < end; i += 2) w_plane2<COUNT>(L, geom + i, i, live);
-            if (i < end) w_plane<COUNT>(L, geom[i], i, live);
+#endif
+            for (; i < end; ++i) w_plane<COUNT>(L, geom[i], i, live);
         }
     }
 }

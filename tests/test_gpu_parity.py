@@ -33,7 +33,7 @@ def test_device_is_a_b200_and_kernels_launch(gpu):
     assert info["sm_count"] > 0
     before = gpu.launch_count()
     gpu.whitted_render(__import__("rt_b200").whitted_create_scene(0), 32, 24)
-    assert gpu.launch_count() == before + 1
+    assert gpu.launch_count() == before + 2          # cost-order pre-pass + the render kernel
 
 
 def test_device_sincos_equals_host_libm_on_the_whole_domain(gpu, orc):
@@ -106,6 +106,24 @@ def test_whitted_scene1_and_open_scene(gpu, orc, rt):
         px_o, hits_o, _ = oracle_whitted(orc, prims, 240, 180)
         assert (hits_o == -1).any() or not expect_miss
         assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
+
+
+def test_whitted_cost_ordered_schedule_changes_nothing(gpu, rt):
+    """The scheduling pre-pass (expensive pixels first) only reorders work: same bytes with it on or off,
+    on sizes with padding items and under sharding."""
+    prims = rt.whitted_create_scene(0)
+    try:
+        for (w, h, rank, world, tile) in [(333, 250, 0, 1, 8), (61, 37, 1, 3, 4), (640, 360, 0, 1, 8)]:
+            gpu.set_shard(rank, world, tile)
+            gpu.set_tuning(rt.TUNE_WHITTED_COST_ORDER, 1)
+            a, ha = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+            gpu.set_tuning(rt.TUNE_WHITTED_COST_ORDER, 0)
+            b, hb = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+            rows = np.array([(y // tile) % world == rank for y in range(h)])
+            assert np.array_equal(a[rows], b[rows]) and np.array_equal(ha[rows], hb[rows]) and a[rows].any()
+    finally:
+        gpu.set_shard(0, 1, 8)
+        gpu.set_tuning(rt.TUNE_WHITTED_COST_ORDER, 1)
 
 
 def test_whitted_counters_equal_oracle(gpu, orc, rt):
