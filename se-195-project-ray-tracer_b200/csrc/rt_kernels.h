@@ -6,11 +6,14 @@
 #include "whitted_lane.cuh"
 
 // Launch shape (overridable with -D for the A/B builds of tools/variants.sh).
+// smallpt: 128-thread CTAs capped at 64 registers (8 CTAs = 32 warps per SM) measured 6 % faster on Cornell than
+// 256 threads at the 65 registers ptxas picks on its own, which costs a whole CTA per SM (profiles/r01_ab_variants.txt).
+// Whitted: left to ptxas (83 registers, 20 warps per SM) -- every cap tried was slower.
 #ifndef PT_THREADS
-#define PT_THREADS 256
+#define PT_THREADS 128
 #endif
 #ifndef PT_MIN_BLOCKS
-#define PT_MIN_BLOCKS 1
+#define PT_MIN_BLOCKS 8
 #endif
 #ifndef W_THREADS
 #define W_THREADS 128
