@@ -172,9 +172,17 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
         const bool active = L.phase != PH_IDLE;
         if (!__any_sync(FULL_MASK, active || !exhausted)) break;
 
-        w_query<COUNT>(L, s_geom, s_runs, F.n_runs, active);
-
-        if (active && w_advance<COUNT>(L, F, queue))
+        // round 1: every lane with a ray finds its nearest hit; round 2 (repeated while lights remain): every lane
+        // that hit a surface tests up to three shadow rays at once; then the finished rays are folded into their pixels.
+        const bool nq = L.phase == PH_NEAREST;
+        w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
+        if (nq) w_after_nearest<COUNT>(L, F);
+        while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
+            const bool sq = L.phase == PH_SHADOW;
+            w_query_shadow<COUNT>(L, s_geom, s_runs, F.n_runs, sq);
+            if (sq) w_after_shadow<COUNT>(L, F);
+        }
+        if (L.phase == PH_FINAL && w_finalize<COUNT>(L, F, queue))
             pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(L.ar, L.ag, L.ab);
     }
 
@@ -217,7 +225,7 @@ whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* 
         L.phase = PH_IDLE; L.qhit = -1; L.cumu = 0.f; L.qkind = 0;
         L.qox = L.qoy = L.qoz = 0.f; L.qdx = L.qdy = L.qdz = 0.f;
         if (valid) { L.x = x; L.y = y; L.sub = 4; w_start_subsample(L, F); }
-        w_query<false>(L, s_geom, s_runs, F.n_runs, valid);
+        w_query_nearest<false>(L, s_geom, s_runs, F.n_runs, valid);
         int cls = W_COST_CLASSES - 1;
         if (valid && L.qhit >= 0) cls = F.mat_b[L.qhit].y > 0.f ? 0 : (F.mat_a[L.qhit].w > 0.f ? 1 : 2);
         const uint32_t below = (1u << lane) - 1u;

@@ -5,9 +5,12 @@
 // nine sub-samples in the reference's order (tx outer, ty inner), each expanded breadth-first
 // through a FIFO of secondary rays (RNO:30-40, 330-433), because the float accumulation order
 // inside a pixel is part of the result.  As in pt_lane.cuh the control flow is cut into RAY QUERIES:
-// a nearest-hit query over all primitives (RNO:185-193) or a hard-shadow query over the non-light
-// primitives that stops at the first blocker (RNO:232-240).  w_advance() runs everything between two
-// queries: shading, accumulation, spawning of the reflected / refracted children, next sub-sample.
+// a nearest-hit query over all primitives (RNO:185-193), then ONE batched hard-shadow query in which the
+// lane tests up to three shadow rays (one per light, RNO:206-241) against the non-light primitives at
+// once.  Every warp alternates the two rounds, so that all of its lanes run the same kind of query (a
+// shadow lane never rides along a nearest loop, and the primitive record / loop overhead is shared by three
+// rays).  Between the rounds: w_after_nearest (hit point, shadow-ray set-up), w_after_shadow (shading in
+// light order) and w_finalize (accumulation, reflected / refracted children, next ray / sub-sample).
 #pragma once
 #include "rt_math.cuh"
 #include "pt_lane.cuh"   // f4, PH_*, Shard
@@ -18,6 +21,8 @@ namespace rtb {
 #define W_FAR 10000000.0f        /* RNO:181 */
 #define W_TRACEDEPTH 5           /* RNO:4   */
 #define W_QUEUE_SLOTS 32         /* a breadth-first queue over a depth-5 binary ray tree never holds more */
+#define W_SHADOW_BATCH 3          /* shadow rays per lane per shadow round */
+#define PH_FINAL 3                /* the current ray is complete: w_finalize() folds it into the pixel */
 #define W_FLAG_SPHERE 1
 #define W_FLAG_LIGHT 2
 enum { W_PRIMARY = 0, W_REFLECTED = 1, W_REFRACTED = 2 };   /* RNO:59-63 */
@@ -50,6 +55,10 @@ struct WLane {
     float dist; int hit, hkind;                     // result of the nearest query while lights are processed
     float px, py, pz;                               // intersection point
     float cr, cg, cb;                               // colour gathered for this ray
+    float sox[W_SHADOW_BATCH], soy[W_SHADOW_BATCH], soz[W_SHADOW_BATCH];   // shadow rays of the current batch: origins,
+    float slx[W_SHADOW_BATCH], sly[W_SHADOW_BATCH], slz[W_SHADOW_BATCH];   //  unit directions to lights li .. li+ns-1
+    float sreach[W_SHADOW_BATCH];                   //  and distances to them
+    int ns, sblk;                                   // rays in the batch; bit k set = ray k is blocked
     int li, phase;
     uint32_t c_nearest, c_shadow, c_samples;
     uint64_t c_sphere_tests, c_plane_tests;
@@ -151,36 +160,99 @@ RT_HD void w_sphere2(WLane &L, const f4 *g, int i, bool live) {
     } else if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests += 2;
 }
 
-// Host-side reference loop over all primitives (used by tests/devsim): ascending index, strict '<' => the
-// lowest index keeps an exact tie (RNO:185-193); a shadow query skips lights (RNO:234).
+// Nearest-hit round: runs of equal (type, is_light) in ascending index order (ties: the lowest index keeps
+// an exact tie because the acceptance test is a strict '<', RNO:185-193).  `has` = this lane has a ray.
 template <bool COUNT>
-RT_HD void w_test(WLane &L, const f4 g, int flag, int i) {
-    const bool live = !(L.phase == PH_SHADOW && ((flag & W_FLAG_LIGHT) || L.qhit >= 0));
-    if (flag & W_FLAG_SPHERE) w_sphere<COUNT>(L, g, i, live);
-    else w_plane<COUNT>(L, g, i, live);
-}
-
-// The primitive loop of one query round: runs of equal (type, is_light) in ascending index order
-// (ties: the lowest index keeps an exact tie because the acceptance test is a strict '<', RNO:185-193).
-// A run is skipped when no lane of the warp can still be affected by it: idle lanes, shadow queries that
-// are already blocked, and shadow queries in front of a light run (RNO:234) take no part.
-template <bool COUNT>
-RT_HD void w_query(WLane &L, const f4 *geom, const int *runs, int n_runs, bool active) {
+RT_HD void w_query_nearest(WLane &L, const f4 *geom, const int *runs, int n_runs, bool has) {
+    if (!warp_any(has)) return;
     for (int r = 0; r < n_runs; ++r) {
         const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
-        const bool live = active && !(L.phase == PH_SHADOW && ((fl & W_FLAG_LIGHT) || L.qhit >= 0));
-        if (!warp_any(live)) continue;
         int i = start;
         const int end = start + count;
         if (fl & W_FLAG_SPHERE) {
-            for (; i + 1 < end; i += 2) w_sphere2<COUNT>(L, geom + i, i, live);
-            if (i < end) w_sphere<COUNT>(L, geom[i], i, live);
+            for (; i + 1 < end; i += 2) w_sphere2<COUNT>(L, geom + i, i, has);
+            if (i < end) w_sphere<COUNT>(L, geom[i], i, has);
         } else {
 #if !defined(W_PLANE_PAIRS) || W_PLANE_PAIRS
-            for (; i + 1 < end; i += 2) w_plane2<COUNT>(L, geom + i, i, live);
+            for (; i + 1 < end; i += 2) w_plane2<COUNT>(L, geom + i, i, has);
 #endif
-            for (; i < end; ++i) w_plane<COUNT>(L, geom[i], i, live);
+            for (; i < end; ++i) w_plane<COUNT>(L, geom[i], i, has);
         }
+    }
+}
+
+// Shadow round, one primitive against the lane's (up to) three shadow rays.  Only the boolean matters
+// ("is there a non-light primitive with 0 < dist < distance to the light", RNO:232-240), so:
+//   sphere: det > 0, far root > 0, and the entry root (or the far root when the origin is inside) < reach;
+//           the three square roots share one warp vote;
+//   plane:  dist = num/d is never formed unless the comparison is within rounding distance of the limit:
+//           with m = reach*|d| (rounded), |num| < m*(1-2^-21) proves 0 < dist < reach and
+//           |num| > m*(1+2^-21) proves dist >= reach (same error analysis as pre-filter B above; the quotient
+//           is normal because |num| > 1e-30 and |d| < 1e7); only the sliver in between takes the division.
+template <bool COUNT>
+RT_HD void w_shadow_sphere(WLane &L, const f4 g, bool has) {
+    float b[W_SHADOW_BATCH], det[W_SHADOW_BATCH];
+    bool cand[W_SHADOW_BATCH];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < W_SHADOW_BATCH; k++) {
+        const bool alive = has && k < L.ns && !((L.sblk >> k) & 1);
+        if (COUNT && alive) L.c_sphere_tests++;
+        const float vx = f_sub(L.sox[k], g.x), vy = f_sub(L.soy[k], g.y), vz = f_sub(L.soz[k], g.z);
+        b[k] = -dot3(vx, vy, vz, L.slx[k], L.sly[k], L.slz[k]);
+        det[k] = f_add(f_sub(f_mul(b[k], b[k]), dot3(vx, vy, vz, vx, vy, vz)), g.w);
+        cand[k] = alive && det[k] > 0.f;
+        any = any || cand[k];
+    }
+    if (warp_any(any)) {
+        float sq[W_SHADOW_BATCH];
+        sqrt_group<W_SHADOW_BATCH>(det, sq);
+#pragma unroll
+        for (int k = 0; k < W_SHADOW_BATCH; k++) {
+            const float i1 = f_sub(b[k], sq[k]), i2 = f_add(b[k], sq[k]);
+            const float t = i1 < 0.f ? i2 : i1;
+            if (cand[k] && i2 > 0.f && t < L.sreach[k]) L.sblk |= 1 << k;
+        }
+    }
+}
+template <bool COUNT>
+RT_HD void w_shadow_plane(WLane &L, const f4 g, bool has) {
+    float d[W_SHADOW_BATCH], num[W_SHADOW_BATCH];
+    bool ambiguous[W_SHADOW_BATCH];
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < W_SHADOW_BATCH; k++) {
+        const bool alive = has && k < L.ns && !((L.sblk >> k) & 1);
+        if (COUNT && alive) L.c_plane_tests++;
+        d[k] = dot3(g.x, g.y, g.z, L.slx[k], L.sly[k], L.slz[k]);
+        num[k] = -f_add(dot3(g.x, g.y, g.z, L.sox[k], L.soy[k], L.soz[k]), g.w);
+        const float an = fabsf(num[k]), ad = fabsf(d[k]);
+        const bool sign_ok = alive && d[k] != 0.f && num[k] != 0.f && ((num[k] > 0.f) == (d[k] > 0.f));
+        const float m = f_mul(L.sreach[k], ad);
+        const bool sure_hit = an < f_mul(m, 0.999999523162841796875f) && an > 1e-30f && m < 1e30f && ad < 1e7f;
+        const bool sure_miss = an > f_mul(m, 1.000000476837158203125f) && m > 1e-30f;
+        if (sign_ok && sure_hit) L.sblk |= 1 << k;
+        ambiguous[k] = sign_ok && !sure_hit && !sure_miss;
+        any = any || ambiguous[k];
+    }
+    if (warp_any(any)) {
+#pragma unroll
+        for (int k = 0; k < W_SHADOW_BATCH; k++) {
+            const float dist = f_div(num[k], d[k]);
+            if (ambiguous[k] && dist > 0.f && dist < L.sreach[k]) L.sblk |= 1 << k;
+        }
+    }
+}
+template <bool COUNT>
+RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs, bool has) {
+    for (int r = 0; r < n_runs; ++r) {
+        const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
+        if (fl & W_FLAG_LIGHT) continue;                                   // RNO:234: lights cast no shadow
+        const bool open = has && L.sblk != (1 << L.ns) - 1;                // some ray of this lane is still unblocked
+        if (!warp_any(open)) return;                                       // the `break` of RNO:237, for the whole warp
+        const int end = start + count;
+        if (fl & W_FLAG_SPHERE) for (int i = start; i < end; ++i) w_shadow_sphere<COUNT>(L, geom[i], has);
+        else                    for (int i = start; i < end; ++i) w_shadow_plane<COUNT>(L, geom[i], has);
     }
 }
 
@@ -267,52 +339,78 @@ RT_HD void w_shade(WLane &L, const WFrame &F, int l, float Lx, float Ly, float L
     }
 }
 
-// Runs everything between two queries.  Returns true when the pixel is finished (L.ar/ag/ab final).
-template <bool COUNT>
-RT_HD bool w_advance(WLane &L, const WFrame &F, f4 *q) {
-    bool to_lights;
-    if (L.phase == PH_NEAREST) {
-        if (COUNT) { L.c_nearest++; L.c_sphere_tests += (uint32_t)F.n_spheres; L.c_plane_tests += (uint32_t)F.n_planes; }
-        L.dist = L.cumu; L.hit = L.qhit; L.hkind = L.qkind;
-        L.cr = L.cg = L.cb = 0.f;
-        to_lights = false;
-        if (L.hit >= 0) {
-            if (F.flags[L.hit] & W_FLAG_LIGHT) {                       // RNO:197-200
-                const f4 ma = F.mat_a[L.hit];
-                L.cr = ma.x; L.cg = ma.y; L.cb = ma.z;
-            } else {
-                L.px = f_add(L.qox, f_mul(L.qdx, L.dist));
-                L.py = f_add(L.qoy, f_mul(L.qdy, L.dist));
-                L.pz = f_add(L.qoz, f_mul(L.qdz, L.dist));
-                L.li = 0;
-                to_lights = true;
-            }
-        }
-    } else {                                                           // shadow query finished
-        if (COUNT) L.c_shadow++;
-        if (L.qhit < 0) w_shade(L, F, F.lights[L.li], L.qdx, L.qdy, L.qdz, 1.0f);   // a blocked light adds exactly 0
+// Sets up the next batch of shadow rays (lights li, li+1, ... in index order, RNO:206-241), or marks the
+// ray complete when no light is left.  A light that is not a sphere casts no shadow ray (RNO:223) and is
+// shaded on the spot -- but only when no batch is pending before it, so that the float accumulation keeps
+// the reference's light order.
+RT_HD void w_light_vector(const WFrame &F, const WLane &L, int l, float &Lx, float &Ly, float &Lz, float &reach) {
+    const f4 lg = F.geom[l];
+    const float ex = f_sub(lg.x, L.px), ey = f_sub(lg.y, L.py), ez = f_sub(lg.z, L.pz);
+    reach = f_sqrt(f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(ez, ez)));
+    const float inv = f_rcp(reach);
+    Lx = f_mul(inv, ex); Ly = f_mul(inv, ey); Lz = f_mul(inv, ez);
+}
+RT_HD void w_next_shadow_batch(WLane &L, const WFrame &F) {
+    for (;;) {
+        if (L.li >= F.n_lights) { L.phase = PH_FINAL; return; }
+        const int l = F.lights[L.li];
+        if (F.flags[l] & W_FLAG_SPHERE) break;
+        float Lx, Ly, Lz, reach;
+        w_light_vector(F, L, l, Lx, Ly, Lz, reach);
+        w_shade(L, F, l, Lx, Ly, Lz, 1.0f);
         L.li++;
-        to_lights = true;
     }
-
-    if (to_lights) {
-        for (; L.li < F.n_lights; L.li++) {                            // RNO:206-277
-            const int l = F.lights[L.li];
-            const f4 lg = F.geom[l];
-            const float ex = f_sub(lg.x, L.px), ey = f_sub(lg.y, L.py), ez = f_sub(lg.z, L.pz);
-            const float reach = f_sqrt(f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(ez, ez)));
-            const float inv = f_rcp(reach);
-            const float Lx = f_mul(inv, ex), Ly = f_mul(inv, ey), Lz = f_mul(inv, ez);
-            if (F.flags[l] & W_FLAG_SPHERE) {                          // only sphere lights cast shadows (RNO:223)
-                L.qox = f_add(L.px, f_mul(Lx, W_EPS)); L.qoy = f_add(L.py, f_mul(Ly, W_EPS)); L.qoz = f_add(L.pz, f_mul(Lz, W_EPS));
-                L.qdx = Lx; L.qdy = Ly; L.qdz = Lz;
-                L.cumu = reach; L.qhit = -1; L.phase = PH_SHADOW;
-                return false;
-            }
-            w_shade(L, F, l, Lx, Ly, Lz, 1.0f);
+    L.ns = 0; L.sblk = 0;
+#pragma unroll
+    for (int k = 0; k < W_SHADOW_BATCH; k++) {
+        if (L.ns == k && L.li + k < F.n_lights && (F.flags[F.lights[L.li + k]] & W_FLAG_SPHERE)) {
+            float Lx, Ly, Lz, reach;
+            w_light_vector(F, L, F.lights[L.li + k], Lx, Ly, Lz, reach);
+            L.sox[k] = f_add(L.px, f_mul(Lx, W_EPS)); L.soy[k] = f_add(L.py, f_mul(Ly, W_EPS)); L.soz[k] = f_add(L.pz, f_mul(Lz, W_EPS));
+            L.slx[k] = Lx; L.sly[k] = Ly; L.slz[k] = Lz; L.sreach[k] = reach;
+            L.ns = k + 1;
         }
     }
+    L.phase = PH_SHADOW;
+}
 
+// After the nearest-hit round (RNO:194-205).
+template <bool COUNT>
+RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
+    if (COUNT) { L.c_nearest++; L.c_sphere_tests += (uint32_t)F.n_spheres; L.c_plane_tests += (uint32_t)F.n_planes; }
+    L.dist = L.cumu; L.hit = L.qhit; L.hkind = L.qkind;
+    L.cr = L.cg = L.cb = 0.f;
+    L.phase = PH_FINAL;
+    if (L.hit >= 0) {
+        if (F.flags[L.hit] & W_FLAG_LIGHT) {                           // RNO:197-200
+            const f4 ma = F.mat_a[L.hit];
+            L.cr = ma.x; L.cg = ma.y; L.cb = ma.z;
+        } else {
+            L.px = f_add(L.qox, f_mul(L.qdx, L.dist));
+            L.py = f_add(L.qoy, f_mul(L.qdy, L.dist));
+            L.pz = f_add(L.qoz, f_mul(L.qdz, L.dist));
+            L.li = 0;
+            w_next_shadow_batch(L, F);
+        }
+    }
+}
+
+// After a shadow round: shade the batch's lights in index order (a blocked light adds exactly 0, so it is
+// skipped), then set up the next batch or complete the ray.
+template <bool COUNT>
+RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
+    if (COUNT) L.c_shadow += (uint32_t)L.ns;
+#pragma unroll
+    for (int k = 0; k < W_SHADOW_BATCH; k++)
+        if (k < L.ns && !((L.sblk >> k) & 1)) w_shade(L, F, F.lights[L.li + k], L.slx[k], L.sly[k], L.slz[k], 1.0f);
+    L.li += L.ns;
+    w_next_shadow_batch(L, F);
+}
+
+// The ray is complete: fold its colour into the pixel (RNO:351-368), spawn its children (RNO:370-432) and move
+// on to the next ray of the FIFO, the next sub-sample, or the end of the pixel (returns true).
+template <bool COUNT>
+RT_HD bool w_finalize(WLane &L, const WFrame &F, f4 *q) {
     // The ray is finished: fold its colour into the pixel (RNO:351-368).
     if (L.kind == W_PRIMARY) {
         if (COUNT) L.c_samples++;

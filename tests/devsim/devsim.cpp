@@ -59,9 +59,14 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
         memset(&L, 0, sizeof L);
         w_begin_pixel(L, F, x, y);
         for (;;) {
-            if (use_runs) w_query<true>(L, F.geom, F.runs, F.n_runs, true);                  // the kernel's loop
-            else for (int s = 0; s < F.n; ++s) w_test<true>(L, F.geom[s], F.flags[s], s);    // plain per-primitive loop
-            if (w_advance<true>(L, F, queue)) break;
+            // the body of the kernel's loop, for one lane
+            w_query_nearest<true>(L, F.geom, F.runs, F.n_runs, true);
+            w_after_nearest<true>(L, F);
+            while (L.phase == PH_SHADOW) {
+                w_query_shadow<true>(L, F.geom, F.runs, F.n_runs, true);
+                w_after_shadow<true>(L, F);
+            }
+            if (w_finalize<true>(L, F, queue)) break;
         }
         const uint32_t p = w_pack_pixel(L.ar, L.ag, L.ab);
         memcpy(pixels + ((size_t)y * w + x) * 4, &p, 4);
