@@ -22,6 +22,7 @@ namespace rtb {
 #define W_TRACEDEPTH 5           /* RNO:4   */
 #define W_QUEUE_SLOTS 32         /* a breadth-first queue over a depth-5 binary ray tree never holds more */
 #define W_SHADOW_BATCH 3          /* shadow rays per lane per shadow round */
+static_assert(W_SHADOW_BATCH == 3, "w_after_shadow picks the batch's rays with three-way selects");
 #define PH_FINAL 3                /* the current ray is complete: w_finalize() folds it into the pixel */
 #define W_FLAG_SPHERE 1
 #define W_FLAG_LIGHT 2
@@ -64,6 +65,11 @@ struct WLane {
     uint64_t c_sphere_tests, c_plane_tests;
 };
 
+// "Sphere entirely behind the ray": b < 0 and det < b*b*(1-2^-22) imply sqrt_rn(det) <= |b|, so the far root
+// b + sqrt(det) is <= 0 and the reference's `i2 > 0` fails (bb = fl(b*b) <= b*b*(1+2^-24), and the rounded
+// product with 1-2^-22 stays below b*b; sqrt_rn is monotonic and |b| is representable).  Skips most roots.
+RT_HD bool w_sphere_behind(float b, float bb, float det) { return b < 0.f && det < f_mul(bb, 0.999999761581420898437500f); }
+
 // plane_intersect (RNO:95-109) and sphere_intersect (RNO:111-148) against the lane's query ray, written
 // without per-lane branches: the primitive index is warp-uniform, so all 32 lanes run one instruction
 // stream and a hit is a predicated update of (cumu, qhit, qkind).  `live` masks lanes that take no part
@@ -95,8 +101,9 @@ RT_HD void w_sphere(WLane &L, const f4 g, int i, bool live) {
     if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests++;
     const float vx = f_sub(L.qox, g.x), vy = f_sub(L.qoy, g.y), vz = f_sub(L.qoz, g.z);
     const float b = -dot3(vx, vy, vz, L.qdx, L.qdy, L.qdz);
-    const float det = f_add(f_sub(f_mul(b, b), dot3(vx, vy, vz, vx, vy, vz)), g.w);
-    const bool cand = live && det > 0.f;
+    const float bb = f_mul(b, b);
+    const float det = f_add(f_sub(bb, dot3(vx, vy, vz, vx, vy, vz)), g.w);
+    const bool cand = live && det > 0.f && !w_sphere_behind(b, bb, det);
     if (warp_any(cand)) {
         const float sq = f_sqrt(det);
         const float i1 = f_sub(b, sq), i2 = f_add(b, sq);
@@ -142,8 +149,9 @@ RT_HD void w_sphere2(WLane &L, const f4 *g, int i, bool live) {
         const f4 s = g[k];
         const float vx = f_sub(L.qox, s.x), vy = f_sub(L.qoy, s.y), vz = f_sub(L.qoz, s.z);
         b[k] = -dot3(vx, vy, vz, L.qdx, L.qdy, L.qdz);
-        det[k] = f_add(f_sub(f_mul(b[k], b[k]), dot3(vx, vy, vz, vx, vy, vz)), s.w);
-        cand[k] = live && det[k] > 0.f;
+        const float bb = f_mul(b[k], b[k]);
+        det[k] = f_add(f_sub(bb, dot3(vx, vy, vz, vx, vy, vz)), s.w);
+        cand[k] = live && det[k] > 0.f && !w_sphere_behind(b[k], bb, det[k]);
     }
     if (warp_any(cand[0] || cand[1])) {
         float sqv[2];
@@ -189,19 +197,24 @@ RT_HD void w_query_nearest(WLane &L, const f4 *geom, const int *runs, int n_runs
 //           with m = reach*|d| (rounded), |num| < m*(1-2^-21) proves 0 < dist < reach and
 //           |num| > m*(1+2^-21) proves dist >= reach (same error analysis as pre-filter B above; the quotient
 //           is normal because |num| > 1e-30 and |d| < 1e7); only the sliver in between takes the division.
+// `alive` = per-ray participation mask (bit k: ray k exists and was not blocked when the run started; counting
+// builds refresh it per primitive so that the test counters stop exactly at the first blocker).
+RT_HD int w_alive_mask(const WLane &L, bool has) { return has ? (((1 << L.ns) - 1) & ~L.sblk) : 0; }
+
 template <bool COUNT>
-RT_HD void w_shadow_sphere(WLane &L, const f4 g, bool has) {
+RT_HD void w_shadow_sphere(WLane &L, const f4 g, int alive_in, bool has) {
     float b[W_SHADOW_BATCH], det[W_SHADOW_BATCH];
     bool cand[W_SHADOW_BATCH];
     bool any = false;
+    const int alive = COUNT ? w_alive_mask(L, has) : alive_in;
 #pragma unroll
     for (int k = 0; k < W_SHADOW_BATCH; k++) {
-        const bool alive = has && k < L.ns && !((L.sblk >> k) & 1);
-        if (COUNT && alive) L.c_sphere_tests++;
+        if (COUNT && ((alive >> k) & 1)) L.c_sphere_tests++;
         const float vx = f_sub(L.sox[k], g.x), vy = f_sub(L.soy[k], g.y), vz = f_sub(L.soz[k], g.z);
         b[k] = -dot3(vx, vy, vz, L.slx[k], L.sly[k], L.slz[k]);
-        det[k] = f_add(f_sub(f_mul(b[k], b[k]), dot3(vx, vy, vz, vx, vy, vz)), g.w);
-        cand[k] = alive && det[k] > 0.f;
+        const float bb = f_mul(b[k], b[k]);
+        det[k] = f_add(f_sub(bb, dot3(vx, vy, vz, vx, vy, vz)), g.w);
+        cand[k] = ((alive >> k) & 1) && det[k] > 0.f && !w_sphere_behind(b[k], bb, det[k]);
         any = any || cand[k];
     }
     if (warp_any(any)) {
@@ -216,30 +229,29 @@ RT_HD void w_shadow_sphere(WLane &L, const f4 g, bool has) {
     }
 }
 template <bool COUNT>
-RT_HD void w_shadow_plane(WLane &L, const f4 g, bool has) {
+RT_HD void w_shadow_plane(WLane &L, const f4 g, int alive_in, bool has) {
     float d[W_SHADOW_BATCH], num[W_SHADOW_BATCH];
-    bool ambiguous[W_SHADOW_BATCH];
+    bool cand[W_SHADOW_BATCH];
     bool any = false;
+    const int alive = COUNT ? w_alive_mask(L, has) : alive_in;
 #pragma unroll
     for (int k = 0; k < W_SHADOW_BATCH; k++) {
-        const bool alive = has && k < L.ns && !((L.sblk >> k) & 1);
-        if (COUNT && alive) L.c_plane_tests++;
+        if (COUNT && ((alive >> k) & 1)) L.c_plane_tests++;
         d[k] = dot3(g.x, g.y, g.z, L.slx[k], L.sly[k], L.slz[k]);
         num[k] = -f_add(dot3(g.x, g.y, g.z, L.sox[k], L.soy[k], L.soz[k]), g.w);
-        const float an = fabsf(num[k]), ad = fabsf(d[k]);
-        const bool sign_ok = alive && d[k] != 0.f && num[k] != 0.f && ((num[k] > 0.f) == (d[k] > 0.f));
-        const float m = f_mul(L.sreach[k], ad);
-        const bool sure_hit = an < f_mul(m, 0.999999523162841796875f) && an > 1e-30f && m < 1e30f && ad < 1e7f;
-        const bool sure_miss = an > f_mul(m, 1.000000476837158203125f) && m > 1e-30f;
-        if (sign_ok && sure_hit) L.sblk |= 1 << k;
-        ambiguous[k] = sign_ok && !sure_hit && !sure_miss;
-        any = any || ambiguous[k];
+        // dist = num/d > 0 needs both non-zero and of equal sign; and |num| > (reach*|d|)*(1+2^-21) proves
+        // dist >= reach (pre-filter B).  What survives -- a plane that may really block -- takes the division.
+        const bool same_sign = (int)(f_bits(num[k]) ^ f_bits(d[k])) >= 0;
+        const float hi = f_mul(f_mul(L.sreach[k], fabsf(d[k])), 1.000000476837158203125f);
+        const bool beyond = fabsf(num[k]) > hi && hi > 1e-30f;
+        cand[k] = ((alive >> k) & 1) && same_sign && d[k] != 0.f && num[k] != 0.f && !beyond;
+        any = any || cand[k];
     }
     if (warp_any(any)) {
 #pragma unroll
         for (int k = 0; k < W_SHADOW_BATCH; k++) {
             const float dist = f_div(num[k], d[k]);
-            if (ambiguous[k] && dist > 0.f && dist < L.sreach[k]) L.sblk |= 1 << k;
+            if (cand[k] && dist > 0.f && dist < L.sreach[k]) L.sblk |= 1 << k;
         }
     }
 }
@@ -248,11 +260,11 @@ RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs,
     for (int r = 0; r < n_runs; ++r) {
         const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
         if (fl & W_FLAG_LIGHT) continue;                                   // RNO:234: lights cast no shadow
-        const bool open = has && L.sblk != (1 << L.ns) - 1;                // some ray of this lane is still unblocked
-        if (!warp_any(open)) return;                                       // the `break` of RNO:237, for the whole warp
+        const int alive = w_alive_mask(L, has);                            // rays of this lane that are still unblocked
+        if (!warp_any(alive != 0)) return;                                 // the `break` of RNO:237, for the whole warp
         const int end = start + count;
-        if (fl & W_FLAG_SPHERE) for (int i = start; i < end; ++i) w_shadow_sphere<COUNT>(L, geom[i], has);
-        else                    for (int i = start; i < end; ++i) w_shadow_plane<COUNT>(L, geom[i], has);
+        if (fl & W_FLAG_SPHERE) for (int i = start; i < end; ++i) w_shadow_sphere<COUNT>(L, geom[i], alive, has);
+        else                    for (int i = start; i < end; ++i) w_shadow_plane<COUNT>(L, geom[i], alive, has);
     }
 }
 
@@ -350,14 +362,18 @@ RT_HD void w_light_vector(const WFrame &F, const WLane &L, int l, float &Lx, flo
     const float inv = f_rcp(reach);
     Lx = f_mul(inv, ex); Ly = f_mul(inv, ey); Lz = f_mul(inv, ez);
 }
+// A light that is not a sphere (none in the reference's scenes): shaded without a shadow ray.
+RT_HD void w_shade_unshadowed(WLane &L, const WFrame &F, int l) {
+    float Lx, Ly, Lz, reach;
+    w_light_vector(F, L, l, Lx, Ly, Lz, reach);
+    w_shade(L, F, l, Lx, Ly, Lz, 1.0f);
+}
 RT_HD void w_next_shadow_batch(WLane &L, const WFrame &F) {
     for (;;) {
         if (L.li >= F.n_lights) { L.phase = PH_FINAL; return; }
         const int l = F.lights[L.li];
         if (F.flags[l] & W_FLAG_SPHERE) break;
-        float Lx, Ly, Lz, reach;
-        w_light_vector(F, L, l, Lx, Ly, Lz, reach);
-        w_shade(L, F, l, Lx, Ly, Lz, 1.0f);
+        w_shade_unshadowed(L, F, l);
         L.li++;
     }
     L.ns = 0; L.sblk = 0;
@@ -400,9 +416,13 @@ RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
 template <bool COUNT>
 RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
     if (COUNT) L.c_shadow += (uint32_t)L.ns;
-#pragma unroll
-    for (int k = 0; k < W_SHADOW_BATCH; k++)
-        if (k < L.ns && !((L.sblk >> k) & 1)) w_shade(L, F, F.lights[L.li + k], L.slx[k], L.sly[k], L.slz[k], 1.0f);
+#pragma unroll 1
+    for (int k = 0; k < L.ns; k++) {          // a real loop (one copy of the shading code); the rays are picked with selects
+        const float Lx = k == 0 ? L.slx[0] : (k == 1 ? L.slx[1] : L.slx[2]);
+        const float Ly = k == 0 ? L.sly[0] : (k == 1 ? L.sly[1] : L.sly[2]);
+        const float Lz = k == 0 ? L.slz[0] : (k == 1 ? L.slz[1] : L.slz[2]);
+        if (!((L.sblk >> k) & 1)) w_shade(L, F, F.lights[L.li + k], Lx, Ly, Lz, 1.0f);
+    }
     L.li += L.ns;
     w_next_shadow_batch(L, F);
 }

@@ -5,10 +5,10 @@ cd "$(dirname "$0")/../se-195-project-ray-tracer_b200"
 rm -f ../variants/*.so
 build() { tag=$1; shift; nvcc "$@" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -std=c++17 -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off -shared -o ../variants/librt_$tag.so csrc/rt_kernels.cu csrc/rt_api.cu host/scene_io.cpp & }
 build base
-build w6_p4 -DW_MIN_BLOCKS=6 -DPT_MIN_BLOCKS=4
-build w7_p5 -DW_MIN_BLOCKS=7 -DPT_MIN_BLOCKS=5
-build w8_p128b8 -DW_MIN_BLOCKS=8 -DPT_THREADS=128 -DPT_MIN_BLOCKS=8
-build w256b3_p128b10 -DW_THREADS=256 -DW_MIN_BLOCKS=3 -DPT_THREADS=128 -DPT_MIN_BLOCKS=10
-build w64b12_p6 -DW_THREADS=64 -DW_MIN_BLOCKS=12 -DPT_MIN_BLOCKS=6
+build w128b5 -DW_MIN_BLOCKS=5
+build w128b6 -DW_MIN_BLOCKS=6
+build w64b10 -DW_THREADS=64 -DW_MIN_BLOCKS=10
+build w256b2 -DW_THREADS=256 -DW_MIN_BLOCKS=2
+build w64 -DW_THREADS=64
 wait
 ls ../variants
