@@ -160,6 +160,11 @@ int rt_pt_render(rt_ctx *ctx, int integrator, int n_passes,
 /* Asynchronous launch only (state stays in HBM), and the matching blocking read-back. */
 int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes);
 int rt_pt_download(rt_ctx *ctx, uint32_t *pixels_out, float *colors_out, uint32_t *seeds_out);
+/* Checkpoint / resume of a progressive render (the reference keeps this state only in its
+ * buffers and loses it on exit).  The state is exactly (colors, seeds, currentSample): save it with
+ * rt_pt_download + rt_pt_current_sample; after rt_pt_resize / set_scene / set_camera on any context,
+ * rt_pt_restore puts it back and the next rt_pt_render continues bit-identically. */
+int rt_pt_restore(rt_ctx *ctx, const float *colors, const uint32_t *seeds, int current_sample);
 /* currentSample of the reference (SPT/smallptGPU.cpp:60): passes accumulated so far. */
 int rt_pt_current_sample(const rt_ctx *ctx);
 /* Sample-sharded progressive mode: colors hold running SUMS instead of running

@@ -66,6 +66,7 @@ SYMBOLS = {
     "rt_pt_launch": (_I, [_VP, _I, _I]),
     "rt_pt_download": (_I, [_VP, _VP, _VP, _VP]),
     "rt_pt_current_sample": (_I, [_VP]),
+    "rt_pt_restore": (_I, [_VP, _VP, _VP, _I]),
     "rt_pt_set_accumulate_sums": (_I, [_VP, _I]),
     "rt_pt_resolve_sums": (_I, [_VP, _I]),
     "rt_sync": (_I, [_VP]),
@@ -420,6 +421,11 @@ class Renderer:
         seeds = np.zeros(2 * w * h, np.uint32) if "seeds" in want else None
         self._ck(self._lib.rt_pt_download(self._ctx, _ptr(pixels), _ptr(colors), _ptr(seeds)))
         return {"pixels": pixels, "colors": colors, "seeds": seeds}
+
+    def pt_restore(self, colors, seeds, current_sample):
+        colors = np.ascontiguousarray(colors, dtype=np.float32)
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        self._ck(self._lib.rt_pt_restore(self._ctx, _ptr(colors), _ptr(seeds), int(current_sample)))
 
     def pt_current_sample(self):
         return int(self._lib.rt_pt_current_sample(self._ctx))

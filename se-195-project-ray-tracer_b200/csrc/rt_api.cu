@@ -299,6 +299,19 @@ int rt_pt_resize(rt_ctx *ctx, int w, int h, const uint32_t *seeds) {
     return RT_OK;
 }
 
+int rt_pt_restore(rt_ctx *ctx, const float *colors, const uint32_t *seeds, int current_sample) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ctx->have_size) return fail(ctx, RT_ERR_STATE, "rt_pt_restore: call rt_pt_resize first");
+    if (!colors || !seeds || current_sample < 0) return fail(ctx, RT_ERR_ARG, "rt_pt_restore: need colors, seeds and current_sample >= 0");
+    CK(cudaSetDevice(ctx->device));
+    const size_t px = (size_t)ctx->p_w * ctx->p_h;
+    CK(cudaMemcpyAsync(ctx->d_colors, colors, px * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_seeds, seeds, px * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->current_sample = current_sample;
+    return RT_OK;
+}
+
 int rt_pt_set_scene(rt_ctx *ctx, const rt_sphere *spheres, uint32_t n) {
     if (!ctx) return RT_ERR_ARG;
     if (!spheres || n < 1) return fail(ctx, RT_ERR_ARG, "rt_pt_set_scene: need at least one sphere");

@@ -208,6 +208,37 @@ def test_smallpt_progressive_calls_continue_the_sample_counter(gpu, orc, rt, cor
     assert gpu.pt_current_sample() == 0
 
 
+def test_smallpt_checkpoint_resume_and_reinit_semantics(gpu, orc, rt, cornell):
+    """Progressive state = (colors, seeds, currentSample): saved from one context and restored into another, the
+    render continues bit-identically.  Moving an object (ReInitSceneGPU) or the camera (ReInitGPU) restarts at
+    sample 0 with the RNG state left where it was, exactly like the reference (SPT/smallptGPU.cpp:784-830)."""
+    spheres, cam = cornell
+    w, h = 80, 60
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=8)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    st = gpu.pt_render(0, 3)
+    assert gpu.pt_current_sample() == 3
+    r2 = rt.Renderer(0)
+    try:
+        r2.pt_resize(w, h, seeds); r2.pt_set_scene(spheres); r2.pt_set_camera(cam)
+        r2.pt_restore(st["colors"], st["seeds"], 3)
+        resumed = r2.pt_render(0, 4)
+    finally:
+        r2.close()
+    col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, spheres, cam, w, h, seeds, 7)
+    assert np.array_equal(resumed["seeds"], sd_o) and np.array_equal(resumed["pixels"].reshape(-1), pix_o)
+    assert np.array_equal(resumed["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32))
+    # object move: sphere 6 shifted by the viewer's MOVE_STEP-like offset, sample counter back to 0, seeds continue
+    moved = spheres.copy(); moved["p"][6] += np.float32(2.5)
+    gpu.pt_set_scene(moved)
+    assert gpu.pt_current_sample() == 0
+    out = gpu.pt_render(0, 2)
+    col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, moved, cam, w, h, st["seeds"], 2)
+    assert np.array_equal(out["seeds"], sd_o) and np.array_equal(out["pixels"].reshape(-1), pix_o)
+    assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32))
+
+
 def test_smallpt_chunked_staging_equals_resident(gpu, orc, rt, tmp_path):
     """A scene streamed through shared memory in chunks (forced by a tiny residency limit, ragged last
     chunk) gives the same bits as the resident path and as the oracle."""
@@ -312,6 +343,36 @@ def test_full_size_properties(gpu, rt, cornell):
     assert np.array_equal(outs[0]["seeds"], outs[1]["seeds"]) and np.array_equal(outs[0]["pixels"], outs[1]["pixels"])
     assert np.isfinite(outs[0]["colors"]).all() and (outs[0]["colors"] >= 0).all()
     assert (outs[0]["pixels"] >> 24 == 0).all()
+
+
+# ------------------------------------------------------------------------------------------ headless driver
+def test_cli_with_the_reference_command_line(gpu, orc, rt, whitted_golden, tmp_path):
+    """rt_cli takes the reference's argv (<1> <work-group> <kernel file> <w> <h> <scene>) and dumps the viewer's
+    PPM / the Whitted BMP.  Seeds are libc rand() like the reference's, so the oracle can be fed the same ones."""
+    import os
+    import subprocess
+    cli = os.path.join(os.path.dirname(rt.LIB_PATH), "rt_cli")
+    scn = tmp_path / "c2.scn"
+    rt.write_complex_scene(str(scn), 2)
+    w, h, passes = 96, 72, 5
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)                                         # a fresh process starts at srand(1)
+    seeds = np.array([max(libc.rand(), 2) for _ in range(2 * w * h)], np.uint32)
+    spheres, cam = rt.read_scene(str(scn), w, h)
+    for kernel, integ in [("rendering_kernel.cl", 0), ("scenes\\rendering_kernel_dl.cl", 1)]:
+        out = tmp_path / f"image{integ}.ppm"
+        p = subprocess.run([cli, "1", "64", kernel, str(w), str(h), str(scn), str(passes), str(out)], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        assert "Sample/sec" in p.stdout
+        _, _, pix_o, _ = oracle_pt(orc, integ, spheres, cam, w, h, seeds, passes)
+        want = tmp_path / f"want{integ}.ppm"
+        rt.write_ppm(str(want), pix_o.reshape(h, w))
+        assert out.read_bytes() == want.read_bytes()
+    bmp = tmp_path / "test.bmp"
+    p = subprocess.run([cli, "1", "64", "raytracer_kernel.cl", "800", "600", "0", "-", str(bmp)], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.startswith("Runtime: "), p.stderr
+    assert hashlib.md5(bmp.read_bytes()).hexdigest() == whitted_golden["bmp_md5"]
+    assert subprocess.run([cli, "0", "64", "rendering_kernel.cl", "8", "8", str(scn)], capture_output=True).returncode == 2   # no CPU device
 
 
 # ------------------------------------------------------------------------------------------ error behaviour
