@@ -186,6 +186,15 @@ uint64_t rt_launch_count(const rt_ctx *ctx);
  * torch.distributed in bench.py) -- returns NULL if not allocated.  which: */
 enum { RT_BUF_WHITTED_PIXELS = 0, RT_BUF_WHITTED_HITS = 1, RT_BUF_PT_PIXELS = 2, RT_BUF_PT_COLORS = 3, RT_BUF_PT_SEEDS = 4 };
 void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes);
+/* Fused frame assembly over NVLink (second option): rank 0 exports its pixel buffer as a
+ * 64-byte CUDA IPC handle (rt_ipc_export, after rt_whitted_upload / rt_pt_resize); every other rank's process
+ * imports it (rt_ipc_import) and from then on its render kernel stores the pixels of the rows it owns straight
+ * into rank 0's frame through the peer mapping -- the transfer rides inside the kernel, tile by tile, and no
+ * gather step exists.  The caller only has to order "all ranks' kernels done" before rank 0 reads the frame
+ * (any barrier collective on the render stream).  which: RT_BUF_WHITTED_PIXELS or RT_BUF_PT_PIXELS. */
+int rt_ipc_export(rt_ctx *ctx, int which, unsigned char *handle64);
+int rt_ipc_import(rt_ctx *ctx, int which, const unsigned char *handle64);
+int rt_ipc_close(rt_ctx *ctx);
 /* The context's cudaStream_t as an opaque pointer (for callers that order their own work after it). */
 void *rt_stream(rt_ctx *ctx);
 /* Makes the context issue all its work on a caller-owned cudaStream_t (e.g. torch's current stream, so

@@ -75,6 +75,9 @@ SYMBOLS = {
     "rt_launch_count": (_U64, [_VP]),
     "rt_device_buffer": (_VP, [_VP, _I, C.POINTER(_U64)]),
     "rt_selftest_math": (_I, [_VP, _I, _VP, _VP, _U64]),
+    "rt_ipc_export": (_I, [_VP, _I, _VP]),
+    "rt_ipc_import": (_I, [_VP, _I, _VP]),
+    "rt_ipc_close": (_I, [_VP]),
     "rt_stream": (_VP, [_VP]),
     "rt_set_stream": (_I, [_VP, _VP]),
     "rt_update_camera": (None, [_VP, _I, _I]),
@@ -268,6 +271,36 @@ def gather_staging(frame, world, tile_rows):
     return [torch.empty(v.numel() + (t.numel() if t is not None else 0), dtype=frame.dtype, device=frame.device) for v, t in views]
 
 
+def share_rank0_framebuffer(renderer, which, rank, world):
+    """Fused frame assembly: rank 0 exports its pixel buffer (CUDA IPC), the others map it and will render their
+    rows straight into it.  Collective over the default process group; returns True if EVERY rank succeeded (else
+    nothing is redirected and the caller falls back to gather_row_tiles)."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return False
+    dev = torch.device("cuda", torch.cuda.current_device())
+    handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+    ok = torch.ones(1, dtype=torch.int32, device=dev)
+    if rank == 0:
+        try:
+            handle.copy_(torch.from_numpy(renderer.ipc_export(which)))
+        except RtError:
+            ok.zero_()
+    dist.broadcast(handle, 0)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) and rank != 0:
+        try:
+            renderer.ipc_import(which, handle.cpu().numpy())
+        except RtError:
+            ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if not int(ok.item()):
+        renderer.ipc_close()
+        return False
+    return True
+
+
 def allreduce_sums(colors):
     """Sample-sharded mode: adds the per-rank float accumulation buffers in place (ncclAllReduce, sum)."""
     import torch.distributed as dist
@@ -353,6 +386,19 @@ class Renderer:
                3: np.zeros((x.size, 2), np.float32), 4: np.zeros(x.size, np.float64)}[op]
         self._ck(self._lib.rt_selftest_math(self._ctx, op, _ptr(x), _ptr(out), x.size))
         return out
+
+    def ipc_export(self, which):
+        h = np.zeros(64, np.uint8)
+        self._ck(self._lib.rt_ipc_export(self._ctx, which, _ptr(h)))
+        return h
+
+    def ipc_import(self, which, handle):
+        h = np.ascontiguousarray(handle, dtype=np.uint8)
+        assert h.size == 64
+        self._ck(self._lib.rt_ipc_import(self._ctx, which, _ptr(h)))
+
+    def ipc_close(self):
+        self._ck(self._lib.rt_ipc_close(self._ctx))
 
     def device_buffer(self, which):
         n = C.c_uint64()

@@ -31,6 +31,7 @@ struct rt_ctx {
     int pt_chunk_spheres = 3072;                   // 48 KB of (p, rad^2) per chunk
     int max_blocks_per_sm = 0;
     int whitted_sort = 1;                          // cost-sorted work order (scheduling pre-pass)
+    uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
     unsigned *d_wclass = nullptr;
     // Whitted
@@ -129,6 +130,8 @@ void rt_destroy(rt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->peer_wpixels) cudaIpcCloseMemHandle(ctx->peer_wpixels);
+    if (ctx->peer_ppixels) cudaIpcCloseMemHandle(ctx->peer_ppixels);
     void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
@@ -235,7 +238,8 @@ int rt_whitted_launch(rt_ctx *ctx) {
     F.DX = (WX2 - WX1) / ctx->w_w; F.DY = (WY2 - WY1) / ctx->w_h;
     F.hit_ids = ctx->w_want_hits ? ctx->d_whits : nullptr;
     p.shard = make_shard(ctx->w_w, ctx->w_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
-    p.pixels = ctx->d_wpixels; p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
+    p.pixels = ctx->peer_wpixels ? ctx->peer_wpixels : ctx->d_wpixels;     // fused gather: store straight into rank 0's frame
+    p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
     p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
     p.stage_materials = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 1) <= 32 * 1024 ? 1 : 0;
     p.order = nullptr; p.class_counts = nullptr;
@@ -364,7 +368,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
     F.pass0 = ctx->current_sample; F.n_passes = n_passes;
     F.direct_only = integrator; F.sum_mode = ctx->sum_mode;
     p.shard = make_shard(ctx->p_w, ctx->p_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
-    p.colors = ctx->d_colors; p.seeds = ctx->d_seeds; p.pixels = ctx->d_ppixels;
+    p.colors = ctx->d_colors; p.seeds = ctx->d_seeds; p.pixels = ctx->peer_ppixels ? ctx->peer_ppixels : ctx->d_ppixels;
     p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
     p.count = ctx->counting; p.sm_count = ctx->sm_count;
     p.max_smem_geom = ctx->pt_max_resident_bytes < ctx->max_smem_optin ? ctx->pt_max_resident_bytes : ctx->max_smem_optin;
@@ -447,6 +451,41 @@ void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes) {
     }
     if (bytes) *bytes = p ? b : 0;
     return p;
+}
+
+int rt_ipc_export(rt_ctx *ctx, int which, unsigned char *handle64) {
+    if (!ctx || !handle64) return RT_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    void *p = which == RT_BUF_WHITTED_PIXELS ? (void *)ctx->d_wpixels : which == RT_BUF_PT_PIXELS ? (void *)ctx->d_ppixels : nullptr;
+    if (!p) return fail(ctx, RT_ERR_STATE, "rt_ipc_export: buffer %d is not allocated (upload / resize first) or cannot be shared", which);
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    return RT_OK;
+}
+
+int rt_ipc_import(rt_ctx *ctx, int which, const unsigned char *handle64) {
+    if (!ctx || !handle64) return RT_ERR_ARG;
+    if (which != RT_BUF_WHITTED_PIXELS && which != RT_BUF_PT_PIXELS) return fail(ctx, RT_ERR_ARG, "rt_ipc_import: only the pixel buffers can be redirected");
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    uint32_t **slot = which == RT_BUF_WHITTED_PIXELS ? &ctx->peer_wpixels : &ctx->peer_ppixels;
+    if (*slot) cudaIpcCloseMemHandle(*slot);
+    *slot = (uint32_t *)p;
+    return RT_OK;
+}
+
+int rt_ipc_close(rt_ctx *ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->peer_wpixels) { cudaIpcCloseMemHandle(ctx->peer_wpixels); ctx->peer_wpixels = nullptr; }
+    if (ctx->peer_ppixels) { cudaIpcCloseMemHandle(ctx->peer_ppixels); ctx->peer_ppixels = nullptr; }
+    return RT_OK;
 }
 
 int rt_selftest_math(rt_ctx *ctx, int op, const float *in, void *out, uint64_t n) {

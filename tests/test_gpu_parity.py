@@ -396,3 +396,44 @@ def test_errors_are_codes_not_exits(gpu, rt, cornell):
         assert e.value.code == rt.RT_ERR_ARG
     finally:
         r.close()
+
+
+# ------------------------------------------------------------------------------------------ fused frame assembly (CUDA IPC)
+def _ipc_worker(rank, world, port, out_dir):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # control plane only; both ranks drive cuda:0
+    import __graft_entry__ as graft
+    rt = graft.load()
+    r = rt.Renderer(0)
+    prims = rt.whitted_create_scene(0)
+    w, h, tile = 160, 120, 8
+    r.set_shard(rank, world, tile)
+    r.whitted_upload(prims, w, h)
+    box = [r.ipc_export(rt.BUF_WHITTED_PIXELS).tobytes() if rank == 0 else None]
+    dist.broadcast_object_list(box, 0)
+    if rank != 0:
+        r.ipc_import(rt.BUF_WHITTED_PIXELS, np.frombuffer(box[0], np.uint8))
+    dist.barrier()
+    r.whitted_launch(); r.sync()
+    dist.barrier()                                                     # every rank's kernel has finished
+    if rank == 0:
+        np.save(os.path.join(out_dir, "assembled.npy"), r.whitted_download())
+    dist.barrier()
+    r.close()
+    dist.destroy_process_group()
+
+
+def test_fused_frame_assembly_through_ipc_peer_memory(rt, orc, tmp_path):
+    """Two processes (two ranks) render interleaved row tiles; rank 1's kernel stores its rows straight into rank 0's
+    framebuffer through the CUDA-IPC mapping.  The assembled frame equals the unsharded oracle frame."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    mp.spawn(_ipc_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    prims = rt.whitted_create_scene(0)
+    px_o, _, _ = oracle_whitted(orc, prims, 160, 120)
+    assert np.array_equal(np.load(tmp_path / "assembled.npy"), px_o)
