@@ -320,11 +320,27 @@ def run_ours(args, rank, world, local_rank):
         threads = host_threads()
         mrays, ms, kind, sample = time_reference(rt, 2, 1, threads)
         out["cpu_baseline"] = {"value": round(mrays, 3), "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample}
+        out["config1_cpu"] = time_config1()
     if rank == 0:
         print(json.dumps(out))
     r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_config1():
+    """BASELINE configs[0]: the reference's own CPU render (raytracer3.0.06: Engine_InitRender + Engine_Render, unmodified,
+    oracle/_ref/libref_r306.so) of its built-in scene at 800x600, one frame, one core (its engine keeps state in globals)."""
+    path = os.path.join(graft.ORACLE_DIR, "_ref", "libref_r306.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libref_r306.so not shipped"}
+    lib = ctypes.CDLL(path)
+    frame = np.zeros((600, 800), np.uint32)
+    t0 = time.perf_counter()
+    lib.ref_r306_render(vp(frame), 800, 600)
+    dt = time.perf_counter() - t0
+    return {"workload": "raytracer3.0.06 CPU Whitted render, 800x600 (rows 20..529), 3x3 AA, 1 frame", "seconds_per_frame": round(dt, 3),
+            "cores": 1, "kind": "reference", "rows_rendered": int(frame.any(axis=1).sum())}
 
 
 def cornell_scene(rt, w, h):
