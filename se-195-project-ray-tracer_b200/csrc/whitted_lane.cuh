@@ -68,7 +68,7 @@ struct WLane {
 // "Sphere entirely behind the ray": b < 0 and det < b*b*(1-2^-22) imply sqrt_rn(det) <= |b|, so the far root
 // b + sqrt(det) is <= 0 and the reference's `i2 > 0` fails (bb = fl(b*b) <= b*b*(1+2^-24), and the rounded
 // product with 1-2^-22 stays below b*b; sqrt_rn is monotonic and |b| is representable).  Skips most roots.
-RT_HD bool w_sphere_behind(float b, float bb, float det) { return b < 0.f && det < f_mul(bb, 0.999999761581420898437500f); }
+RT_HD bool w_sphere_behind(float b, float bb, float det) { return (b < 0.f) & (det < f_mul(bb, 0.999999761581420898437500f)); }
 
 // plane_intersect (RNO:95-109) and sphere_intersect (RNO:111-148) against the lane's query ray, written
 // without per-lane branches: the primitive index is warp-uniform, so all 32 lanes run one instruction
@@ -83,17 +83,26 @@ RT_HD bool w_sphere_behind(float b, float bb, float det) { return b < 0.f && det
 //   B. |num| > (cumu*|d|)*(1+2^-21), all factors rounded, implies |num|/|d| > cumu*(1+2^-22), hence the
 //      correctly rounded quotient is >= cumu + ulp and `dist < cumu` fails.  Skipped when the product is
 //      not comfortably normal (the error bound would not hold for subnormals; inf never rejects).
+//   Both at once: with s = N.o + depth (num = -s) and the signed limit w = (d*cumu)*(1+2^-21), A and B say that the
+//   division is only worth taking if num lies between 0 and w, i.e. num*(w - num) >= 0, i.e. s*(w + s) <= 0: one
+//   addition, one multiplication and one comparison (w_plane_candidate).  The sign of a rounded sum is the exact one,
+//   an underflowing product keeps its sign, and a zero counts as "take the division".  The candidate set is a superset
+//   of A-and-B (it keeps d == 0 / num == 0); it only gates the exact stage, which re-checks 0 < dist < cumu and
+//   rejects the inf / NaN a zero d produces, so the accepted hits are the same.
+RT_HD bool w_plane_candidate(float s, float d, float limit) {
+    const float w = f_mul(f_mul(d, limit), 1.000000476837158203125f);
+    const float m = f_mul(s, f_add(w, s));
+    return (m <= 0.f) | !(fabsf(w) > 1e-30f);
+}
 template <bool COUNT>
 RT_HD void w_plane(WLane &L, const f4 g, int i, bool live) {
     if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests++;
     const float d = dot3(g.x, g.y, g.z, L.qdx, L.qdy, L.qdz);
-    const float num = -f_add(dot3(g.x, g.y, g.z, L.qox, L.qoy, L.qoz), g.w);
-    const float bound = f_mul(f_mul(L.cumu, fabsf(d)), 1.000000476837158203125f);
-    const bool far_away = fabsf(num) > bound && bound > 1e-30f;
-    const bool cand = live && d != 0.f && num != 0.f && ((num > 0.f) == (d > 0.f)) && !far_away;
-    if (warp_any(cand)) {
-        const float dist = f_div(num, d);
-        if (cand && dist > 0.f && dist < L.cumu) { L.cumu = dist; L.qhit = i; L.qkind = 1; }
+    const float s = f_add(dot3(g.x, g.y, g.z, L.qox, L.qoy, L.qoz), g.w);
+    const bool cand = w_plane_candidate(s, d, L.cumu);
+    if (warp_any(cand & live)) {
+        const float dist = f_div(-s, d);
+        if (live & cand & (dist > 0.f) & (dist < L.cumu)) { L.cumu = dist; L.qhit = i; L.qkind = 1; }
     }
 }
 template <bool COUNT>
@@ -103,38 +112,40 @@ RT_HD void w_sphere(WLane &L, const f4 g, int i, bool live) {
     const float b = -dot3(vx, vy, vz, L.qdx, L.qdy, L.qdz);
     const float bb = f_mul(b, b);
     const float det = f_add(f_sub(bb, dot3(vx, vy, vz, vx, vy, vz)), g.w);
-    const bool cand = live && det > 0.f && !w_sphere_behind(b, bb, det);
-    if (warp_any(cand)) {
-        const float sq = f_sqrt(det);
+    const bool cand = (det > 0.f) & !w_sphere_behind(b, bb, det);
+    if (warp_any(cand & live)) {
+        const float dv[1] = { det };
+        const bool need[1] = { cand & live };
+        float sqv[1];
+        sqrt_group<1>(dv, need, sqv);
+        const float sq = sqv[0];
         const float i1 = f_sub(b, sq), i2 = f_add(b, sq);
         const bool inside = i1 < 0.f;                           // ray starts inside: take the far root, INPRIM
         const float t = inside ? i2 : i1;
-        if (cand && i2 > 0.f && t < L.cumu) { L.cumu = t; L.qhit = i; L.qkind = inside ? -1 : 1; }
+        if (live & cand & (i2 > 0.f) & (t < L.cumu)) { L.cumu = t; L.qhit = i; L.qkind = inside ? -1 : 1; }
     }
 }
 
 // Two consecutive planes (i, i+1) at once: two independent chains, one vote for both divisions.
 template <bool COUNT>
 RT_HD void w_plane2(WLane &L, const f4 *g, int i, bool live) {
-    float d[2], num[2];
+    float d[2], sv[2];
     bool cand[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const f4 s = g[k];
         d[k] = dot3(s.x, s.y, s.z, L.qdx, L.qdy, L.qdz);
-        num[k] = -f_add(dot3(s.x, s.y, s.z, L.qox, L.qoy, L.qoz), s.w);
+        sv[k] = f_add(dot3(s.x, s.y, s.z, L.qox, L.qoy, L.qoz), s.w);
         // pre-filter B uses the limit before either plane of the pair is applied: cumu only shrinks, so a
         // plane that is beyond this limit is beyond the later one too
-        const float bound = f_mul(f_mul(L.cumu, fabsf(d[k])), 1.000000476837158203125f);
-        const bool far_away = fabsf(num[k]) > bound && bound > 1e-30f;
-        cand[k] = live && d[k] != 0.f && num[k] != 0.f && ((num[k] > 0.f) == (d[k] > 0.f)) && !far_away;
+        cand[k] = w_plane_candidate(sv[k], d[k], L.cumu);
     }
-    if (warp_any(cand[0] || cand[1])) {
-        const float q0 = f_div(num[0], d[0]), q1 = f_div(num[1], d[1]);
+    if (warp_any((cand[0] | cand[1]) & live)) {
+        const float q0 = f_div(-sv[0], d[0]), q1 = f_div(-sv[1], d[1]);
         if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests++;
-        if (cand[0] && q0 > 0.f && q0 < L.cumu) { L.cumu = q0; L.qhit = i; L.qkind = 1; }
+        if (live & cand[0] & (q0 > 0.f) & (q0 < L.cumu)) { L.cumu = q0; L.qhit = i; L.qkind = 1; }
         if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests++;
-        if (cand[1] && q1 > 0.f && q1 < L.cumu) { L.cumu = q1; L.qhit = i + 1; L.qkind = 1; }
+        if (live & cand[1] & (q1 > 0.f) & (q1 < L.cumu)) { L.cumu = q1; L.qhit = i + 1; L.qkind = 1; }
     } else if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_plane_tests += 2;
 }
 
@@ -151,11 +162,11 @@ RT_HD void w_sphere2(WLane &L, const f4 *g, int i, bool live) {
         b[k] = -dot3(vx, vy, vz, L.qdx, L.qdy, L.qdz);
         const float bb = f_mul(b[k], b[k]);
         det[k] = f_add(f_sub(bb, dot3(vx, vy, vz, vx, vy, vz)), s.w);
-        cand[k] = live && det[k] > 0.f && !w_sphere_behind(b[k], bb, det[k]);
+        cand[k] = live & (det[k] > 0.f) & !w_sphere_behind(b[k], bb, det[k]);
     }
-    if (warp_any(cand[0] || cand[1])) {
+    if (warp_any(cand[0] | cand[1])) {
         float sqv[2];
-        sqrt_group<2>(det, sqv);
+        sqrt_group<2>(det, cand, sqv);
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests++;
@@ -163,7 +174,7 @@ RT_HD void w_sphere2(WLane &L, const f4 *g, int i, bool live) {
             const float i1 = f_sub(b[k], sq), i2 = f_add(b[k], sq);
             const bool inside = i1 < 0.f;
             const float t = inside ? i2 : i1;
-            if (cand[k] && i2 > 0.f && t < L.cumu) { L.cumu = t; L.qhit = i + k; L.qkind = inside ? -1 : 1; }
+            if (cand[k] & (i2 > 0.f) & (t < L.cumu)) { L.cumu = t; L.qhit = i + k; L.qkind = inside ? -1 : 1; }
         }
     } else if (COUNT && live && L.phase == PH_SHADOW && L.qhit < 0) L.c_sphere_tests += 2;
 }
@@ -193,10 +204,8 @@ RT_HD void w_query_nearest(WLane &L, const f4 *geom, const int *runs, int n_runs
 // ("is there a non-light primitive with 0 < dist < distance to the light", RNO:232-240), so:
 //   sphere: det > 0, far root > 0, and the entry root (or the far root when the origin is inside) < reach;
 //           the three square roots share one warp vote;
-//   plane:  dist = num/d is never formed unless the comparison is within rounding distance of the limit:
-//           with m = reach*|d| (rounded), |num| < m*(1-2^-21) proves 0 < dist < reach and
-//           |num| > m*(1+2^-21) proves dist >= reach (same error analysis as pre-filter B above; the quotient
-//           is normal because |num| > 1e-30 and |d| < 1e7); only the sliver in between takes the division.
+//   plane:  the candidate test of the nearest round with the distance to the light as the limit (pre-filters A
+//           and B): dist = num/d is only formed for a plane that may really lie between the point and the light.
 // `alive` = per-ray participation mask (bit k: ray k exists and was not blocked when the run started; counting
 // builds refresh it per primitive so that the test counters stop exactly at the first blocker).
 RT_HD int w_alive_mask(const WLane &L, bool has) { return has ? (((1 << L.ns) - 1) & ~L.sblk) : 0; }
@@ -214,23 +223,23 @@ RT_HD void w_shadow_sphere(WLane &L, const f4 g, int alive_in, bool has) {
         b[k] = -dot3(vx, vy, vz, L.slx[k], L.sly[k], L.slz[k]);
         const float bb = f_mul(b[k], b[k]);
         det[k] = f_add(f_sub(bb, dot3(vx, vy, vz, vx, vy, vz)), g.w);
-        cand[k] = ((alive >> k) & 1) && det[k] > 0.f && !w_sphere_behind(b[k], bb, det[k]);
-        any = any || cand[k];
+        cand[k] = (((alive >> k) & 1) != 0) & (det[k] > 0.f) & !w_sphere_behind(b[k], bb, det[k]);
+        any = any | cand[k];
     }
     if (warp_any(any)) {
         float sq[W_SHADOW_BATCH];
-        sqrt_group<W_SHADOW_BATCH>(det, sq);
+        sqrt_group<W_SHADOW_BATCH>(det, cand, sq);
 #pragma unroll
         for (int k = 0; k < W_SHADOW_BATCH; k++) {
             const float i1 = f_sub(b[k], sq[k]), i2 = f_add(b[k], sq[k]);
             const float t = i1 < 0.f ? i2 : i1;
-            if (cand[k] && i2 > 0.f && t < L.sreach[k]) L.sblk |= 1 << k;
+            if (cand[k] & (i2 > 0.f) & (t < L.sreach[k])) L.sblk |= 1 << k;
         }
     }
 }
 template <bool COUNT>
 RT_HD void w_shadow_plane(WLane &L, const f4 g, int alive_in, bool has) {
-    float d[W_SHADOW_BATCH], num[W_SHADOW_BATCH];
+    float d[W_SHADOW_BATCH], sv[W_SHADOW_BATCH];
     bool cand[W_SHADOW_BATCH];
     bool any = false;
     const int alive = COUNT ? w_alive_mask(L, has) : alive_in;
@@ -238,20 +247,17 @@ RT_HD void w_shadow_plane(WLane &L, const f4 g, int alive_in, bool has) {
     for (int k = 0; k < W_SHADOW_BATCH; k++) {
         if (COUNT && ((alive >> k) & 1)) L.c_plane_tests++;
         d[k] = dot3(g.x, g.y, g.z, L.slx[k], L.sly[k], L.slz[k]);
-        num[k] = -f_add(dot3(g.x, g.y, g.z, L.sox[k], L.soy[k], L.soz[k]), g.w);
-        // dist = num/d > 0 needs both non-zero and of equal sign; and |num| > (reach*|d|)*(1+2^-21) proves
-        // dist >= reach (pre-filter B).  What survives -- a plane that may really block -- takes the division.
-        const bool same_sign = (int)(f_bits(num[k]) ^ f_bits(d[k])) >= 0;
-        const float hi = f_mul(f_mul(L.sreach[k], fabsf(d[k])), 1.000000476837158203125f);
-        const bool beyond = fabsf(num[k]) > hi && hi > 1e-30f;
-        cand[k] = ((alive >> k) & 1) && same_sign && d[k] != 0.f && num[k] != 0.f && !beyond;
-        any = any || cand[k];
+        sv[k] = f_add(dot3(g.x, g.y, g.z, L.sox[k], L.soy[k], L.soz[k]), g.w);
+        // pre-filters A and B with the distance to the light as the limit: what survives -- a plane that may
+        // really block -- takes the division.
+        cand[k] = (((alive >> k) & 1) != 0) & w_plane_candidate(sv[k], d[k], L.sreach[k]);
+        any = any | cand[k];
     }
     if (warp_any(any)) {
 #pragma unroll
         for (int k = 0; k < W_SHADOW_BATCH; k++) {
-            const float dist = f_div(num[k], d[k]);
-            if (cand[k] && dist > 0.f && dist < L.sreach[k]) L.sblk |= 1 << k;
+            const float dist = f_div(-sv[k], d[k]);
+            if (cand[k] & (dist > 0.f) & (dist < L.sreach[k])) L.sblk |= 1 << k;
         }
     }
 }
