@@ -216,6 +216,21 @@ int rt_selftest_math(rt_ctx *ctx, int op, const float *in, void *out, uint64_t n
 
 /* UpdateCamera (SPT/displayfunc.cpp:182-195): derives dir, x, y from orig, target and the image size. */
 void rt_update_camera(rt_camera *cam, int w, int h);
+/* keyFunc / specialFunc of the reference viewer (SPT/displayfunc.cpp:252-420) without GLUT: applies ONE key press
+ * to the caller's camera and sphere table exactly as the viewer does (same float / double expression order, including
+ * the rotation keys' use of the already-updated component) and returns what the viewer would do next:
+ *   RT_KEY_NONE     nothing changed ('h', unknown keys)
+ *   RT_KEY_CAMERA   ReInit(0): the camera moved and rt_update_camera has been applied -> rt_pt_set_camera
+ *   RT_KEY_SCENE    ReInitScene(): the selected sphere moved or the selection changed -> rt_pt_set_scene
+ *   RT_KEY_RESTART  ' ': ReInit(1), the viewer frees and re-allocates its buffers -> rt_pt_resize with fresh seeds
+ *   RT_KEY_DUMP     'p': write image.ppm -> rt_write_ppm;    RT_KEY_QUIT  Escape
+ * Every one of CAMERA / SCENE / RESTART restarts the progressive image at sample 0, which is what
+ * rt_pt_set_camera / rt_pt_set_scene / rt_pt_resize do.  Keys: the viewer's characters; the GLUT special keys are
+ * passed as RT_KEY_SPECIAL + GLUT code (UP 101, DOWN 103, LEFT 100, RIGHT 102, PAGE_UP 104, PAGE_DOWN 105).
+ * *current_sphere is the viewer's selection ('+' / '-'), 0 at start. */
+enum { RT_KEY_NONE = 0, RT_KEY_CAMERA = 1, RT_KEY_SCENE = 2, RT_KEY_RESTART = 3, RT_KEY_DUMP = 4, RT_KEY_QUIT = 5 };
+#define RT_KEY_SPECIAL 0x100
+int rt_viewer_key(int key, rt_camera *cam, int w, int h, rt_sphere *spheres, uint32_t n, uint32_t *current_sphere);
 /* ReadScene (SPT/displayfunc.cpp:120-180): parses a .scn file.  *spheres_out is malloc'd
  * (free with rt_free); cam_out receives orig/target only.  Returns RT_OK or RT_ERR_IO. */
 int rt_read_scene(const char *path, rt_camera *cam_out, rt_sphere **spheres_out, uint32_t *n_out);

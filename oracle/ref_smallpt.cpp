@@ -34,6 +34,9 @@ static void drop_buffers() {
     colors = 0; seeds = 0; pixels = 0;
 }
 
+void keyFunc(unsigned char key, int x, int y);      // displayfunc.cpp:252, :367 (C++ linkage)
+void specialFunc(int key, int x, int y);
+
 extern "C" {
 
 // ReadScene + UpdateCamera of the reference (displayfunc.cpp:120-195). Returns the sphere count.
@@ -133,6 +136,14 @@ void ref_pt_render_mt(int integrator, int pass0, int n_passes, float *colors_io,
     }
     for (int k = 0; k < threads; k++) pthread_join(t[k], 0);
     free(t); free(j);
+}
+
+// One key press through the reference's own GLUT callbacks (displayfunc.cpp:252-420).  ReInit(0) / ReInitScene()
+// restart the image and, in the CPU build, render one pass at once -- so the render buffers must exist
+// (ref_pt_render first; keep the image tiny).  Returns currentSample afterwards (1 after a camera key).
+int ref_pt_key(int key, int special) {
+    if (special) specialFunc(key, 0, 0); else keyFunc((unsigned char)key, 0, 0);
+    return currentSample;
 }
 
 // Known-answer taps on the reference's own inline functions.

@@ -81,6 +81,7 @@ SYMBOLS = {
     "rt_stream": (_VP, [_VP]),
     "rt_set_stream": (_I, [_VP, _VP]),
     "rt_update_camera": (None, [_VP, _I, _I]),
+    "rt_viewer_key": (_I, [_I, _VP, _I, _I, _VP, _U32, C.POINTER(_U32)]),
     "rt_read_scene": (_I, [C.c_char_p, _VP, C.POINTER(_VP), C.POINTER(_U32)]),
     "rt_write_complex_scene": (_I, [C.c_char_p, _I]),
     "rt_whitted_create_scene": (_I, [_I, _VP, _I]),
@@ -123,6 +124,27 @@ def update_camera(cam, w, h):
     assert cam.dtype == CAMERA_DTYPE and cam.size == 1
     lib().rt_update_camera(_ptr(cam), w, h)
     return cam
+
+
+KEY_NONE, KEY_CAMERA, KEY_SCENE, KEY_RESTART, KEY_DUMP, KEY_QUIT = 0, 1, 2, 3, 4, 5
+KEY_SPECIAL = 0x100
+KEY_UP, KEY_DOWN, KEY_LEFT, KEY_RIGHT, KEY_PAGE_UP, KEY_PAGE_DOWN = (KEY_SPECIAL + c for c in (101, 103, 100, 102, 104, 105))
+
+
+class ViewerState:
+    """What the reference viewer keeps between key presses (SPT/displayfunc.cpp): camera, sphere table, selection."""
+
+    def __init__(self, spheres, cam, w, h):
+        self.spheres, self.cam, self.w, self.h = spheres.copy(), cam.copy(), w, h
+        self.current = C.c_uint32(0)
+
+    def key(self, key):
+        """keyFunc / specialFunc for one key (a character or one of the KEY_* specials); returns the KEY_* action."""
+        code = ord(key) if isinstance(key, str) else int(key)
+        rc = lib().rt_viewer_key(code, _ptr(self.cam), self.w, self.h, _ptr(self.spheres), self.spheres.size, C.byref(self.current))
+        if rc < 0:
+            raise RtError(rc, f"rt_viewer_key({key!r})")
+        return rc
 
 
 def read_scene(path, w, h):

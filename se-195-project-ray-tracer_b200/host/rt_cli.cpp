@@ -9,8 +9,13 @@
 // instead renders the Raytracer3.2.03 frame (R323/raytracer.c:705-797) and writes test.bmp; the scene argument
 // is then CHOOSE_SCENE (0 or 1, R323/common.h:6).
 //
-//   rt_cli 1 64 rendering_kernel.cl 640 480 scenes/cornell.scn [passes=64] [out=image.ppm]
+//   rt_cli 1 64 rendering_kernel.cl 640 480 scenes/cornell.scn [passes=64] [out=image.ppm] [keys]
 //   rt_cli 1 64 raytracer_kernel.cl 800 600 0 [ignored] [out=test.bmp]
+//
+// `keys` scripts an interactive session: each character is one key press of the reference viewer
+// (SPT/displayfunc.cpp:252-420: a d w s r f move the camera, + - 4 6 8 2 9 3 select / move a sphere, space restarts,
+// U D L R < > stand for the arrow and page keys), applied by rt_viewer_key after `passes` passes; the camera or scene
+// is re-uploaded, the image restarts at sample 0 as in ReInit / ReInitScene, and `passes` more passes are rendered.
 //
 // Seeds follow the reference: 2*w*h draws of libc rand(), each raised to >= 2 (SPT/smallptGPU.cpp:105-110).
 // The device argument must be 1: there is no CPU path.  The work-group argument is accepted and ignored (the
@@ -71,6 +76,22 @@ int main(int argc, char **argv) {
         if (!rc) rc = rt_pt_set_camera(ctx, &cam);
         const double t0 = now();
         if (!rc) rc = rt_pt_render(ctx, integrator, passes < 1 ? 1 : passes, pixels.data(), nullptr, nullptr);
+        uint32_t current_sphere = 0;
+        for (const char *k = argc > 9 ? argv[9] : ""; *k && !rc; ++k) {
+            int key = (unsigned char)*k;
+            switch (*k) { case 'U': key = RT_KEY_SPECIAL + 101; break; case 'D': key = RT_KEY_SPECIAL + 103; break; case 'L': key = RT_KEY_SPECIAL + 100; break;
+                          case 'R': key = RT_KEY_SPECIAL + 102; break; case '<': key = RT_KEY_SPECIAL + 104; break; case '>': key = RT_KEY_SPECIAL + 105; break; default: break; }
+            const int action = rt_viewer_key(key, &cam, w, h, spheres, n, &current_sphere);
+            if (action == RT_KEY_CAMERA) rc = rt_pt_set_camera(ctx, &cam);
+            else if (action == RT_KEY_SCENE) rc = rt_pt_set_scene(ctx, spheres, n);
+            else if (action == RT_KEY_RESTART) {
+                for (auto &s : seeds) { s = (uint32_t)rand(); if (s < 2) s = 2; }
+                rc = rt_pt_resize(ctx, w, h, seeds.data());
+            } else if (action == RT_KEY_QUIT) break;
+            else if (action == RT_KEY_DUMP) { rc = rt_write_ppm("image.ppm", pixels.data(), w, h); continue; }
+            else continue;
+            if (!rc) rc = rt_pt_render(ctx, integrator, passes < 1 ? 1 : passes, pixels.data(), nullptr, nullptr);
+        }
         const double dt = now() - t0;
         if (rc) fprintf(stderr, "%s\n", rt_last_error(ctx));
         else {

@@ -87,6 +87,62 @@ void rt_update_camera(rt_camera *cam, int w, int h) {       // SPT/displayfunc.c
     cam->y.x = fov * cy.x; cam->y.y = fov * cy.y; cam->y.z = fov * cy.z;
 }
 
+// One key press of the reference viewer, SPT/displayfunc.cpp:250-420.  MOVE_STEP is a float; ROTATE_STEP is
+// (2.f * M_PI / 180.f), a double, so the rotation keys evaluate in double and round once per assignment.
+int rt_viewer_key(int key, rt_camera *cam, int w, int h, rt_sphere *spheres, uint32_t n, uint32_t *current_sphere) {
+    if (!cam) return RT_ERR_ARG;
+    const float MOVE_STEP = 10.0f;
+    const double ROTATE_STEP = 2.f * M_PI / 180.f;
+    auto slide = [&](rt_vec dir, float k) {                 // vsmul + two vadd
+        const rt_vec d = { k * dir.x, k * dir.y, k * dir.z };
+        cam->orig.x = cam->orig.x + d.x; cam->orig.y = cam->orig.y + d.y; cam->orig.z = cam->orig.z + d.z;
+        cam->target.x = cam->target.x + d.x; cam->target.y = cam->target.y + d.y; cam->target.z = cam->target.z + d.z;
+    };
+    auto moved = [&]() { rt_update_camera(cam, w, h); return (int)RT_KEY_CAMERA; };
+    auto sphere_key = [&](float dx, float dy, float dz) {
+        if (!spheres || !current_sphere || *current_sphere >= n) return (int)RT_ERR_ARG;
+        rt_sphere &s = spheres[*current_sphere];
+        if (dx != 0.f) s.p.x += dx;
+        if (dy != 0.f) s.p.y += dy;
+        if (dz != 0.f) s.p.z += dz;
+        return (int)RT_KEY_SCENE;
+    };
+    if (key >= RT_KEY_SPECIAL) {
+        rt_vec t = { cam->target.x - cam->orig.x, cam->target.y - cam->orig.y, cam->target.z - cam->orig.z };
+        switch (key - RT_KEY_SPECIAL) {
+            case 101: t.y = t.y * cos(-ROTATE_STEP) + t.z * sin(-ROTATE_STEP); t.z = -t.y * sin(-ROTATE_STEP) + t.z * cos(-ROTATE_STEP); break;   // UP
+            case 103: t.y = t.y * cos(ROTATE_STEP) + t.z * sin(ROTATE_STEP); t.z = -t.y * sin(ROTATE_STEP) + t.z * cos(ROTATE_STEP); break;       // DOWN
+            case 100: t.x = t.x * cos(-ROTATE_STEP) - t.z * sin(-ROTATE_STEP); t.z = t.x * sin(-ROTATE_STEP) + t.z * cos(-ROTATE_STEP); break;    // LEFT
+            case 102: t.x = t.x * cos(ROTATE_STEP) - t.z * sin(ROTATE_STEP); t.z = t.x * sin(ROTATE_STEP) + t.z * cos(ROTATE_STEP); break;        // RIGHT
+            case 104: cam->target.y += MOVE_STEP; return moved();                                                                                // PAGE_UP
+            case 105: cam->target.y -= MOVE_STEP; return moved();                                                                                // PAGE_DOWN
+            default: return RT_KEY_NONE;
+        }
+        cam->target.x = t.x + cam->orig.x; cam->target.y = t.y + cam->orig.y; cam->target.z = t.z + cam->orig.z;
+        return moved();
+    }
+    switch (key) {
+        case 'p': return RT_KEY_DUMP;
+        case 27: return RT_KEY_QUIT;
+        case ' ': rt_update_camera(cam, w, h); return RT_KEY_RESTART;
+        case 'a': slide(unit(cam->x), -MOVE_STEP); return moved();
+        case 'd': slide(unit(cam->x), MOVE_STEP); return moved();
+        case 'w': slide(cam->dir, MOVE_STEP); return moved();
+        case 's': slide(cam->dir, -MOVE_STEP); return moved();
+        case 'r': cam->orig.y += MOVE_STEP; cam->target.y += MOVE_STEP; return moved();
+        case 'f': cam->orig.y -= MOVE_STEP; cam->target.y -= MOVE_STEP; return moved();
+        case '+': if (!current_sphere || !n) return RT_ERR_ARG; *current_sphere = (*current_sphere + 1) % n; return RT_KEY_SCENE;
+        case '-': if (!current_sphere || !n) return RT_ERR_ARG; *current_sphere = (*current_sphere + (n - 1)) % n; return RT_KEY_SCENE;
+        case '4': return sphere_key(-0.5f * MOVE_STEP, 0.f, 0.f);
+        case '6': return sphere_key(0.5f * MOVE_STEP, 0.f, 0.f);
+        case '8': return sphere_key(0.f, 0.f, -0.5f * MOVE_STEP);
+        case '2': return sphere_key(0.f, 0.f, 0.5f * MOVE_STEP);
+        case '9': return sphere_key(0.f, 0.5f * MOVE_STEP, 0.f);
+        case '3': return sphere_key(0.f, -0.5f * MOVE_STEP, 0.f);
+        default: return RT_KEY_NONE;
+    }
+}
+
 int rt_read_scene(const char *path, rt_camera *cam_out, rt_sphere **spheres_out, uint32_t *n_out) {   // SPT/displayfunc.cpp:120-180
     if (!path || !cam_out || !spheres_out || !n_out) return RT_ERR_ARG;
     *spheres_out = nullptr; *n_out = 0;

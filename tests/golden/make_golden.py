@@ -11,6 +11,8 @@ and the compiled oracle/_ref exist).  The fixtures are OUTPUTS of the reference'
                               for the path-tracing and the direct-lighting integrator.
   smallpt_kat.json            GetRandom and SphereIntersect known answers from the compiled reference.
   complex_scene_md5.json      md5 of `perl scene_build_complex.pl` output for $maxDepth 1..5.
+  viewer_keys.json            a scripted session through the reference viewer's own keyFunc / specialFunc
+                              (displayfunc.cpp compiled in oracle/_ref): camera and sphere table after every key.
 """
 import ctypes, hashlib, json, os, re, struct, subprocess, sys, zlib
 import numpy as np
@@ -101,8 +103,31 @@ def complex_scene():
     json.dump(md5, open(os.path.join(HERE, "complex_scene_md5.json"), "w"), indent=1)
 
 
+VIEWER_KEYS = ["a", "a", "w", "S103", "d", "r", "S100", "S100", "S101", "s", "f", "S102", "S104", "S105", "+", "+", "4", "9", "-", "8", "2", "6", "3",
+               "S101", "S101", "w", "+", "+", "+", "+", "+", "+", "+", "+", "6", "h"]
+
+
+def viewer_keys():
+    L = ctypes.CDLL(os.path.join(ROOT, "oracle/_ref/libref_smallpt.so"))
+    w, h = 8, 6
+    n = L.ref_pt_load_scene(os.path.join(SPT, "scenes", "cornell.scn").encode(), w, h)
+    seeds = np.full(2 * w * h, 7, np.uint32)
+    L.ref_pt_render(vp(seeds), 1, None, None, None)                 # the key handlers re-render: buffers must exist
+    steps = []
+    for k in VIEWER_KEYS:
+        L.ref_pt_key(int(k[1:]) if k.startswith("S") else ord(k), 1 if k.startswith("S") else 0)
+        sph = np.zeros(n * 11, np.float32); cam = np.zeros(15, np.float32)
+        L.ref_pt_get_scene(vp(sph), vp(cam))
+        steps.append({"key": k, "camera": ["%08x" % v for v in cam.view(np.uint32)],
+                      "spheres_sha256": hashlib.sha256(sph.tobytes()).hexdigest()})
+    json.dump({"scene": "cornell.scn", "w": w, "h": h, "steps": steps}, open(os.path.join(HERE, "viewer_keys.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container)")
-    whitted(); smallpt(); complex_scene()
+    only = sys.argv[1:]
+    for name, fn in (("whitted", whitted), ("smallpt", smallpt), ("complex_scene", complex_scene), ("viewer_keys", viewer_keys)):
+        if not only or name in only:
+            fn()
     print("golden fixtures written to", HERE)

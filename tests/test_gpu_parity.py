@@ -375,6 +375,55 @@ def test_cli_with_the_reference_command_line(gpu, orc, rt, whitted_golden, tmp_p
     assert subprocess.run([cli, "0", "64", "rendering_kernel.cl", "8", "8", str(scn)], capture_output=True).returncode == 2   # no CPU device
 
 
+def test_scripted_interactive_session(gpu, orc, rt, cornell, tmp_path):
+    """The caller side of the boundary (SPT/displayfunc.cpp:237-420) without GLUT: key presses through rt_viewer_key,
+    then the re-upload the viewer's ReInit(0) / ReInitScene() would do.  After every key the image restarts at sample 0
+    with the RNG state left where it was, and equals the oracle rendered with the same camera / scene / seeds."""
+    import os
+    import subprocess
+    spheres, cam = cornell
+    w, h, passes = 64, 48, 2
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=21)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    out = gpu.pt_render(0, passes)
+    view = rt.ViewerState(spheres, cam, w, h)
+    for key in ["a", rt.KEY_UP, "+", "+", "+", "+", "+", "+", "9", "w", rt.KEY_LEFT, "4", "h", rt.KEY_PAGE_DOWN]:
+        action = view.key(key)
+        if action == rt.KEY_CAMERA:
+            gpu.pt_set_camera(view.cam)
+        elif action == rt.KEY_SCENE:
+            gpu.pt_set_scene(view.spheres)
+        else:
+            continue
+        assert gpu.pt_current_sample() == 0
+        seeds_before = out["seeds"].reshape(-1)
+        out = gpu.pt_render(0, passes)
+        col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, view.spheres, view.cam, w, h, seeds_before, passes)
+        assert np.array_equal(out["seeds"].reshape(-1), sd_o), key
+        assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32)), key
+        assert np.array_equal(out["pixels"].reshape(-1), pix_o), key
+    # the same kind of session through the headless driver's key script
+    cli = os.path.join(os.path.dirname(rt.LIB_PATH), "rt_cli")
+    scn = tmp_path / "c1.scn"
+    rt.write_complex_scene(str(scn), 1)
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    sd = np.array([max(libc.rand(), 2) for _ in range(2 * w * h)], np.uint32)
+    sph, c0 = rt.read_scene(str(scn), w, h)
+    ppm = tmp_path / "session.ppm"
+    p = subprocess.run([cli, "1", "64", "rendering_kernel.cl", str(w), str(h), str(scn), str(passes), str(ppm), "dU+6s"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    view = rt.ViewerState(sph, c0, w, h)
+    _, sd, pix_o, _ = oracle_pt(orc, 0, view.spheres, view.cam, w, h, sd, passes)
+    for key in ["d", rt.KEY_UP, "+", "6", "s"]:
+        view.key(key)
+        _, sd, pix_o, _ = oracle_pt(orc, 0, view.spheres, view.cam, w, h, sd, passes)
+    want = tmp_path / "want.ppm"
+    rt.write_ppm(str(want), pix_o.reshape(h, w))
+    assert ppm.read_bytes() == want.read_bytes()
+
+
 # ------------------------------------------------------------------------------------------ error behaviour
 def test_errors_are_codes_not_exits(gpu, rt, cornell):
     spheres, cam = cornell

@@ -100,3 +100,21 @@ def test_builtin_cornell_equals_scn_fixture(rt):
     g = load_smallpt_golden(rt, "cornell")
     spheres, cam = rt.cornell_scene(g["w"], g["h"])
     assert spheres.tobytes() == g["spheres"].tobytes() and cam.tobytes() == g["camera"].tobytes()
+
+
+def test_viewer_keys_equal_the_reference_callbacks(rt, cornell):
+    """rt_viewer_key against a session scripted through the reference's own keyFunc / specialFunc (fixture made by
+    tests/golden/make_golden.py viewer_keys from oracle/_ref): camera bits and sphere table after every key press."""
+    g = json.load(open(os.path.join(GOLDEN, "viewer_keys.json")))
+    spheres, cam = cornell
+    cam = cam.copy()
+    rt.update_camera(cam, g["w"], g["h"])
+    v = rt.ViewerState(spheres, cam, g["w"], g["h"])
+    for i, step in enumerate(g["steps"]):
+        k = step["key"]
+        action = v.key(rt.KEY_SPECIAL + int(k[1:]) if k.startswith("S") else k)
+        want = {"+": rt.KEY_SCENE, "-": rt.KEY_SCENE, "h": rt.KEY_NONE}.get(k, rt.KEY_SCENE if k in "468293" else rt.KEY_CAMERA)
+        assert action == want, (i, k, action)
+        assert ["%08x" % x for x in v.cam.view(np.uint32).reshape(-1)] == step["camera"], (i, k)
+        assert hashlib.sha256(v.spheres.view(np.float32).tobytes()).hexdigest() == step["spheres_sha256"], (i, k)
+    assert v.key(" ") == rt.KEY_RESTART and v.key("p") == rt.KEY_DUMP and v.key(chr(27)) == rt.KEY_QUIT
