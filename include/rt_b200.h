@@ -54,6 +54,14 @@ typedef struct {                                               /* R323/common.h:
     float depth, radius, sq_radius, r_radius;
 } rt_primitive;
 
+enum { RT_R306_SPHERE = 1, RT_R306_PLANE = 2 };                /* R306/raytracer.h:13-17 PRIMTYPE */
+typedef struct {                                               /* R306/raytracer.h:19-34 Primitive + Material (96 B) */
+    int32_t type, m_light;
+    rt_vec centre; float sq_radius, radius, r_radius;
+    rt_vec plane_n; float plane_d, plane_cell[4];              /* R306/common.h:47-51 plane */
+    rt_vec m_color; float m_refl, m_refr, m_diff, m_spec, m_rindex;
+} rt_r306_primitive;
+
 typedef enum {
     RT_OK = 0,
     RT_ERR_NO_DEVICE = -1,   /* no usable CUDA device / driver: the product never falls back to the CPU */
@@ -131,6 +139,19 @@ int rt_whitted_render(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
 int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int h, int want_hit_ids);
 int rt_whitted_launch(rt_ctx *ctx);
 int rt_whitted_download(rt_ctx *ctx, rt_uchar4 *pixels_out, int32_t *hit_id_out);
+
+/* ------------------------------------------------------------------ raytracer3.0.06 (BASELINE config 1)
+ *
+ * The CPU tracer of raytracer3.0.06.no_rec.samp -- the reference's own baseline program -- as a GPU frame:
+ * Engine_SetTarget + Engine_InitRender + Engine_Render (R306/raytracer.cpp:17-23, :278-530) over Engine_Raytrace
+ * (:30-271).  Same intersection core as the 3.2.03 tracer, different everything else (63-node implicit ray tree folded
+ * bottom-up, running-sum screen coordinates, rows 20 .. h-71 only, 0x00RRGGBB pixels); see csrc/r306_lane.cuh.
+ * dest: w*h Pixels (unsigned int); like the reference, rows outside 20 .. h-71 are left untouched, so h must be > 90. */
+int rt_r306_render(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, int h, uint32_t *dest);
+/* The same in three steps (scene + screen tables to HBM, asynchronous kernel, blocking read-back of the rendered rows). */
+int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, int h);
+int rt_r306_launch(rt_ctx *ctx);
+int rt_r306_download(rt_ctx *ctx, uint32_t *dest);
 
 /* ------------------------------------------------------------------ smallpt path tracer
  *
@@ -240,6 +261,8 @@ int rt_write_complex_scene(const char *path, int max_depth);
 /* create_scene + the Primitive -> Primitive_2 copy (R323/scene.c:48-128, R323/raytracer.c:721-746).
  * which = CHOOSE_SCENE (0: 17 slots, 1: 64 slots).  Returns the primitive count, or <0. */
 int rt_whitted_create_scene(int which, rt_primitive *out, int cap);
+/* Scene_InitScene (R306/scene.cpp:217-272): the 17 primitives of the 3.0.06 program.  Returns the count, or <0. */
+int rt_r306_create_scene(rt_r306_primitive *out, int cap);
 /* write_bmp_file (R323/bitmap.c:8-75): 24-bit BMP, bottom row first, BGR. */
 int rt_write_bmp(const char *path, const rt_uchar4 *pixels, int w, int h);
 /* The 'p' key of the reference viewer (SPT/displayfunc.cpp:254-271): P3 PPM, bottom row first. */

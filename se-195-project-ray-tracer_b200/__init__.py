@@ -28,7 +28,12 @@ PRIMITIVE_DTYPE = np.dtype([
     ("m_spec", "<f4"), ("dummy_3", "<f4"), ("type", "<i4"), ("is_light", "u1"), ("pad_", "u1", 3),
     ("normal", "<f4", 4), ("center", "<f4", 4), ("depth", "<f4"), ("radius", "<f4"), ("sq_radius", "<f4"),
     ("r_radius", "<f4")])
+R306_PRIMITIVE_DTYPE = np.dtype([                    # R306/raytracer.h:19-34 Primitive (+ Material)
+    ("type", "<i4"), ("m_light", "<i4"), ("centre", "<f4", 3), ("sq_radius", "<f4"), ("radius", "<f4"), ("r_radius", "<f4"),
+    ("plane_n", "<f4", 3), ("plane_d", "<f4"), ("plane_cell", "<f4", 4),
+    ("m_color", "<f4", 3), ("m_refl", "<f4"), ("m_refr", "<f4"), ("m_diff", "<f4"), ("m_spec", "<f4"), ("m_rindex", "<f4")])
 assert SPHERE_DTYPE.itemsize == 44 and CAMERA_DTYPE.itemsize == 60 and PRIMITIVE_DTYPE.itemsize == 96
+assert R306_PRIMITIVE_DTYPE.itemsize == 96
 
 
 class Counters(C.Structure):
@@ -59,6 +64,11 @@ SYMBOLS = {
     "rt_whitted_upload": (_I, [_VP, _VP, _I, _I, _I, _I]),
     "rt_whitted_launch": (_I, [_VP]),
     "rt_whitted_download": (_I, [_VP, _VP, _VP]),
+    "rt_r306_render": (_I, [_VP, _VP, _I, _I, _I, _VP]),
+    "rt_r306_upload": (_I, [_VP, _VP, _I, _I, _I]),
+    "rt_r306_launch": (_I, [_VP]),
+    "rt_r306_download": (_I, [_VP, _VP]),
+    "rt_r306_create_scene": (_I, [_VP, _I]),
     "rt_pt_resize": (_I, [_VP, _I, _I, _VP]),
     "rt_pt_set_scene": (_I, [_VP, _VP, _U32]),
     "rt_pt_set_camera": (_I, [_VP, _VP]),
@@ -174,6 +184,15 @@ def whitted_create_scene(which=0):
     n = lib().rt_whitted_create_scene(which, _ptr(out), out.size)
     if n < 0:
         raise RtError(n, "rt_whitted_create_scene")
+    return out[:n].copy()
+
+
+def r306_create_scene():
+    """Scene_InitScene of R306/scene.cpp:217-272 as flat Primitive records."""
+    out = np.zeros(32, R306_PRIMITIVE_DTYPE)
+    n = lib().rt_r306_create_scene(_ptr(out), out.size)
+    if n < 0:
+        raise RtError(n, "rt_r306_create_scene")
     return out[:n].copy()
 
 
@@ -438,6 +457,22 @@ class Renderer:
         self._ck(self._lib.rt_whitted_render(self._ctx, _ptr(prims), prims.size, w, h, _ptr(pixels), _ptr(hits)))
         self.whitted_size = (w, h)
         return (pixels, hits) if want_hit_ids else pixels
+
+    def r306_render(self, prims, w, h, dest=None):
+        """Engine_Render of raytracer3.0.06: w*h Pixels 0x00RRGGBB; rows outside 20 .. h-71 keep what `dest` held."""
+        prims = np.ascontiguousarray(prims)
+        assert prims.dtype == R306_PRIMITIVE_DTYPE
+        dest = dest if dest is not None else np.zeros((h, w), np.uint32)
+        self._ck(self._lib.rt_r306_render(self._ctx, _ptr(prims), prims.size, w, h, _ptr(dest)))
+        return dest
+
+    def r306_upload(self, prims, w, h):
+        prims = np.ascontiguousarray(prims)
+        assert prims.dtype == R306_PRIMITIVE_DTYPE
+        self._ck(self._lib.rt_r306_upload(self._ctx, _ptr(prims), prims.size, w, h))
+
+    def r306_launch(self):
+        self._ck(self._lib.rt_r306_launch(self._ctx))
 
     def whitted_upload(self, prims, w, h, want_hit_ids=False):
         prims = np.ascontiguousarray(prims)

@@ -44,6 +44,15 @@ struct rt_ctx {
     size_t w_pixels_cap = 0, w_hits_cap = 0;
     size_t cap_wgeom = 0, cap_wma = 0, cap_wmb = 0, cap_wflags = 0, cap_wlights = 0, cap_wrrad = 0, cap_wruns = 0;
     size_t cap_pgeom = 0, cap_pemis = 0, cap_pcolr = 0, cap_plights = 0;
+    // raytracer3.0.06 frame (config 1)
+    struct {
+        f4 *geom = nullptr, *ma = nullptr, *mb = nullptr; int *flags = nullptr, *lights = nullptr, *runs = nullptr; float *rrad = nullptr, *sx = nullptr, *sy = nullptr;
+        size_t cap_geom = 0, cap_ma = 0, cap_mb = 0, cap_flags = 0, cap_lights = 0, cap_runs = 0, cap_rrad = 0, cap_sx = 0, cap_sy = 0;
+        uint32_t *dest = nullptr; size_t dest_cap = 0;
+        int w = 0, h = 0, n = 0, nl = 0, nr = 0, ns = 0, np = 0;
+        float DX = 0.f, DY = 0.f;
+        WSoA soa; std::vector<float> h_sx, h_sy;
+    } r306;
     WSoA w_soa;                                    // host staging of the last uploaded scenes (kept alive
     PtSoA p_soa;                                   //  until the asynchronous copies have been issued and synced)
     bool own_stream = true;
@@ -136,6 +145,8 @@ void rt_destroy(rt_ctx *ctx) {
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
     for (void *b : bufs) if (b) cudaFree(b);
+    void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest };
+    for (void *b : rbufs) if (b) cudaFree(b);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -279,6 +290,78 @@ int rt_whitted_render(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     if (rc) return rc;
     if ((rc = rt_whitted_launch(ctx))) return rc;
     return rt_whitted_download(ctx, pixels_out, hit_id_out);
+}
+
+// ------------------------------------------------------------------------------------------------ raytracer3.0.06
+
+int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, int h) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!prims || n < 1 || w < 1 || h <= 90) return fail(ctx, RT_ERR_ARG, "rt_r306_upload: need prims, n >= 1, w >= 1 and h > 90 (rows 20 .. h-71 are rendered)");
+    CK(cudaSetDevice(ctx->device));
+    auto &R = ctx->r306;
+    build_r306_soa(prims, n, R.soa);
+    build_r306_screen(w, h, R.h_sx, R.h_sy, &R.DX, &R.DY);
+    if (rtk_whitted_smem_bytes(n, (int)R.soa.lights.size(), (int)R.soa.runs.size() / 3, 1) > (size_t)ctx->max_smem_optin)
+        return fail(ctx, RT_ERR_CAPACITY, "rt_r306_upload: %d primitives exceed the %d-byte shared-memory staging of this build", n, ctx->max_smem_optin);
+    CK(upload_vec(&R.geom, &R.cap_geom, R.soa.geom, ctx->stream));
+    CK(upload_vec(&R.ma, &R.cap_ma, R.soa.mat_a, ctx->stream));
+    CK(upload_vec(&R.mb, &R.cap_mb, R.soa.mat_b, ctx->stream));
+    CK(upload_vec(&R.flags, &R.cap_flags, R.soa.flags, ctx->stream));
+    CK(upload_vec(&R.lights, &R.cap_lights, R.soa.lights, ctx->stream));
+    CK(upload_vec(&R.runs, &R.cap_runs, R.soa.runs, ctx->stream));
+    CK(upload_vec(&R.rrad, &R.cap_rrad, R.soa.rrad, ctx->stream));
+    CK(upload_vec(&R.sx, &R.cap_sx, R.h_sx, ctx->stream));
+    CK(upload_vec(&R.sy, &R.cap_sy, R.h_sy, ctx->stream));
+    const size_t px = (size_t)w * h;
+    if (px > R.dest_cap) {
+        if (R.dest) cudaFree(R.dest);
+        R.dest = nullptr; R.dest_cap = 0;
+        CK(cudaMalloc((void **)&R.dest, px * sizeof(uint32_t)));
+        R.dest_cap = px;
+    }
+    R.w = w; R.h = h; R.n = n; R.nl = (int)R.soa.lights.size(); R.nr = (int)R.soa.runs.size() / 3;
+    R.ns = R.soa.n_spheres; R.np = R.soa.n_planes;
+    return RT_OK;
+}
+
+int rt_r306_launch(rt_ctx *ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    auto &R = ctx->r306;
+    if (!R.geom || !R.dest) return fail(ctx, RT_ERR_STATE, "rt_r306_launch: call rt_r306_upload first");
+    CK(cudaSetDevice(ctx->device));
+    R306Launch p;
+    WFrame &F = p.frame.W;
+    F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.runs = R.runs; F.n_runs = R.nr;
+    F.rrad = R.rrad; F.n = R.n; F.n_lights = R.nl; F.n_spheres = R.ns; F.n_planes = R.np;
+    F.w = R.w; F.h = R.h; F.DX = R.DX; F.DY = R.DY; F.hit_ids = nullptr;
+    p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;
+    p.shard = make_shard(R.w, R.h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
+    p.dest = R.dest; p.work_counter = ctx->d_work; p.sm_count = ctx->sm_count;
+    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
+    if (p.n_items) { CK(rtk_launch_r306(p, ctx->stream)); ctx->launches++; }
+    return RT_OK;
+}
+
+int rt_r306_download(rt_ctx *ctx, uint32_t *dest) {
+    if (!ctx) return RT_ERR_ARG;
+    auto &R = ctx->r306;
+    if (!R.dest) return fail(ctx, RT_ERR_STATE, "rt_r306_download: nothing rendered yet");
+    if (!dest) return fail(ctx, RT_ERR_ARG, "rt_r306_download: dest is NULL");
+    CK(cudaSetDevice(ctx->device));
+    // only the rows Engine_Render writes (20 .. h-71): everything else in the caller's buffer stays as it was
+    const size_t off = (size_t)20 * R.w, rows = (size_t)(R.h - 70 - 20);
+    CK(cudaMemcpyAsync(dest + off, R.dest + off, rows * R.w * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_r306_render(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, int h, uint32_t *dest) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!dest) return fail(ctx, RT_ERR_ARG, "rt_r306_render: dest is NULL");
+    int rc = rt_r306_upload(ctx, prims, n, w, h);
+    if (rc) return rc;
+    if ((rc = rt_r306_launch(ctx))) return rc;
+    return rt_r306_download(ctx, dest);
 }
 
 // ------------------------------------------------------------------------------------------------ smallpt

@@ -114,6 +114,30 @@ __global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, 
     }
 }
 
+// Stages the scene tables of a WFrame into shared memory and redirects the frame's pointers to the copies.
+// layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | runs[3*n_runs] | rrad[n] (optional) | lights[n_lights] (optional)
+__device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, int stage_materials, f4 *&s_geom, int *&s_runs) {
+    const int n = F.n;
+    s_geom = s_raw;
+    f4 *s_ma = s_geom + n, *s_mb = s_ma + n;
+    int *ibase = stage_materials ? (int *)(s_mb + n) : (int *)(s_geom + n);
+    int *s_flags = ibase;
+    s_runs = ibase + n;
+    float *s_rr = (float *)(s_runs + 3 * F.n_runs);
+    int *s_li = (int *)(s_rr + n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        s_geom[i] = F.geom[i];
+        s_flags[i] = F.flags[i];
+        if (stage_materials) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; }
+    }
+    for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) s_runs[i] = F.runs[i];
+    if (stage_materials)
+        for (int i = threadIdx.x; i < F.n_lights; i += blockDim.x) s_li[i] = F.lights[i];
+    __syncthreads();
+    F.geom = s_geom; F.flags = s_flags;
+    if (stage_materials) { F.mat_a = s_ma; F.mat_b = s_mb; F.rrad = s_rr; F.lights = s_li; }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Whitted: replaces raytracer_kernel (R323/raytracer_kernel.cl:246-383) with the numerics of its CPU
 // twin.  The reference copies the 96-byte AoS primitives to local memory (:254-258) and keeps a
@@ -124,30 +148,9 @@ __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
                uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, int stage_materials) {
     extern __shared__ f4 s_raw[];
-    // layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | runs[3*n_runs] | rrad[n] (optional) | lights[n_lights] (optional)
-    f4 *s_geom = s_raw;
-    int *s_flags, *s_runs;
     const uint32_t lane = threadIdx.x & 31u;
-    {
-        const int n = F.n;
-        f4 *s_ma = s_geom + n, *s_mb = s_ma + n;
-        int *ibase = stage_materials ? (int *)(s_mb + n) : (int *)(s_geom + n);
-        s_flags = ibase;
-        s_runs = ibase + n;
-        float *s_rr = (float *)(s_runs + 3 * F.n_runs);
-        int *s_li = (int *)(s_rr + n);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            s_geom[i] = F.geom[i];
-            s_flags[i] = F.flags[i];
-            if (stage_materials) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; }
-        }
-        for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) s_runs[i] = F.runs[i];
-        if (stage_materials)
-            for (int i = threadIdx.x; i < F.n_lights; i += blockDim.x) s_li[i] = F.lights[i];
-        __syncthreads();
-        F.geom = s_geom; F.flags = s_flags;
-        if (stage_materials) { F.mat_a = s_ma; F.mat_b = s_mb; F.rrad = s_rr; F.lights = s_li; }
-    }
+    f4 *s_geom; int *s_runs;
+    stage_scene(F, s_raw, stage_materials, s_geom, s_runs);
 
     f4 queue[3 * W_QUEUE_SLOTS];
     WLane L;
@@ -194,6 +197,50 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             atomicAdd(&counters[2], (unsigned long long)c); atomicAdd(&counters[3], (unsigned long long)d);
             atomicAdd(&counters[4], (unsigned long long)e);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// raytracer3.0.06 (BASELINE config 1): the frame of Engine_Render (R306/raytracer.cpp:301-530) on the GPU.  Same shape as
+// the Whitted kernel -- persistent warps, one lane per pixel, a nearest round then batched shadow rounds over the
+// shared-memory scene -- around the 63-node implicit ray tree of r306_lane.cuh, which lives in local memory.
+__global__ void __launch_bounds__(W_THREADS)
+r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *work_counter) {
+    extern __shared__ f4 s_raw[];
+    const uint32_t lane = threadIdx.x & 31u;
+    f4 *s_geom; int *s_runs;
+    stage_scene(F.W, s_raw, 1, s_geom, s_runs);
+
+    R306Tree T;
+    R306Lane L;
+    L.q.phase = PH_IDLE;
+    L.q.c_nearest = L.q.c_shadow = L.q.c_samples = 0; L.q.c_sphere_tests = L.q.c_plane_tests = 0;
+    bool exhausted = false;
+
+    for (;;) {
+        const bool need = (L.q.phase == PH_IDLE) && !exhausted;
+        const uint32_t item = fetch_items(work_counter, need, lane);
+        if (need) {
+            if (item < n_items) {
+                int x, y;
+                if (item_to_pixel(S, F.W.w, item, x, y) && y >= F.row0 && y < F.row1) r306_begin_pixel(L, F, x, y);
+            } else exhausted = true;
+        }
+        const bool active = L.q.phase != PH_IDLE;
+        if (!__any_sync(FULL_MASK, active || !exhausted)) break;
+
+        const bool nq = L.q.phase == PH_NEAREST;
+        w_query_nearest<false>(L.q, s_geom, s_runs, F.W.n_runs, nq);
+        bool node_done = false;
+        if (nq) node_done = r306_after_nearest(L, F, T);
+        while (__any_sync(FULL_MASK, L.q.phase == PH_SHADOW)) {
+            const bool sq = L.q.phase == PH_SHADOW;
+            w_query_shadow<false>(L.q, s_geom, s_runs, F.W.n_runs, sq);
+            if (sq) r306_after_shadow(L, F);
+        }
+        if (L.q.phase == PH_FINAL) { r306_finish_hit(L, F, T); node_done = true; }
+        if (node_done && r306_next_node(L, F, T))
+            dest[(size_t)L.q.y * F.W.w + L.q.x] = r306_pack_pixel(L.tr, L.tg, L.tb);
     }
 }
 
@@ -302,6 +349,19 @@ cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, 
 
 cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigned long long n, int sm_count, cudaStream_t stream) {
     selftest_math_kernel<<<sm_count * 8, 256, 0, stream>>>(op, in, out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
+    const size_t smem = rtk_whitted_smem_bytes(p.frame.W.n, p.frame.W.n_lights, p.frame.W.n_runs, 1);
+    cudaError_t e = cudaFuncSetAttribute(r306_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int nb = blocks_per_sm(r306_kernel, W_THREADS, smem);
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    long grid = (long)nb * p.sm_count;
+    const long need = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
+    if (grid > need) grid = need > 0 ? need : 1;
+    r306_kernel<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, p.dest, p.work_counter);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include "pt_lane.cuh"
 #include "whitted_lane.cuh"
+#include "r306_lane.cuh"
 
 // Launch shape (overridable with -D for the A/B builds of tools/variants.sh).
 // smallpt: 128-thread CTAs capped at 64 registers (8 CTAs = 32 warps per SM) measured 6 % faster on Cornell than
@@ -50,6 +51,16 @@ struct WLaunch {
     uint32_t n_valid;           // pixels owned by this rank (n_items minus the padding of the 8x4 blocks)
 };
 
+struct R306Launch {
+    rtb::R306Frame frame;
+    rtb::Shard shard;
+    uint32_t n_items;
+    uint32_t *dest;
+    unsigned *work_counter;
+    int sm_count;
+};
+
+cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream);
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream);
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);

@@ -72,6 +72,44 @@ inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
     }
 }
 
+static_assert(sizeof(rt_r306_primitive) == 96, "rt_r306_primitive must match the reference Primitive (R306/raytracer.h:24-34)");
+
+// The 3.0.06 scene table in the same structure-of-arrays form (its intersection core is the 3.2.03 one):
+// mat_a = (m_Color, m_Refl), mat_b = (m_Diff, m_Refr, m_RIndex, m_Spec).  A type that is neither sphere nor plane is
+// never hit (R306/scene.cpp:185-187): an all-zero plane.
+inline void build_r306_soa(const rt_r306_primitive *p, int n, WSoA &out) {
+    std::vector<rt_primitive> q((size_t)n);
+    for (int i = 0; i < n; i++) {
+        rt_primitive &r = q[i];
+        memset(&r, 0, sizeof r);
+        r.m_color.x = p[i].m_color.x; r.m_color.y = p[i].m_color.y; r.m_color.z = p[i].m_color.z;
+        r.m_refl = p[i].m_refl; r.m_diff = p[i].m_diff; r.m_refr = p[i].m_refr; r.m_refr_index = p[i].m_rindex; r.m_spec = p[i].m_spec;
+        r.is_light = p[i].m_light > 0 ? 1 : 0;
+        if (p[i].type == RT_R306_SPHERE) {
+            r.type = RT_SPHERE;
+            r.center.x = p[i].centre.x; r.center.y = p[i].centre.y; r.center.z = p[i].centre.z;
+            r.radius = p[i].radius; r.sq_radius = p[i].sq_radius; r.r_radius = p[i].r_radius;
+        } else if (p[i].type == RT_R306_PLANE) {
+            r.type = RT_PLANE;
+            r.normal.x = p[i].plane_n.x; r.normal.y = p[i].plane_n.y; r.normal.z = p[i].plane_n.z; r.depth = p[i].plane_d;
+        } else r.type = -1;
+    }
+    build_w_soa(q.data(), n, out);
+}
+
+// Engine_InitRender / Engine_Render screen coordinates (R306/raytracer.cpp:278-296, :313, :523-525): running float sums.
+inline void build_r306_screen(int w, int h, std::vector<float> &sx, std::vector<float> &sy, float *DX, float *DY) {
+    const float WX1 = -3, WX2 = 3, WY1 = 2.25f, WY2 = -2.25f;
+    const float dx = (WX2 - WX1) / w, dy = (WY2 - WY1) / h;
+    sx.assign((size_t)w, 0.f); sy.assign((size_t)h, 0.f);
+    float v = WX1;
+    for (int x = 0; x < w; x++) { sx[x] = v; v += dx; }
+    float u = WY1;
+    u += 20 * dy;
+    for (int y = 20; y < h; y++) { sy[y] = u; u += dy; }
+    *DX = dx; *DY = dy;
+}
+
 // Rows of an h-row frame owned by `rank` when tiles of tile_rows rows are dealt round-robin.
 inline int shard_local_rows(int h, int rank, int world, int tile_rows) {
     int rows = 0;

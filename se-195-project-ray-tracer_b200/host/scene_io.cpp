@@ -143,6 +143,48 @@ int rt_viewer_key(int key, rt_camera *cam, int w, int h, rt_sphere *spheres, uin
     }
 }
 
+// Scene_InitScene + Primitive_Create, R306/scene.cpp:53-82, :217-272 (maxx = maxy = 0: no sphere grid).
+int rt_r306_create_scene(rt_r306_primitive *out, int cap) {
+    struct Row { int type; float a, b, c, rd, r, g, bl, refl, refr, ri, diff, spec; bool light; };
+    const int S = RT_R306_SPHERE, P = RT_R306_PLANE;
+    static const Row rows[] = {
+        { P, 0.0f, 0.75f, 0.0f, 4.4f, 0.6f, 0.6f, 0.6f, 0.0f, 0.0f, 0.0f, 0.4f, 1.8f, false },        // floor plane
+        { S, 0.0f, 6.5f, 22.0f, 0.35f, 0.85f, 0.85f, 0.85f, 0.0f, 0.0f, 0.0f, 1.0f, 1.0f, true },     // light source center
+        { S, 3.4f, -3.40f, 23.0f, 2.5f, 0.08f, 0.08f, 0.08f, 1.9f, 1.0f, 2.3f, 0.0f, 0.0f, false },   // big sphere
+        { S, -0.7f, -4.90f, 27.0f, 1.0f, 0.07f, 0.17f, 0.07f, 0.1f, 1.5f, 2.3f, 0.2f, 0.8f, false },  // small sphere 5
+        { S, -3.4f, -3.40f, 29.0f, 2.5f, 1.0f, 1.0f, 1.0f, 0.8f, 0.0f, 0.0f, 0.0f, 0.0f, false },     // small sphere
+        { S, 0.5f, -4.10f, 29.0f, 1.5f, 1.5f, 0.7f, 0.7f, 0.1f, 0.0f, 0.0f, 0.2f, 0.2f, false },      // small sphere 2
+        { S, -6.0f, -4.10f, 32.0f, 1.5f, 0.7f, 0.7f, 1.7f, 0.2f, 0.0f, 0.0f, 0.2f, 0.2f, false },     // small sphere 3
+        { S, -6.7f, -4.90f, 29.0f, 1.0f, 0.07f, 0.17f, 0.07f, 0.1f, 1.5f, 2.3f, 0.2f, 0.8f, false },  // small sphere 4
+        { S, 6.4f, -4.90f, 18.0f, 1.0f, 0.18f, 0.18f, 0.18f, 1.7f, 1.0f, 2.6f, 1.8f, 0.0f, false },   // small sphere 6
+        { P, 0.7f, 0.0f, 0.0f, 5.4f, 1.0f, 0.6f, 0.6f, 0.0f, 0.0f, 0.0f, 0.8f, 1.5f, false },         // left wall
+        { P, -0.7f, 0.0f, 0.0f, 5.4f, 0.7f, 0.6f, 1.0f, 0.0f, 0.0f, 0.0f, 0.8f, 0.8f, false },        // right wall
+        { P, 0.0f, -0.8f, 0.0f, 5.4f, 1.0f, 1.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.2f, 0.8f, false },        // top wall
+        { P, 0.0f, 0.0f, -0.14f, 5.4f, 2.5f, 2.5f, 2.5f, 0.0f, 0.0f, 0.0f, 1.2f, 0.8f, false },       // back wall
+        { P, 0.0f, 0.0f, 0.72f, 5.4f, 0.1f, 0.1f, 0.1f, 0.0f, 0.0f, 0.0f, 1.0f, 1.0f, false },        // front wall
+        { S, -3.0f, 6.5f, 22.0f, 0.35f, 0.85f, 0.85f, 0.85f, 0.0f, 0.0f, 0.0f, 0.0f, 1.8f, true },    // light source right
+        { S, 3.0f, 6.5f, 22.0f, 0.35f, 0.85f, 0.85f, 0.85f, 0.0f, 0.0f, 0.0f, 0.0f, 1.8f, true },     // light source left
+        { S, -5.8f, -5.55f, 31.0f, 0.35f, 1.15f, 0.35f, 0.35f, 1.0f, 1.0f, 2.3f, 0.0f, 1.8f, true },  // light source ground back
+    };
+    const int n = (int)(sizeof rows / sizeof rows[0]);
+    if (!out || cap < n) return RT_ERR_ARG;
+    for (int i = 0; i < n; i++) {
+        const Row &r = rows[i];
+        rt_r306_primitive &p = out[i];
+        memset(&p, 0, sizeof p);
+        p.type = r.type; p.m_light = r.light ? 1 : 0;
+        p.m_color.x = r.r; p.m_color.y = r.g; p.m_color.z = r.bl;
+        p.m_refl = r.refl; p.m_refr = r.refr; p.m_rindex = r.ri; p.m_diff = r.diff; p.m_spec = r.spec;
+        if (r.type == S) {
+            p.centre.x = r.a; p.centre.y = r.b; p.centre.z = r.c;
+            p.radius = r.rd; p.sq_radius = r.rd * r.rd; p.r_radius = r.rd > 0 ? 1.0f / r.rd : 0;
+        } else {
+            p.plane_n.x = r.a; p.plane_n.y = r.b; p.plane_n.z = r.c; p.plane_d = r.rd;
+        }
+    }
+    return n;
+}
+
 int rt_read_scene(const char *path, rt_camera *cam_out, rt_sphere **spheres_out, uint32_t *n_out) {   // SPT/displayfunc.cpp:120-180
     if (!path || !cam_out || !spheres_out || !n_out) return RT_ERR_ARG;
     *spheres_out = nullptr; *n_out = 0;

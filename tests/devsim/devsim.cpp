@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "../../se-195-project-ray-tracer_b200/csrc/scene_soa.h"
+#include "../../se-195-project-ray-tracer_b200/csrc/r306_lane.cuh"
 
 using namespace rtb;
 
@@ -74,6 +75,39 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
         c[0] += L.c_nearest; c[1] += L.c_shadow; c[2] += L.c_sphere_tests; c[3] += L.c_plane_tests; c[4] += L.c_samples;
     }
     if (counters5) for (int k = 0; k < 5; k++) counters5[k] += c[k];
+}
+
+// raytracer3.0.06 frame through the lane state machine (rows 20 .. h-71, like Engine_Render).
+void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, int n) {
+    WSoA soa;
+    build_r306_soa(prims, n, soa);
+    std::vector<float> sx, sy;
+    R306Frame F;
+    build_r306_screen(w, h, sx, sy, &F.W.DX, &F.W.DY);
+    F.W.geom = soa.geom.data(); F.W.mat_a = soa.mat_a.data(); F.W.mat_b = soa.mat_b.data();
+    F.W.flags = soa.flags.data(); F.W.lights = soa.lights.data(); F.W.rrad = soa.rrad.data();
+    F.W.runs = soa.runs.data(); F.W.n_runs = (int)soa.runs.size() / 3;
+    F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
+    F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;
+    F.sx = sx.data(); F.sy = sy.data(); F.row0 = 20; F.row1 = h - 70;
+    R306Tree T;
+    for (int y = F.row0; y < F.row1; y++)
+        for (int x = 0; x < w; x++) {
+            R306Lane L;
+            memset(&L, 0, sizeof L);
+            r306_begin_pixel(L, F, x, y);
+            for (;;) {
+                w_query_nearest<false>(L.q, F.W.geom, F.W.runs, F.W.n_runs, true);
+                bool node_done = r306_after_nearest(L, F, T);
+                while (L.q.phase == PH_SHADOW) {
+                    w_query_shadow<false>(L.q, F.W.geom, F.W.runs, F.W.n_runs, true);
+                    r306_after_shadow(L, F);
+                }
+                if (L.q.phase == PH_FINAL) { r306_finish_hit(L, F, T); node_done = true; }
+                if (node_done && r306_next_node(L, F, T)) break;
+            }
+            dest[(size_t)y * w + x] = r306_pack_pixel(L.tr, L.tg, L.tb);
+        }
 }
 
 // smallpt passes through the lane state machine.  colors/seeds updated in place (CPU-twin indexing).

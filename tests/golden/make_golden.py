@@ -11,6 +11,9 @@ and the compiled oracle/_ref exist).  The fixtures are OUTPUTS of the reference'
                               for the path-tracing and the direct-lighting integrator.
   smallpt_kat.json            GetRandom and SphereIntersect known answers from the compiled reference.
   complex_scene_md5.json      md5 of `perl scene_build_complex.pl` output for $maxDepth 1..5.
+  r306_golden.json            raytracer3.0.06 (BASELINE config 1) frames rendered by the reference's own Engine_Render
+                              (oracle/_ref/libref_r306.so): sha256 at 800x600 and two odd sizes, plus the 160x120
+                              frame itself (r306_160x120.u32.zlib) for diffing.
   viewer_keys.json            a scripted session through the reference viewer's own keyFunc / specialFunc
                               (displayfunc.cpp compiled in oracle/_ref): camera and sphere table after every key.
 """
@@ -123,11 +126,23 @@ def viewer_keys():
     json.dump({"scene": "cornell.scn", "w": w, "h": h, "steps": steps}, open(os.path.join(HERE, "viewer_keys.json"), "w"), indent=1)
 
 
+def r306():
+    L = ctypes.CDLL(os.path.join(ROOT, "oracle/_ref/libref_r306.so"))
+    out = {"pixel_format": "0x00RRGGBB, rows 20 .. h-71 rendered, the rest zero", "frames": {}}
+    for (w, h) in [(160, 120), (203, 131), (800, 600), (1003, 377)]:
+        img = np.zeros((h, w), np.uint32)
+        L.ref_r306_render(vp(img), w, h)
+        out["frames"][f"{w}x{h}"] = hashlib.sha256(img.tobytes()).hexdigest()
+        if (w, h) == (160, 120):
+            open(os.path.join(HERE, "r306_160x120.u32.zlib"), "wb").write(zlib.compress(img.tobytes(), 9))
+    json.dump(out, open(os.path.join(HERE, "r306_golden.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (build container)")
     only = sys.argv[1:]
-    for name, fn in (("whitted", whitted), ("smallpt", smallpt), ("complex_scene", complex_scene), ("viewer_keys", viewer_keys)):
+    for name, fn in (("whitted", whitted), ("smallpt", smallpt), ("complex_scene", complex_scene), ("viewer_keys", viewer_keys), ("r306", r306)):
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

@@ -158,6 +158,45 @@ def test_whitted_row_tile_sharding_is_bit_identical(gpu, rt):
         gpu.set_shard(0, 1, 8)
 
 
+# ------------------------------------------------------------------------------------------ raytracer3.0.06 (config 1)
+def test_r306_frame_equals_the_reference(gpu, rt):
+    """BASELINE config 1 on the GPU: the 800x600 frame (and odd sizes) of raytracer3.0.06 bit-identical to what the
+    reference's own Engine_Render produced (fixture; and oracle/_ref itself when it travelled to this box).  Rows outside
+    20 .. h-71 are left as the caller's buffer had them, like the reference."""
+    import json, os, zlib
+    from conftest import GOLDEN, graft
+    g = json.load(open(os.path.join(GOLDEN, "r306_golden.json")))
+    prims = rt.r306_create_scene()
+    for key, want in g["frames"].items():
+        w, h = (int(v) for v in key.split("x"))
+        img = gpu.r306_render(prims, w, h)
+        assert hashlib.sha256(img.tobytes()).hexdigest() == want, key
+    want = np.frombuffer(zlib.decompress(open(os.path.join(GOLDEN, "r306_160x120.u32.zlib"), "rb").read()), np.uint32).reshape(120, 160)
+    dest = np.full((120, 160), 0xdeadbeef, np.uint32)
+    gpu.r306_render(prims, 160, 120, dest=dest)
+    assert np.array_equal(dest[20:50], want[20:50]) and (dest[:20] == 0xdeadbeef).all() and (dest[50:] == 0xdeadbeef).all()
+    ref = os.path.join(graft.ORACLE_DIR, "_ref", "libref_r306.so")
+    if os.path.exists(ref):
+        L = ctypes.CDLL(ref)
+        b = np.zeros((333, 517), np.uint32)
+        L.ref_r306_render(vp(b), 517, 333)
+        assert np.array_equal(gpu.r306_render(prims, 517, 333), b)
+    # sharded over interleaved row tiles: the union equals the frame
+    full = gpu.r306_render(prims, 203, 131)
+    try:
+        acc = np.zeros_like(full)
+        for rank in range(3):
+            gpu.set_shard(rank, 3, 4)
+            part = gpu.r306_render(prims, 203, 131)
+            rows = np.array([(y // 4) % 3 == rank for y in range(131)])
+            acc[rows] = part[rows]
+        assert np.array_equal(acc, full)
+    finally:
+        gpu.set_shard(0, 1, 8)
+    with pytest.raises(rt.RtError):
+        gpu.r306_render(prims, 64, 90)
+
+
 # ------------------------------------------------------------------------------------------ smallpt
 @pytest.mark.parametrize("scene", ["cornell", "caustic3", "simple", "complex"])
 def test_smallpt_equals_reference_fixture(gpu, rt, scene):

@@ -83,3 +83,28 @@ def test_smallpt_lane_counters_equal_oracle(devsim, orc, rt):
     col_o, sd_o, ctr_o = np.zeros(3 * w * h, np.float32), g["seeds_in"].copy(), np.zeros(4, np.uint64)
     orc.oracle_pt_render(0, vp(g["spheres"]), g["spheres"].size, vp(g["camera"]), w, h, 0, 3, vp(col_o), vp(sd_o), None, 2, vp(ctr_o))
     assert (ctr[4], ctr[0], ctr[1], ctr[2]) == tuple(ctr_o)
+
+
+def test_r306_lanes_equal_the_reference_frame(devsim, rt):
+    """raytracer3.0.06 (config 1) through the lane code on the host == the frame the reference's own Engine_Render
+    produced (fixture from oracle/_ref), and == that code run now where it is built."""
+    import hashlib, json, os, zlib
+    from conftest import GOLDEN, graft
+    g = json.load(open(os.path.join(GOLDEN, "r306_golden.json")))
+    prims = rt.r306_create_scene()
+    assert prims.size == 17
+    for (w, h) in [(160, 120), (203, 131)]:
+        img = np.zeros((h, w), np.uint32)
+        devsim.devsim_r306(vp(img), w, h, vp(prims), prims.size)
+        assert hashlib.sha256(img.tobytes()).hexdigest() == g["frames"][f"{w}x{h}"], (w, h)
+    want = np.frombuffer(zlib.decompress(open(os.path.join(GOLDEN, "r306_160x120.u32.zlib"), "rb").read()), np.uint32).reshape(120, 160)
+    img = np.zeros((120, 160), np.uint32)
+    devsim.devsim_r306(vp(img), 160, 120, vp(prims), prims.size)
+    assert np.array_equal(img, want)
+    ref = os.path.join(graft.ORACLE_DIR, "_ref", "libref_r306.so")
+    if os.path.exists(ref):
+        L = ctypes.CDLL(ref)
+        a, b = np.zeros((150, 97), np.uint32), np.zeros((150, 97), np.uint32)
+        devsim.devsim_r306(vp(a), 97, 150, vp(prims), prims.size)
+        L.ref_r306_render(vp(b), 97, 150)
+        assert np.array_equal(a, b)
