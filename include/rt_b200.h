@@ -261,6 +261,15 @@ int rt_write_complex_scene(const char *path, int max_depth);
 /* create_scene + the Primitive -> Primitive_2 copy (R323/scene.c:48-128, R323/raytracer.c:721-746).
  * which = CHOOSE_SCENE (0: 17 slots, 1: 64 slots).  Returns the primitive count, or <0. */
 int rt_whitted_create_scene(int which, rt_primitive *out, int cap);
+/* A smallpt sphere table (.scn scene, e.g. the generated complex scenes) as a Whitted scene (no
+ * reference counterpart -- the two programs never shared scenes).  Each sphere becomes a create_sphere record
+ * (R323/scene.c:36-46: sq_radius, r_radius derived the same way); an emitter becomes a light whose colour is e scaled
+ * to a maximum of 1, DIFF -> m_diff 1 with m_spec 0.5, SPEC -> m_refl 1, REFR -> m_refr 1 at index 1.5 with m_refl 0.1.
+ * The Whitted tracer's eye is fixed at (0, 0.25, -7) looking down +z (R323/raytracer_non_OpenCL.c:299-316); with a
+ * camera (orig/target as read from the .scn file) the spheres are moved into that frame -- rotated into the camera's
+ * axes and scaled so that the target lies 14 units in front of the eye; with cam == NULL coordinates are kept.
+ * Returns the primitive count (= n), or RT_ERR_ARG when cap < n. */
+int rt_whitted_from_spheres(const rt_sphere *spheres, uint32_t n, const rt_camera *cam, rt_primitive *out, int cap);
 /* Scene_InitScene (R306/scene.cpp:217-272): the 17 primitives of the 3.0.06 program.  Returns the count, or <0. */
 int rt_r306_create_scene(rt_r306_primitive *out, int cap);
 /* write_bmp_file (R323/bitmap.c:8-75): 24-bit BMP, bottom row first, BGR. */

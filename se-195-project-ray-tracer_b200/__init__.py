@@ -95,6 +95,7 @@ SYMBOLS = {
     "rt_read_scene": (_I, [C.c_char_p, _VP, C.POINTER(_VP), C.POINTER(_U32)]),
     "rt_write_complex_scene": (_I, [C.c_char_p, _I]),
     "rt_whitted_create_scene": (_I, [_I, _VP, _I]),
+    "rt_whitted_from_spheres": (_I, [_VP, _U32, _VP, _VP, _I]),
     "rt_write_bmp": (_I, [C.c_char_p, _VP, _I, _I]),
     "rt_write_ppm": (_I, [C.c_char_p, _VP, _I, _I]),
     "rt_free": (None, [_VP]),
@@ -185,6 +186,18 @@ def whitted_create_scene(which=0):
     if n < 0:
         raise RtError(n, "rt_whitted_create_scene")
     return out[:n].copy()
+
+
+def whitted_from_spheres(spheres, cam=None):
+    """A smallpt sphere table as Primitive_2 records for the Whitted tracer (rt_whitted_from_spheres); with a camera
+    the scene is moved into the Whitted tracer's fixed eye frame."""
+    spheres = np.ascontiguousarray(spheres)
+    assert spheres.dtype == SPHERE_DTYPE
+    out = np.zeros(spheres.size, PRIMITIVE_DTYPE)
+    n = lib().rt_whitted_from_spheres(_ptr(spheres), spheres.size, _ptr(cam), _ptr(out), out.size)
+    if n < 0:
+        raise RtError(n, "rt_whitted_from_spheres")
+    return out[:n]
 
 
 def r306_create_scene():

@@ -143,6 +143,43 @@ int rt_viewer_key(int key, rt_camera *cam, int w, int h, rt_sphere *spheres, uin
     }
 }
 
+int rt_whitted_from_spheres(const rt_sphere *s, uint32_t n, const rt_camera *cam, rt_primitive *out, int cap) {
+    if (!s || !out || cap < 0 || (uint32_t)cap < n) return RT_ERR_ARG;
+    // camera frame (doubles; this conversion has no reference counterpart to be bit-compatible with)
+    double ex[3] = { 1, 0, 0 }, ey[3] = { 0, 1, 0 }, ez[3] = { 0, 0, 1 }, o[3] = { 0, 0, 0 }, scale = 1.0, shift[3] = { 0, 0, 0 };
+    if (cam) {
+        const double d[3] = { (double)cam->target.x - cam->orig.x, (double)cam->target.y - cam->orig.y, (double)cam->target.z - cam->orig.z };
+        const double len = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (!(len > 0.0)) return RT_ERR_ARG;
+        for (int k = 0; k < 3; k++) ez[k] = d[k] / len;
+        double x[3] = { -ez[2], 0.0, ez[0] };                               // up x dir, up = (0,1,0): points to the viewer's right
+        double xl = sqrt(x[0] * x[0] + x[2] * x[2]);
+        if (!(xl > 1e-12)) { x[0] = 1.0; x[2] = 0.0; xl = 1.0; }
+        for (int k = 0; k < 3; k++) ex[k] = x[k] / xl;
+        ey[0] = ez[1] * ex[2] - ez[2] * ex[1]; ey[1] = ez[2] * ex[0] - ez[0] * ex[2]; ey[2] = ez[0] * ex[1] - ez[1] * ex[0];
+        o[0] = cam->orig.x; o[1] = cam->orig.y; o[2] = cam->orig.z;
+        scale = 14.0 / len;
+        shift[1] = 0.25; shift[2] = -7.0;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        const bool light = s[i].e.x != 0.f || s[i].e.y != 0.f || s[i].e.z != 0.f;
+        float r = s[i].c.x, g = s[i].c.y, b = s[i].c.z;
+        float refl = 0.f, refr = 0.f, ri = 1.f, diff = 0.f, spec = 0.f;
+        if (light) {
+            const float m = fmaxf(s[i].e.x, fmaxf(s[i].e.y, s[i].e.z));
+            r = s[i].e.x / m; g = s[i].e.y / m; b = s[i].e.z / m;
+        } else if (s[i].refl == RT_DIFF) { diff = 1.f; spec = 0.5f; }
+        else if (s[i].refl == RT_SPEC) { refl = 1.f; }
+        else { refr = 1.f; ri = 1.5f; refl = 0.1f; }
+        const double v[3] = { s[i].p.x - o[0], s[i].p.y - o[1], s[i].p.z - o[2] };
+        const double cx = scale * (v[0] * ex[0] + v[1] * ex[1] + v[2] * ex[2]) + shift[0];
+        const double cy = scale * (v[0] * ey[0] + v[1] * ey[1] + v[2] * ey[2]) + shift[1];
+        const double cz = scale * (v[0] * ez[0] + v[1] * ez[1] + v[2] * ez[2]) + shift[2];
+        out[i] = sphere(r, g, b, refl, refr, ri, diff, spec, light, (float)cx, (float)cy, (float)cz, (float)(scale * s[i].rad));
+    }
+    return (int)n;
+}
+
 // Scene_InitScene + Primitive_Create, R306/scene.cpp:53-82, :217-272 (maxx = maxy = 0: no sphere grid).
 int rt_r306_create_scene(rt_r306_primitive *out, int cap) {
     struct Row { int type; float a, b, c, rd, r, g, bl, refl, refr, ri, diff, spec; bool light; };
