@@ -67,6 +67,24 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture
+    (profiles/r01_ncu_full_summary.json, made by tools/ncu_summary.py from the 1920x1080 frame); None when it is missing."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def to_bytes(text):
+        v, u = text.split()
+        return float(v) * unit[u]
+
+    try:
+        for m in json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json"))):
+            if kernel in m.get("Kernel Name", "") and "dram__bytes_read.sum" in m:
+                return int(to_bytes(m["dram__bytes_read.sum"]) + to_bytes(m["dram__bytes_write.sum"]))
+    except (OSError, ValueError, KeyError, TypeError, AttributeError):
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -307,7 +325,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32_fma", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
-                         "frac": round(achieved / fp32_peak, 4), "traffic": None,
+                         "frac": round(achieved / fp32_peak, 4), "traffic": ncu_traffic("whitted_kernel"),
                          "kernel": "whitted_kernel<false>", "kernel_ms": round(kern_ms_max, 4),
                          "algorithmic_flop_per_launch": int(flop_local),
                          "peak_source": f"{info['sm_count']} SMs x 128 FP32 lanes x 2 FLOP x {peaks['sm_max_mhz']:.0f} MHz (sm_max_mhz of {peaks['source']}; that file has no FP32 entry)",
@@ -320,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
         threads = host_threads()
         mrays, ms, kind, sample = time_reference(rt, 2, 1, threads)
         out["cpu_baseline"] = {"value": round(mrays, 3), "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample}
-        out["config1_cpu"] = time_config1()
+        out["config1"] = time_config1(rt, r)
     if rank == 0:
         print(json.dumps(out))
     r.close()
@@ -328,19 +346,39 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def time_config1():
+def time_config1(rt=None, r=None):
     """BASELINE configs[0]: the reference's own CPU render (raytracer3.0.06: Engine_InitRender + Engine_Render, unmodified,
-    oracle/_ref/libref_r306.so) of its built-in scene at 800x600, one frame, one core (its engine keeps state in globals)."""
+    oracle/_ref/libref_r306.so) of its built-in scene at 800x600, one frame, one core (its engine keeps state in globals),
+    next to the same frame from rt_r306_render on the GPU (bit-identical, tests/test_gpu_parity.py)."""
+    out = {"workload": "raytracer3.0.06 Whitted render of its built-in scene, 800x600 (rows 20..529), 3x3 AA, 63-node ray tree, 1 frame"}
+    frame = None
     path = os.path.join(graft.ORACLE_DIR, "_ref", "libref_r306.so")
-    if not os.path.exists(path):
-        return {"unavailable": "oracle/_ref/libref_r306.so not shipped"}
-    lib = ctypes.CDLL(path)
-    frame = np.zeros((600, 800), np.uint32)
-    t0 = time.perf_counter()
-    lib.ref_r306_render(vp(frame), 800, 600)
-    dt = time.perf_counter() - t0
-    return {"workload": "raytracer3.0.06 CPU Whitted render, 800x600 (rows 20..529), 3x3 AA, 1 frame", "seconds_per_frame": round(dt, 3),
-            "cores": 1, "kind": "reference", "rows_rendered": int(frame.any(axis=1).sum())}
+    if os.path.exists(path):
+        lib = ctypes.CDLL(path)
+        frame = np.zeros((600, 800), np.uint32)
+        t0 = time.perf_counter()
+        lib.ref_r306_render(vp(frame), 800, 600)
+        out["cpu"] = {"seconds_per_frame": round(time.perf_counter() - t0, 3), "cores": 1, "kind": "reference",
+                      "rows_rendered": int(frame.any(axis=1).sum())}
+    else:
+        out["cpu"] = {"unavailable": "oracle/_ref/libref_r306.so not shipped"}
+    if r is not None:
+        prims = rt.r306_create_scene()
+        r.r306_upload(prims, 800, 600)
+        for _ in range(3):
+            r.r306_launch()
+        r.sync()
+        ts = []
+        for _ in range(5):
+            r.timer_begin(); r.r306_launch(); ts.append(r.timer_end())
+        t0 = time.perf_counter()
+        img = r.r306_render(prims, 800, 600)
+        e2e = time.perf_counter() - t0
+        out["gpu"] = {"kernel_ms": round(min(ts), 3), "e2e_ms": round(e2e * 1e3, 3),
+                      "equals_cpu_frame": bool((img == frame).all()) if frame is not None else None}
+        if frame is not None:
+            out["gpu"]["speedup_vs_cpu_1core_e2e"] = round(out["cpu"]["seconds_per_frame"] / e2e, 1)
+    return out
 
 
 def cornell_scene(rt, w, h):

@@ -112,7 +112,8 @@ enum {
     RT_TUNE_PT_MAX_RESIDENT_BYTES = 0,  /* sphere (p, rad^2) arrays larger than this are streamed through shared memory in chunks */
     RT_TUNE_PT_CHUNK_SPHERES = 1,       /* spheres per chunk in that mode */
     RT_TUNE_MAX_BLOCKS_PER_SM = 2,      /* cap on resident CTAs per SM (0 = as many as fit) */
-    RT_TUNE_WHITTED_COST_ORDER = 3      /* 1 (default): a pre-pass hands out expensive pixels first; 0: screen order.  Same image either way */
+    RT_TUNE_WHITTED_COST_ORDER = 3,     /* 1 (default): a pre-pass hands out expensive pixels first; 0: screen order.  Same image either way */
+    RT_TUNE_PT_ALIGNED = 4              /* path tracer: 1 = warps run the shading steps in lock-step, 0 = plain query loop, -1 (default) = by scene size.  Same image either way */
 };
 int rt_set_tuning(rt_ctx *ctx, int key, int value);
 

@@ -163,168 +163,178 @@ RT_HD void pt_begin_pixel(PtLane &L, const PtFrame &F, int x, int y, const float
     pt_start_sample(L, F);
 }
 
-// Runs the shading code that follows a finished query until the lane needs its next query
-// (returns false) or has completed the last pass of its pixel (returns true).
-template <bool COUNT>
-RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
-    enum { GO_LIGHTS, GO_BOUNCE, GO_END };
-    int go;
-    if (L.phase == PH_NEAREST) {
-        if (COUNT) { L.c_nearest++; L.c_tests += (uint32_t)F.n; }
-        if (!(L.cumu < PT_INF)) {
-            go = GO_END;                                             // miss: SPT/geomfunc.h:190-193
-        } else {
-            const int id = L.hit;
-            const f4 g = F.geom_global[id];
-            const f4 em = F.emis[id];
-            const float t = L.cumu;
-            const float ax = f_add(L.ox, f_mul(t, L.dx)), ay = f_add(L.oy, f_mul(t, L.dy)), az = f_add(L.oz, f_mul(t, L.dz));
-            float nx = f_sub(ax, g.x), ny = f_sub(ay, g.y), nz = f_sub(az, g.z);
-            pt_unit(nx, ny, nz);
-            const float dp = dot3(nx, ny, nz, L.dx, L.dy, L.dz);
-            const float flip = dp > 0.f ? -1.f : 1.f;                // -1.f * sign(dp), sign(0) = -1 (SPT/vec.h:59)
-            const float nlx = f_mul(flip, nx), nly = f_mul(flip, ny), nlz = f_mul(flip, nz);
-            if (!(em.x == 0.f && em.z == 0.f)) {                     // emitter: SPT/geomfunc.h:216-227
-                if (L.after_spec) {
-                    const float a = fabsf(dp);
-                    L.rr = f_add(L.rr, f_mul(L.tr, f_mul(a, em.x)));
-                    L.rg = f_add(L.rg, f_mul(L.tg, f_mul(a, em.y)));
-                    L.rb = f_add(L.rb, f_mul(L.tb, f_mul(a, em.z)));
-                }
-                go = GO_END;
-            } else {
-                const f4 cl = F.colr[id];
-                const int refl = (int)f_bits(em.w);
-                if (refl == 0) {                                      // DIFF: SPT/geomfunc.h:228-239
-                    L.after_spec = 0;
-                    L.tr = f_mul(L.tr, cl.x); L.tg = f_mul(L.tg, cl.y); L.tb = f_mul(L.tb, cl.z);
-                    L.ox = ax; L.oy = ay; L.oz = az;
-                    L.nlx = nlx; L.nly = nly; L.nlz = nlz;
-                    L.lr = L.lg = L.lb = 0.f;
-                    L.li = 0;
-                    go = GO_LIGHTS;
-                } else {
-                    L.after_spec = 1;
-                    const float k2 = f_mul(2.f, dot3(nx, ny, nz, L.dx, L.dy, L.dz));
-                    const float mx = f_sub(L.dx, f_mul(k2, nx)), my = f_sub(L.dy, f_mul(k2, ny)), mz = f_sub(L.dz, f_mul(k2, nz));
-                    if (refl == 1) {                                  // SPEC: SPT/geomfunc.h:277-288
-                        L.tr = f_mul(L.tr, cl.x); L.tg = f_mul(L.tg, cl.y); L.tb = f_mul(L.tb, cl.z);
-                        L.dx = mx; L.dy = my; L.dz = mz;
-                    } else {                                          // REFR: SPT/geomfunc.h:289-336
-                        const bool into = dot3(nx, ny, nz, nlx, nly, nlz) > 0.f;
-                        const float nnt = into ? 0x1.555556p-1f : 1.5f;       // nc / nt = fl(1.f / 1.5f), nt / nc = 1.5f
-                        const float ddn = dot3(L.dx, L.dy, L.dz, nlx, nly, nlz);
-                        const float cos2t = f_sub(1.f, f_mul(f_mul(nnt, nnt), f_sub(1.f, f_mul(ddn, ddn))));
-                        if (cos2t < 0.f) {                            // total internal reflection
-                            L.tr = f_mul(L.tr, cl.x); L.tg = f_mul(L.tg, cl.y); L.tb = f_mul(L.tb, cl.z);
-                            L.dx = mx; L.dy = my; L.dz = mz;
-                        } else {
-                            const float kk = f_mul(into ? 1.f : -1.f, f_add(f_mul(ddn, nnt), f_sqrt(cos2t)));
-                            float tx = f_sub(f_mul(nnt, L.dx), f_mul(kk, nx));
-                            float ty = f_sub(f_mul(nnt, L.dy), f_mul(kk, ny));
-                            float tz = f_sub(f_mul(nnt, L.dz), f_mul(kk, nz));
-                            pt_unit(tx, ty, tz);
-                            const float R0 = 0.04f;                           // a*a/(b*b) = fl(0.25f / 6.25f), a = nt-nc, b = nt+nc
-                            const float c = f_sub(1.f, into ? -ddn : dot3(tx, ty, tz, nx, ny, nz));
-                            const float Re = f_add(R0, f_mul(f_mul(f_mul(f_mul(f_mul(f_sub(1.f, R0), c), c), c), c), c));
-                            const float Tr = f_sub(1.f, Re);
-                            const float P = f_add(.25f, f_mul(.5f, Re));
-                            const float RP = f_div(Re, P), TP = f_div(Tr, f_sub(1.f, P));
-                            if (get_random(L.s0, L.s1) < P) {
-                                L.tr = f_mul(f_mul(RP, L.tr), cl.x); L.tg = f_mul(f_mul(RP, L.tg), cl.y); L.tb = f_mul(f_mul(RP, L.tb), cl.z);
-                                L.dx = mx; L.dy = my; L.dz = mz;
-                            } else {
-                                L.tr = f_mul(f_mul(TP, L.tr), cl.x); L.tg = f_mul(f_mul(TP, L.tg), cl.y); L.tb = f_mul(f_mul(TP, L.tb), cl.z);
-                                L.dx = tx; L.dy = ty; L.dz = tz;
-                            }
-                        }
-                    }
-                    L.ox = ax; L.oy = ay; L.oz = az;
-                    go = GO_BOUNCE;
-                }
-            }
-        }
-    } else {                                                          // a shadow query has just finished
-        if (COUNT) L.c_shadow++;
-        if (L.hit < 0) {                                              // light visible: SPT/geomfunc.h:157-162
-            const f4 le = F.emis[F.lights[L.li]];
-            L.lr = f_add(L.lr, f_mul(L.lscale, le.x));
-            L.lg = f_add(L.lg, f_mul(L.lscale, le.y));
-            L.lb = f_add(L.lb, f_mul(L.lscale, le.z));
-        }
-        L.li++;
-        go = GO_LIGHTS;
-    }
+// The shading code between two queries, cut into STEPS so that a warp can run each step with all the lanes that are at
+// it (pt_kernel, ALIGNED) -- or one lane can run them back to back (pt_advance).  Either way a lane performs the same
+// operations in the same order (in particular the same RNG draws), so the result does not depend on the schedule.
+//   PH_NEAREST  a nearest-hit query is pending         PH_SHADOW   a shadow query is pending
+//   PH_LIGHTS   SampleLights is at light L.li          PH_DIFFUSE  lights done: cosine-weighted bounce next
+//   PH_BOUNCE   a new direction is set: depth check    PH_END      the sample is complete
+enum { PH_LIGHTS = 4, PH_DIFFUSE = 5, PH_BOUNCE = 6, PH_END = 7 };
 
-    if (go == GO_LIGHTS) {                                            // SampleLights, SPT/geomfunc.h:112-165
-        for (; L.li < F.n_lights; L.li++) {
-            const int lid = F.lights[L.li];
-            const f4 lg = F.geom_global[lid];
-            const float lrad = F.colr[lid].w;
-            // UniformSampleSphere(GetRandom(), GetRandom(), ..): the reference's compiler evaluates the
-            // arguments right to left, so the SECOND argument (u2) takes the first draw.
-            const float u2 = get_random(L.s0, L.s1);
-            const float u1 = get_random(L.s0, L.s1);
-            const float zz = f_sub(1.f, f_mul(2.f, u1));
-            const float inside = f_sub(1.f, f_mul(zz, zz));
-            const float r = f_sqrt(0.f > inside ? 0.f : inside);
-            const float phi = f_mul(f_mul(2.f, PT_PI), u2);
-            float sn, cs;
-            sincos_glibc(phi, &sn, &cs);
-            const float ux = f_mul(r, cs), uy = f_mul(r, sn), uz = zz;
-            const float spx = f_add(f_mul(lrad, ux), lg.x), spy = f_add(f_mul(lrad, uy), lg.y), spz = f_add(f_mul(lrad, uz), lg.z);
-            float sx = f_sub(spx, L.ox), sy = f_sub(spy, L.oy), sz = f_sub(spz, L.oz);
-            const float len = f_sqrt(dot3(sx, sy, sz, sx, sy, sz));
-            const float inv = f_rcp(len);
-            sx = f_mul(inv, sx); sy = f_mul(inv, sy); sz = f_mul(inv, sz);
-            float wo = dot3(sx, sy, sz, ux, uy, uz);
-            if (wo > 0.f) continue;                                   // sample on the far half of the light
-            wo = -wo;
-            const float wi = dot3(sx, sy, sz, L.nlx, L.nly, L.nlz);
-            if (wi > 0.f) {
-                L.lscale = f_div(f_mul(f_mul(f_mul(f_mul(f_mul(4.f, PT_PI), lrad), lrad), wi), wo), f_mul(len, len));
-                L.dx = sx; L.dy = sy; L.dz = sz;
-                L.cumu = f_sub(len, PT_EPS);
-                L.hit = -1;
-                L.phase = PH_SHADOW;
-                return false;
+// After a nearest-hit query (SPT/geomfunc.h:190-288).
+template <bool COUNT>
+RT_HD void pt_hit(PtLane &L, const PtFrame &F) {
+    if (COUNT) { L.c_nearest++; L.c_tests += (uint32_t)F.n; }
+    if (!(L.cumu < PT_INF)) { L.phase = PH_END; return; }            // miss: SPT/geomfunc.h:190-193
+    const int id = L.hit;
+    const f4 g = F.geom_global[id];
+    const f4 em = F.emis[id];
+    const float t = L.cumu;
+    const float ax = f_add(L.ox, f_mul(t, L.dx)), ay = f_add(L.oy, f_mul(t, L.dy)), az = f_add(L.oz, f_mul(t, L.dz));
+    float nx = f_sub(ax, g.x), ny = f_sub(ay, g.y), nz = f_sub(az, g.z);
+    pt_unit(nx, ny, nz);
+    const float dp = dot3(nx, ny, nz, L.dx, L.dy, L.dz);
+    const float flip = dp > 0.f ? -1.f : 1.f;                        // -1.f * sign(dp), sign(0) = -1 (SPT/vec.h:59)
+    const float nlx = f_mul(flip, nx), nly = f_mul(flip, ny), nlz = f_mul(flip, nz);
+    if (!(em.x == 0.f && em.z == 0.f)) {                             // emitter: SPT/geomfunc.h:216-227
+        if (L.after_spec) {
+            const float a = fabsf(dp);
+            L.rr = f_add(L.rr, f_mul(L.tr, f_mul(a, em.x)));
+            L.rg = f_add(L.rg, f_mul(L.tg, f_mul(a, em.y)));
+            L.rb = f_add(L.rb, f_mul(L.tb, f_mul(a, em.z)));
+        }
+        L.phase = PH_END;
+        return;
+    }
+    const f4 cl = F.colr[id];
+    const int refl = (int)f_bits(em.w);
+    if (refl == 0) {                                                  // DIFF: SPT/geomfunc.h:228-239
+        L.after_spec = 0;
+        L.tr = f_mul(L.tr, cl.x); L.tg = f_mul(L.tg, cl.y); L.tb = f_mul(L.tb, cl.z);
+        L.ox = ax; L.oy = ay; L.oz = az;
+        L.nlx = nlx; L.nly = nly; L.nlz = nlz;
+        L.lr = L.lg = L.lb = 0.f;
+        L.li = 0;
+        L.phase = PH_LIGHTS;
+        return;
+    }
+    L.after_spec = 1;
+    const float k2 = f_mul(2.f, dot3(nx, ny, nz, L.dx, L.dy, L.dz));
+    const float mx = f_sub(L.dx, f_mul(k2, nx)), my = f_sub(L.dy, f_mul(k2, ny)), mz = f_sub(L.dz, f_mul(k2, nz));
+    if (refl == 1) {                                                  // SPEC: SPT/geomfunc.h:277-288
+        L.tr = f_mul(L.tr, cl.x); L.tg = f_mul(L.tg, cl.y); L.tb = f_mul(L.tb, cl.z);
+        L.dx = mx; L.dy = my; L.dz = mz;
+    } else {                                                          // REFR: SPT/geomfunc.h:289-336
+        const bool into = dot3(nx, ny, nz, nlx, nly, nlz) > 0.f;
+        const float nnt = into ? 0x1.555556p-1f : 1.5f;               // nc / nt = fl(1.f / 1.5f), nt / nc = 1.5f
+        const float ddn = dot3(L.dx, L.dy, L.dz, nlx, nly, nlz);
+        const float cos2t = f_sub(1.f, f_mul(f_mul(nnt, nnt), f_sub(1.f, f_mul(ddn, ddn))));
+        if (cos2t < 0.f) {                                            // total internal reflection
+            L.tr = f_mul(L.tr, cl.x); L.tg = f_mul(L.tg, cl.y); L.tb = f_mul(L.tb, cl.z);
+            L.dx = mx; L.dy = my; L.dz = mz;
+        } else {
+            const float kk = f_mul(into ? 1.f : -1.f, f_add(f_mul(ddn, nnt), f_sqrt(cos2t)));
+            float tx = f_sub(f_mul(nnt, L.dx), f_mul(kk, nx));
+            float ty = f_sub(f_mul(nnt, L.dy), f_mul(kk, ny));
+            float tz = f_sub(f_mul(nnt, L.dz), f_mul(kk, nz));
+            pt_unit(tx, ty, tz);
+            const float R0 = 0.04f;                                   // a*a/(b*b) = fl(0.25f / 6.25f), a = nt-nc, b = nt+nc
+            const float c = f_sub(1.f, into ? -ddn : dot3(tx, ty, tz, nx, ny, nz));
+            const float Re = f_add(R0, f_mul(f_mul(f_mul(f_mul(f_mul(f_sub(1.f, R0), c), c), c), c), c));
+            const float Tr = f_sub(1.f, Re);
+            const float P = f_add(.25f, f_mul(.5f, Re));
+            const float RP = f_div(Re, P), TP = f_div(Tr, f_sub(1.f, P));
+            if (get_random(L.s0, L.s1) < P) {
+                L.tr = f_mul(f_mul(RP, L.tr), cl.x); L.tg = f_mul(f_mul(RP, L.tg), cl.y); L.tb = f_mul(f_mul(RP, L.tb), cl.z);
+                L.dx = mx; L.dy = my; L.dz = mz;
+            } else {
+                L.tr = f_mul(f_mul(TP, L.tr), cl.x); L.tg = f_mul(f_mul(TP, L.tg), cl.y); L.tb = f_mul(f_mul(TP, L.tb), cl.z);
+                L.dx = tx; L.dy = ty; L.dz = tz;
             }
         }
+    }
+    L.ox = ax; L.oy = ay; L.oz = az;
+    L.phase = PH_BOUNCE;
+}
+
+// After a shadow query: SPT/geomfunc.h:157-162.
+template <bool COUNT>
+RT_HD void pt_light_done(PtLane &L, const PtFrame &F) {
+    if (COUNT) L.c_shadow++;
+    if (L.hit < 0) {
+        const f4 le = F.emis[F.lights[L.li]];
+        L.lr = f_add(L.lr, f_mul(L.lscale, le.x));
+        L.lg = f_add(L.lg, f_mul(L.lscale, le.y));
+        L.lb = f_add(L.lb, f_mul(L.lscale, le.z));
+    }
+    L.li++;
+    L.phase = PH_LIGHTS;
+}
+
+// One light of SampleLights (SPT/geomfunc.h:112-165): a shadow query (PH_SHADOW), the next light (PH_LIGHTS), or, past
+// the last light, the direct light folded into the radiance (PH_DIFFUSE, or PH_END for the direct-lighting integrator).
+RT_HD void pt_light_step(PtLane &L, const PtFrame &F) {
+    if (L.li >= F.n_lights) {
         L.rr = f_add(L.rr, f_mul(L.tr, L.lr));
         L.rg = f_add(L.rg, f_mul(L.tg, L.lg));
         L.rb = f_add(L.rb, f_mul(L.tb, L.lb));
-        if (F.direct_only) {
-            go = GO_END;                                              // SPT/geomfunc.h:412-413
-        } else {                                                      // cosine-weighted bounce, :243-275
-            const float r1 = f_mul(f_mul(2.f, PT_PI), get_random(L.s0, L.s1));
-            const float r2 = get_random(L.s0, L.s1);
-            const float r2s = f_sqrt(r2);
-            const float wx = L.nlx, wy = L.nly, wz = L.nlz;
-            float ux, uy, uz;
-            if (fabsf(wx) > .1f) {        // a = (0,1,0): u = a x w
-                ux = f_sub(f_mul(1.f, wz), f_mul(0.f, wy)); uy = f_sub(f_mul(0.f, wx), f_mul(0.f, wz)); uz = f_sub(f_mul(0.f, wy), f_mul(1.f, wx));
-            } else {                      // a = (1,0,0)
-                ux = f_sub(f_mul(0.f, wz), f_mul(0.f, wy)); uy = f_sub(f_mul(0.f, wx), f_mul(1.f, wz)); uz = f_sub(f_mul(1.f, wy), f_mul(0.f, wx));
-            }
-            pt_unit(ux, uy, uz);
-            const float vx = f_sub(f_mul(wy, uz), f_mul(wz, uy)), vy = f_sub(f_mul(wz, ux), f_mul(wx, uz)), vz = f_sub(f_mul(wx, uy), f_mul(wy, ux));
-            float sn, cs;
-            sincos_glibc(r1, &sn, &cs);
-            const float ku = f_mul(cs, r2s), kv = f_mul(sn, r2s), kw = f_sqrt(f_sub(1.f, r2));
-            L.dx = f_add(f_add(f_mul(ku, ux), f_mul(kv, vx)), f_mul(kw, wx));
-            L.dy = f_add(f_add(f_mul(ku, uy), f_mul(kv, vy)), f_mul(kw, wy));
-            L.dz = f_add(f_add(f_mul(ku, uz), f_mul(kv, vz)), f_mul(kw, wz));
-            go = GO_BOUNCE;
-        }
+        L.phase = F.direct_only ? PH_END : PH_DIFFUSE;               // SPT/geomfunc.h:412-413
+        return;
     }
+    const int lid = F.lights[L.li];
+    const f4 lg = F.geom_global[lid];
+    const float lrad = F.colr[lid].w;
+    // UniformSampleSphere(GetRandom(), GetRandom(), ..): the reference's compiler evaluates the
+    // arguments right to left, so the SECOND argument (u2) takes the first draw.
+    const float u2 = get_random(L.s0, L.s1);
+    const float u1 = get_random(L.s0, L.s1);
+    const float zz = f_sub(1.f, f_mul(2.f, u1));
+    const float inside = f_sub(1.f, f_mul(zz, zz));
+    const float r = f_sqrt(0.f > inside ? 0.f : inside);
+    const float phi = f_mul(f_mul(2.f, PT_PI), u2);
+    float sn, cs;
+    sincos_glibc(phi, &sn, &cs);
+    const float ux = f_mul(r, cs), uy = f_mul(r, sn), uz = zz;
+    const float spx = f_add(f_mul(lrad, ux), lg.x), spy = f_add(f_mul(lrad, uy), lg.y), spz = f_add(f_mul(lrad, uz), lg.z);
+    float sx = f_sub(spx, L.ox), sy = f_sub(spy, L.oy), sz = f_sub(spz, L.oz);
+    const float len = f_sqrt(dot3(sx, sy, sz, sx, sy, sz));
+    const float inv = f_rcp(len);
+    sx = f_mul(inv, sx); sy = f_mul(inv, sy); sz = f_mul(inv, sz);
+    float wo = dot3(sx, sy, sz, ux, uy, uz);
+    const float wi = dot3(sx, sy, sz, L.nlx, L.nly, L.nlz);
+    if (wo > 0.f || !(wi > 0.f)) { L.li++; return; }                // sample on the far half of the light / light below the horizon
+    wo = -wo;
+    L.lscale = f_div(f_mul(f_mul(f_mul(f_mul(f_mul(4.f, PT_PI), lrad), lrad), wi), wo), f_mul(len, len));
+    L.dx = sx; L.dy = sy; L.dz = sz;
+    L.cumu = f_sub(len, PT_EPS);
+    L.hit = -1;
+    L.phase = PH_SHADOW;
+}
 
-    if (go == GO_BOUNCE) {
-        L.depth++;
-        if (L.depth > 6) go = GO_END;                                 // SPT/geomfunc.h:182-185
-        else { L.phase = PH_NEAREST; L.cumu = PT_INF; L.hit = -1; return false; }
+// Cosine-weighted bounce, SPT/geomfunc.h:243-275.
+RT_HD void pt_diffuse_bounce(PtLane &L) {
+    const float r1 = f_mul(f_mul(2.f, PT_PI), get_random(L.s0, L.s1));
+    const float r2 = get_random(L.s0, L.s1);
+    const float r2s = f_sqrt(r2);
+    const float wx = L.nlx, wy = L.nly, wz = L.nlz;
+    float ux, uy, uz;
+    if (fabsf(wx) > .1f) {        // a = (0,1,0): u = a x w
+        ux = f_sub(f_mul(1.f, wz), f_mul(0.f, wy)); uy = f_sub(f_mul(0.f, wx), f_mul(0.f, wz)); uz = f_sub(f_mul(0.f, wy), f_mul(1.f, wx));
+    } else {                      // a = (1,0,0)
+        ux = f_sub(f_mul(0.f, wz), f_mul(0.f, wy)); uy = f_sub(f_mul(0.f, wx), f_mul(1.f, wz)); uz = f_sub(f_mul(1.f, wy), f_mul(0.f, wx));
     }
+    pt_unit(ux, uy, uz);
+    const float vx = f_sub(f_mul(wy, uz), f_mul(wz, uy)), vy = f_sub(f_mul(wz, ux), f_mul(wx, uz)), vz = f_sub(f_mul(wx, uy), f_mul(wy, ux));
+    float sn, cs;
+    sincos_glibc(r1, &sn, &cs);
+    const float ku = f_mul(cs, r2s), kv = f_mul(sn, r2s), kw = f_sqrt(f_sub(1.f, r2));
+    L.dx = f_add(f_add(f_mul(ku, ux), f_mul(kv, vx)), f_mul(kw, wx));
+    L.dy = f_add(f_add(f_mul(ku, uy), f_mul(kv, vy)), f_mul(kw, wy));
+    L.dz = f_add(f_add(f_mul(ku, uz), f_mul(kv, vz)), f_mul(kw, wz));
+    L.phase = PH_BOUNCE;
+}
 
-    // GO_END: fold the sample into the pixel (SPT/smallptCPU.cpp:110-118) and start the next pass.
+// A new direction is set: SPT/geomfunc.h:182-185.
+RT_HD void pt_bounce(PtLane &L) {
+    L.depth++;
+    if (L.depth > 6) L.phase = PH_END;
+    else { L.phase = PH_NEAREST; L.cumu = PT_INF; L.hit = -1; }
+}
+
+// Folds the finished sample into the pixel (SPT/smallptCPU.cpp:110-118) and starts the next pass; returns true when the
+// last pass of the pixel is done.
+template <bool COUNT>
+RT_HD bool pt_end_sample(PtLane &L, const PtFrame &F) {
     if (COUNT) L.c_samples++;
     if (F.sum_mode) {
         L.cr = f_add(L.cr, L.rr); L.cg = f_add(L.cg, L.rg); L.cb = f_add(L.cb, L.rb);
@@ -341,6 +351,20 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
     if (L.pass >= F.pass0 + F.n_passes) { L.phase = PH_IDLE; return true; }
     pt_start_sample(L, F);
     return false;
+}
+
+// One lane, steps back to back: runs the shading code that follows a finished query until the lane needs its next
+// query (returns false) or has completed the last pass of its pixel (returns true).
+template <bool COUNT>
+RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
+    if (L.phase == PH_NEAREST) pt_hit<COUNT>(L, F);
+    else pt_light_done<COUNT>(L, F);
+    while (L.phase == PH_LIGHTS) pt_light_step(L, F);
+    if (L.phase == PH_SHADOW) return false;
+    if (L.phase == PH_DIFFUSE) pt_diffuse_bounce(L);
+    if (L.phase == PH_BOUNCE) pt_bounce(L);
+    if (L.phase == PH_NEAREST) return false;
+    return pt_end_sample<COUNT>(L, F);
 }
 
 // pixels[y*w + x] of SPT/smallptCPU.cpp:120-122.

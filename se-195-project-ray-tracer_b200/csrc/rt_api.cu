@@ -31,6 +31,7 @@ struct rt_ctx {
     int pt_chunk_spheres = 3072;                   // 48 KB of (p, rad^2) per chunk
     int max_blocks_per_sm = 0;
     int whitted_sort = 1;                          // cost-sorted work order (scheduling pre-pass)
+    int pt_aligned = -1;                           // step-aligned path-tracer warps: -1 by scene size, 0 off, 1 on
     uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
     unsigned *d_wclass = nullptr;
@@ -194,6 +195,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_PT_CHUNK_SPHERES: if (value < 1) break; ctx->pt_chunk_spheres = value; return RT_OK;
         case RT_TUNE_MAX_BLOCKS_PER_SM: if (value < 0) break; ctx->max_blocks_per_sm = value; return RT_OK;
         case RT_TUNE_WHITTED_COST_ORDER: ctx->whitted_sort = value ? 1 : 0; return RT_OK;
+        case RT_TUNE_PT_ALIGNED: if (value < -1 || value > 1) break; ctx->pt_aligned = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -457,6 +459,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
     p.max_smem_geom = ctx->pt_max_resident_bytes < ctx->max_smem_optin ? ctx->pt_max_resident_bytes : ctx->max_smem_optin;
     p.chunk_spheres = ctx->pt_chunk_spheres;
     p.max_blocks_per_sm = ctx->max_blocks_per_sm;
+    p.aligned = ctx->pt_aligned;
     CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches++; }

@@ -43,7 +43,13 @@ __device__ __forceinline__ uint64_t warp_sum(uint64_t v) {
 // smallpt: replaces RadianceGPU (SPT/rendering_kernel.cl:53-97, rendering_kernel_dl.cl) with the pass
 // loop inside the kernel.  CHUNKED = the (p, rad^2) array does not fit in shared memory: the CTA walks
 // it in chunks, all warps in lock-step (one __syncthreads pair per chunk per query round).
-template <bool COUNT, bool CHUNKED>
+// ALIGNED = the warp runs the shading STEPS of pt_lane.cuh in lock-step: a nearest round for the lanes that need one,
+// then light sample -> shadow round -> accumulate per light, then the bounce, each step executed by all the lanes that
+// are at it.  With few spheres (Cornell: 9) the shading between two queries is most of the work, and in the plain
+// "one query, then advance" loop lanes at different steps serialise it (9 active lanes per instruction, ncu); aligned,
+// a shadow lane no longer shares a round with nearest lanes, which costs idle lanes in the sphere loop instead -- the
+// right trade only while the loop is short.  Per lane the sequence of operations is the same, so are the results.
+template <bool COUNT, bool CHUNKED, bool ALIGNED>
 __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS)
 pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, uint32_t *pixels,
           unsigned *work_counter, unsigned long long *counters, int chunk) {
@@ -75,6 +81,28 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
         if (CHUNKED) { if (!__syncthreads_or(more)) break; }
         else         { if (!__any_sync(FULL_MASK, more)) break; }
 
+        if (ALIGNED) {
+            const bool nq = L.phase == PH_NEAREST;
+            pt_query_range<COUNT>(L, s_geom, 0, F.n, nq);
+            if (nq) pt_hit<COUNT>(L, F);
+            while (__any_sync(FULL_MASK, L.phase == PH_LIGHTS)) {
+                if (L.phase == PH_LIGHTS) pt_light_step(L, F);
+                const bool sq = L.phase == PH_SHADOW;
+                if (__any_sync(FULL_MASK, sq)) {
+                    pt_query_range<COUNT>(L, s_geom, 0, F.n, sq);
+                    if (sq) pt_light_done<COUNT>(L, F);
+                }
+            }
+            if (L.phase == PH_DIFFUSE) pt_diffuse_bounce(L);
+            if (L.phase == PH_BOUNCE) pt_bounce(L);
+            if (L.phase == PH_END && pt_end_sample<COUNT>(L, F)) {
+                const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
+                colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
+                seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
+                if (!F.sum_mode) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
+            }
+            continue;
+        }
         if (!CHUNKED) {
             pt_query_range<COUNT>(L, s_geom, 0, F.n, active);
         } else {
@@ -327,8 +355,10 @@ cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
     }
     if (smem < 16) smem = 16;
     typedef void (*kern_t)(PtFrame, Shard, uint32_t, float *, uint32_t *, uint32_t *, unsigned *, unsigned long long *, int);
-    kern_t k = chunked ? (p.count ? pt_kernel<true, true> : pt_kernel<false, true>)
-                       : (p.count ? pt_kernel<true, false> : pt_kernel<false, false>);
+    const bool aligned = !chunked && (p.aligned > 0 || (p.aligned < 0 && p.frame.n <= PT_ALIGNED_MAX_SPHERES));
+    kern_t k = chunked ? (p.count ? pt_kernel<true, true, false> : pt_kernel<false, true, false>)
+             : aligned ? (p.count ? pt_kernel<true, false, true> : pt_kernel<false, false, true>)
+                       : (p.count ? pt_kernel<true, false, false> : pt_kernel<false, false, false>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int nb = blocks_per_sm(k, PT_THREADS, smem);

@@ -16,6 +16,10 @@
 #ifndef PT_MIN_BLOCKS
 #define PT_MIN_BLOCKS 8
 #endif
+// Scenes of up to this many spheres run the step-aligned path tracer (see pt_kernel); larger ones are loop-bound.
+#ifndef PT_ALIGNED_MAX_SPHERES
+#define PT_ALIGNED_MAX_SPHERES 64
+#endif
 #ifndef W_THREADS
 #define W_THREADS 128
 #endif
@@ -37,6 +41,7 @@ struct PtLaunch {
     int max_smem_geom;          // (p, rad^2) arrays larger than this many bytes are streamed in chunks
     int chunk_spheres;          // spheres per chunk in that case
     int max_blocks_per_sm;      // 0 = whatever fits
+    int aligned;                // -1: by scene size, 0: plain query loop, 1: step-aligned warps
 };
 
 struct WLaunch {
