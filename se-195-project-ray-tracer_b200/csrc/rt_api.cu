@@ -38,7 +38,7 @@ struct rt_ctx {
     // Whitted
     int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_nr = 0, w_want_hits = 0;
     f4 *d_wgeom = nullptr, *d_wma = nullptr, *d_wmb = nullptr;
-    int *d_wflags = nullptr, *d_wlights = nullptr, *d_wruns = nullptr;
+    int *d_wflags = nullptr, *d_wlights = nullptr, *d_wruns = nullptr, *d_wruns_hot = nullptr; size_t cap_wruns_hot = 0; int w_nr_hot = 0;
     float *d_wrrad = nullptr;
     uint32_t *d_wpixels = nullptr;
     int32_t *d_whits = nullptr;
@@ -142,7 +142,7 @@ void rt_destroy(rt_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->peer_wpixels) cudaIpcCloseMemHandle(ctx->peer_wpixels);
     if (ctx->peer_ppixels) cudaIpcCloseMemHandle(ctx->peer_ppixels);
-    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_worder, ctx->d_wclass,
+    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
     for (void *b : bufs) if (b) cudaFree(b);
@@ -218,6 +218,7 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(upload_vec(&ctx->d_wlights, &ctx->cap_wlights, soa.lights, ctx->stream));
     CK(upload_vec(&ctx->d_wrrad, &ctx->cap_wrrad, soa.rrad, ctx->stream));
     CK(upload_vec(&ctx->d_wruns, &ctx->cap_wruns, soa.runs, ctx->stream));
+    CK(upload_vec(&ctx->d_wruns_hot, &ctx->cap_wruns_hot, soa.runs_hot, ctx->stream));
     const size_t px = (size_t)w * h;
     if (px > ctx->w_pixels_cap) {
         if (ctx->d_wpixels) cudaFree(ctx->d_wpixels);
@@ -232,7 +233,7 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
         ctx->w_hits_cap = px * 9;
     }
     ctx->w_w = w; ctx->w_h = h; ctx->w_n = n; ctx->w_nl = (int)soa.lights.size();
-    ctx->w_ns = soa.n_spheres; ctx->w_np = soa.n_planes; ctx->w_nr = (int)soa.runs.size() / 3; ctx->w_want_hits = want_hit_ids ? 1 : 0;
+    ctx->w_ns = soa.n_spheres; ctx->w_np = soa.n_planes; ctx->w_nr = (int)soa.runs.size() / 3; ctx->w_nr_hot = (int)soa.runs_hot.size() / 3; ctx->w_want_hits = want_hit_ids ? 1 : 0;
     return RT_OK;
 }
 
@@ -243,7 +244,8 @@ int rt_whitted_launch(rt_ctx *ctx) {
     WLaunch p;
     WFrame &F = p.frame;
     F.geom = ctx->d_wgeom; F.mat_a = ctx->d_wma; F.mat_b = ctx->d_wmb; F.flags = ctx->d_wflags; F.lights = ctx->d_wlights;
-    F.runs = ctx->d_wruns; F.n_runs = ctx->w_nr;
+    if (ctx->counting) { F.runs = ctx->d_wruns; F.n_runs = ctx->w_nr; }            // every primitive, so that the test counters equal the oracle's
+    else { F.runs = ctx->d_wruns_hot; F.n_runs = ctx->w_nr_hot; }
     F.rrad = ctx->d_wrrad; F.n = ctx->w_n; F.n_lights = ctx->w_nl; F.n_spheres = ctx->w_ns; F.n_planes = ctx->w_np;
     F.w = ctx->w_w; F.h = ctx->w_h;
     // R323/raytracer_non_OpenCL.c:291-296: DX = (WX2 - WX1) / width with float operands.
@@ -310,7 +312,7 @@ int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, in
     CK(upload_vec(&R.mb, &R.cap_mb, R.soa.mat_b, ctx->stream));
     CK(upload_vec(&R.flags, &R.cap_flags, R.soa.flags, ctx->stream));
     CK(upload_vec(&R.lights, &R.cap_lights, R.soa.lights, ctx->stream));
-    CK(upload_vec(&R.runs, &R.cap_runs, R.soa.runs, ctx->stream));
+    CK(upload_vec(&R.runs, &R.cap_runs, R.soa.runs_hot, ctx->stream));
     CK(upload_vec(&R.rrad, &R.cap_rrad, R.soa.rrad, ctx->stream));
     CK(upload_vec(&R.sx, &R.cap_sx, R.h_sx, ctx->stream));
     CK(upload_vec(&R.sy, &R.cap_sy, R.h_sy, ctx->stream));
@@ -321,7 +323,7 @@ int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, in
         CK(cudaMalloc((void **)&R.dest, px * sizeof(uint32_t)));
         R.dest_cap = px;
     }
-    R.w = w; R.h = h; R.n = n; R.nl = (int)R.soa.lights.size(); R.nr = (int)R.soa.runs.size() / 3;
+    R.w = w; R.h = h; R.n = n; R.nl = (int)R.soa.lights.size(); R.nr = (int)R.soa.runs_hot.size() / 3;
     R.ns = R.soa.n_spheres; R.np = R.soa.n_planes;
     return RT_OK;
 }

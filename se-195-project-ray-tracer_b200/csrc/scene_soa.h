@@ -37,6 +37,7 @@ inline void build_pt_soa(const rt_sphere *s, uint32_t n, PtSoA &out) {
 struct WSoA {
     std::vector<f4> geom, mat_a, mat_b;
     std::vector<int> flags, lights, runs;
+    std::vector<int> runs_hot;          // the same runs without primitives that can never be hit (timed launches use these)
     std::vector<float> rrad;
     int n_spheres = 0, n_planes = 0;
 };
@@ -68,6 +69,18 @@ inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
         int j = i;
         while (j < n && out.flags[j] == out.flags[i] && j - i < 32) j++;   // <= 32 per run: the kernel re-votes per run
         out.runs.push_back(i); out.runs.push_back(j - i); out.runs.push_back(out.flags[i]);
+        i = j;
+    }
+    // A plane whose normal is (0,0,0) -- the reference's zeroed slot (R323/scene.c:55-57), or a primitive of unknown
+    // type -- has d = N.dir = 0 (or NaN) for every ray and fails `d != 0` / `dist > 0` (RNO:97-108): it is never hit and
+    // never shadows.  The work counters still include it (counting launches walk `runs`); timed launches skip it.
+    auto dead = [&](int i) { return !(out.flags[i] & W_FLAG_SPHERE) && out.geom[i].x == 0.f && out.geom[i].y == 0.f && out.geom[i].z == 0.f; };
+    out.runs_hot.clear();
+    for (int i = 0; i < n;) {
+        if (dead(i)) { i++; continue; }
+        int j = i;
+        while (j < n && !dead(j) && out.flags[j] == out.flags[i] && j - i < 32) j++;
+        out.runs_hot.push_back(i); out.runs_hot.push_back(j - i); out.runs_hot.push_back(out.flags[i]);
         i = j;
     }
 }

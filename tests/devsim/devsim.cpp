@@ -44,6 +44,7 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     F.geom = soa.geom.data(); F.mat_a = soa.mat_a.data(); F.mat_b = soa.mat_b.data();
     F.flags = soa.flags.data(); F.lights = soa.lights.data(); F.rrad = soa.rrad.data();
     F.runs = soa.runs.data(); F.n_runs = (int)soa.runs.size() / 3;
+    if (use_runs == 2) { F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3; }    // what timed launches walk
     F.n = n; F.n_lights = (int)soa.lights.size(); F.n_spheres = soa.n_spheres; F.n_planes = soa.n_planes;
     F.w = w; F.h = h;
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
@@ -86,7 +87,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
     build_r306_screen(w, h, sx, sy, &F.W.DX, &F.W.DY);
     F.W.geom = soa.geom.data(); F.W.mat_a = soa.mat_a.data(); F.W.mat_b = soa.mat_b.data();
     F.W.flags = soa.flags.data(); F.W.lights = soa.lights.data(); F.W.rrad = soa.rrad.data();
-    F.W.runs = soa.runs.data(); F.W.n_runs = (int)soa.runs.size() / 3;
+    F.W.runs = soa.runs_hot.data(); F.W.n_runs = (int)soa.runs_hot.size() / 3;
     F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
     F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;
     F.sx = sx.data(); F.sy = sy.data(); F.row0 = 20; F.row1 = h - 70;

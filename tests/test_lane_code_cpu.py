@@ -52,6 +52,21 @@ def test_whitted_lanes_equal_oracle(devsim, orc, rt):
         assert list(ctr[:4]) == list(ctr_o[:4]) and ctr[4] == w * h * 9
 
 
+def test_whitted_hot_runs_skip_only_never_hit_primitives(devsim, orc, rt):
+    """Timed launches walk the runs without never-hit primitives (the zeroed slot of scene 0, unknown types): same
+    pixels and hit IDs as the oracle, which tests every primitive."""
+    for scene in (0, 1):
+        prims = rt.whitted_create_scene(scene)
+        if scene == 1:
+            prims = prims.copy(); prims["type"][5] = 7          # an unknown type: intersect() returns MISS (RNO:150-160)
+        w, h = (96, 72) if scene == 0 else (40, 30)
+        px, hits = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, None, None, 2)
+        px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, None)
+        assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
+
+
 def test_whitted_lanes_sharded_equal_unsharded(devsim, rt):
     prims = rt.whitted_create_scene(0)
     w, h = 50, 41
