@@ -144,7 +144,10 @@ __global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, 
 
 // Stages the scene tables of a WFrame into shared memory and redirects the frame's pointers to the copies.
 // layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | runs[3*n_runs] | rrad[n] (optional) | lights[n_lights] (optional)
-__device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, int stage_materials, f4 *&s_geom, int *&s_runs) {
+// STAGED is a template parameter so that the compiler knows the material pointers are shared-memory pointers (LDS
+// instead of generic loads) in the common case.
+template <bool stage_materials>
+__device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, f4 *&s_geom, int *&s_runs) {
     const int n = F.n;
     s_geom = s_raw;
     f4 *s_ma = s_geom + n, *s_mb = s_ma + n;
@@ -171,14 +174,14 @@ __device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, int stage_mate
 // twin.  The reference copies the 96-byte AoS primitives to local memory (:254-258) and keeps a
 // 64-slot x 80-byte ray queue in private memory; here the primitives are SoA float4 in shared memory
 // and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
-template <bool COUNT>
+template <bool COUNT, bool STAGED>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
-               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, int stage_materials) {
+               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     f4 *s_geom; int *s_runs;
-    stage_scene(F, s_raw, stage_materials, s_geom, s_runs);
+    stage_scene<STAGED>(F, s_raw, s_geom, s_runs);
 
     f4 queue[3 * W_QUEUE_SLOTS];
     WLane L;
@@ -237,7 +240,7 @@ r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *wo
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     f4 *s_geom; int *s_runs;
-    stage_scene(F.W, s_raw, 1, s_geom, s_runs);
+    stage_scene<true>(F.W, s_raw, s_geom, s_runs);
 
     R306Tree T;
     R306Lane L;
@@ -403,8 +406,9 @@ size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_materia
 
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_materials);
-    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *, int);
-    kern_t k = p.count ? whitted_kernel<true> : whitted_kernel<false>;
+    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *);
+    kern_t k = p.stage_materials ? (p.count ? whitted_kernel<true, true> : whitted_kernel<false, true>)
+                                 : (p.count ? whitted_kernel<true, false> : whitted_kernel<false, false>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int nb = blocks_per_sm(k, W_THREADS, smem);
@@ -429,6 +433,6 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         n_work = p.n_valid;
     }
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
-                                                  p.counters, p.stage_materials);
+                                                  p.counters);
     return cudaGetLastError();
 }

@@ -9,7 +9,10 @@
 // Launch shape (overridable with -D for the A/B builds of tools/variants.sh).
 // smallpt: 128-thread CTAs capped at 64 registers (8 CTAs = 32 warps per SM) measured 6 % faster on Cornell than
 // 256 threads at the 65 registers ptxas picks on its own, which costs a whole CTA per SM (profiles/r01_ab_variants.txt).
-// Whitted: left to ptxas (83 registers, 20 warps per SM) -- every cap tried was slower.
+// Whitted: 64-thread CTAs capped at 85 registers (12 CTAs = 24 warps per SM): with the materials read through shared-memory
+// pointers the kernel needs 105 registers uncapped; at 85 the few spills cost less than the extra warps bring (3.50 ms
+// against 3.86 ms at 1080p), below that they land in the query loops (profiles/r01_ab_variants.txt).  Parking the cold
+// part of the lane state in shared memory by hand was slower than ptxas's own choice.
 #ifndef PT_THREADS
 #define PT_THREADS 128
 #endif
@@ -21,10 +24,10 @@
 #define PT_ALIGNED_MAX_SPHERES 64
 #endif
 #ifndef W_THREADS
-#define W_THREADS 128
+#define W_THREADS 64
 #endif
 #ifndef W_MIN_BLOCKS
-#define W_MIN_BLOCKS 1
+#define W_MIN_BLOCKS 12
 #endif
 #ifndef W_PLANE_PAIRS
 #define W_PLANE_PAIRS 1
