@@ -257,6 +257,8 @@ int rt_whitted_launch(rt_ctx *ctx) {
     p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
     p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
     p.stage_materials = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 1) <= 32 * 1024 ? 1 : 0;
+    p.sphere_lights = ctx->w_nl;
+    for (int l : ctx->w_soa.lights) if (!(ctx->w_soa.flags[l] & W_FLAG_SPHERE)) p.sphere_lights = 0;
     p.order = nullptr; p.class_counts = nullptr;
     p.n_valid = (uint32_t)p.shard.local_rows * (uint32_t)ctx->w_w;
     if (ctx->whitted_sort && p.n_items) {

@@ -174,7 +174,8 @@ __device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, f4 *&s_geom, i
 // twin.  The reference copies the 96-byte AoS primitives to local memory (:254-258) and keeps a
 // 64-slot x 80-byte ray queue in private memory; here the primitives are SoA float4 in shared memory
 // and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
-template <bool COUNT, bool STAGED>
+// NL > 0: the scene has exactly NL lights and all of them are spheres (straight-line shadow set-up, one batch).
+template <bool COUNT, bool STAGED, int NL>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
                uint32_t *pixels, unsigned *work_counter, unsigned long long *counters) {
@@ -210,11 +211,11 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
         // that hit a surface tests up to three shadow rays at once; then the finished rays are folded into their pixels.
         const bool nq = L.phase == PH_NEAREST;
         w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
-        if (nq) w_after_nearest<COUNT>(L, F);
+        if (nq) w_after_nearest<COUNT, NL>(L, F);
         while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
             const bool sq = L.phase == PH_SHADOW;
             w_query_shadow<COUNT>(L, s_geom, s_runs, F.n_runs, sq);
-            if (sq) w_after_shadow<COUNT>(L, F);
+            if (sq) w_after_shadow<COUNT, NL>(L, F);
         }
         if (L.phase == PH_FINAL && w_finalize<COUNT>(L, F, queue))
             pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(L.ar, L.ag, L.ab);
@@ -407,8 +408,9 @@ size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_materia
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_materials);
     typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *);
-    kern_t k = p.stage_materials ? (p.count ? whitted_kernel<true, true> : whitted_kernel<false, true>)
-                                 : (p.count ? whitted_kernel<true, false> : whitted_kernel<false, false>);
+    kern_t k = !p.stage_materials ? (p.count ? whitted_kernel<true, false, 0> : whitted_kernel<false, false, 0>)
+             : p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, true, 3> : whitted_kernel<false, true, 3>)
+                                    : (p.count ? whitted_kernel<true, true, 0> : whitted_kernel<false, true, 0>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int nb = blocks_per_sm(k, W_THREADS, smem);

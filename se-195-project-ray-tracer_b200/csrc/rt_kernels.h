@@ -54,6 +54,7 @@ struct WLaunch {
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
     int count, sm_count, stage_materials, max_blocks_per_sm;
+    int sphere_lights;          // number of lights when all of them are spheres, else 0
     uint32_t *order;            // NULL: screen order; else scratch of 3 x n_items entries: one work list per cost class
     unsigned *class_counts;     // 3 x u32 scratch: entries in each list
     uint32_t n_valid;           // pixels owned by this rank (n_items minus the padding of the 8x4 blocks)

@@ -396,8 +396,24 @@ RT_HD void w_next_shadow_batch(WLane &L, const WFrame &F) {
     L.phase = PH_SHADOW;
 }
 
+// The common case as straight-line code: exactly NL (<= W_SHADOW_BATCH) lights, all of them spheres (the reference's
+// scenes: 3), so the one batch holds lights[0 .. NL-1] and no selects, cursors or type checks are needed.  Same
+// operations in the same order as the general functions (NL = 0 selects those).
+template <int NL>
+RT_HD void w_shadow_batch_fixed(WLane &L, const WFrame &F) {
+    L.sblk = 0; L.ns = NL;
+#pragma unroll
+    for (int k = 0; k < NL; k++) {
+        float Lx, Ly, Lz, reach;
+        w_light_vector(F, L, F.lights[k], Lx, Ly, Lz, reach);
+        L.sox[k] = f_add(L.px, f_mul(Lx, W_EPS)); L.soy[k] = f_add(L.py, f_mul(Ly, W_EPS)); L.soz[k] = f_add(L.pz, f_mul(Lz, W_EPS));
+        L.slx[k] = Lx; L.sly[k] = Ly; L.slz[k] = Lz; L.sreach[k] = reach;
+    }
+    L.phase = PH_SHADOW;
+}
+
 // After the nearest-hit round (RNO:194-205).
-template <bool COUNT>
+template <bool COUNT, int NL = 0>
 RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
     if (COUNT) { L.c_nearest++; L.c_sphere_tests += (uint32_t)F.n_spheres; L.c_plane_tests += (uint32_t)F.n_planes; }
     L.dist = L.cumu; L.hit = L.qhit; L.hkind = L.qkind;
@@ -412,16 +428,28 @@ RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
             L.py = f_add(L.qoy, f_mul(L.qdy, L.dist));
             L.pz = f_add(L.qoz, f_mul(L.qdz, L.dist));
             L.li = 0;
-            w_next_shadow_batch(L, F);
+            if (NL > 0) w_shadow_batch_fixed<NL>(L, F);
+            else w_next_shadow_batch(L, F);
         }
     }
 }
 
 // After a shadow round: shade the batch's lights in index order (a blocked light adds exactly 0, so it is
 // skipped), then set up the next batch or complete the ray.
-template <bool COUNT>
+template <bool COUNT, int NL = 0>
 RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
     if (COUNT) L.c_shadow += (uint32_t)L.ns;
+    if (NL > 0) {
+#pragma unroll 1
+        for (int k = 0; k < NL; k++) {        // one copy of the shading code; k-th ray picked with selects
+            const float Lx = k == 0 ? L.slx[0] : (k == 1 ? L.slx[NL > 1 ? 1 : 0] : L.slx[NL > 2 ? 2 : 0]);
+            const float Ly = k == 0 ? L.sly[0] : (k == 1 ? L.sly[NL > 1 ? 1 : 0] : L.sly[NL > 2 ? 2 : 0]);
+            const float Lz = k == 0 ? L.slz[0] : (k == 1 ? L.slz[NL > 1 ? 1 : 0] : L.slz[NL > 2 ? 2 : 0]);
+            if (!((L.sblk >> k) & 1)) w_shade(L, F, F.lights[k], Lx, Ly, Lz, 1.0f);
+        }
+        L.phase = PH_FINAL;
+        return;
+    }
 #pragma unroll 1
     for (int k = 0; k < L.ns; k++) {          // a real loop (one copy of the shading code); the rays are picked with selects
         const float Lx = k == 0 ? L.slx[0] : (k == 1 ? L.slx[1] : L.slx[2]);
