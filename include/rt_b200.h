@@ -68,7 +68,7 @@ typedef enum {
     RT_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed; see rt_last_error() */
     RT_ERR_ARG = -3,         /* bad argument (null pointer, non-positive size, unknown integrator ...) */
     RT_ERR_STATE = -4,       /* call order: e.g. rt_pt_render before rt_pt_resize / set_scene / set_camera */
-    RT_ERR_CAPACITY = -5,    /* scene too large for this build's on-chip staging (Whitted only) */
+    RT_ERR_CAPACITY = -5,    /* scene too large for this build's on-chip staging (rt_r306_* only; the other tracers stream or read through L2) */
     RT_ERR_IO = -6           /* scene file could not be read / parsed */
 } rt_status;
 

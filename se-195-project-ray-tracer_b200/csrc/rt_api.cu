@@ -209,8 +209,6 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(cudaSetDevice(ctx->device));
     WSoA &soa = ctx->w_soa;
     build_w_soa(prims, n, soa);
-    if (rtk_whitted_smem_bytes(n, (int)soa.lights.size(), (int)soa.runs.size() / 3, 0) > (size_t)ctx->max_smem_optin)
-        return fail(ctx, RT_ERR_CAPACITY, "rt_whitted_upload: %d primitives exceed the %d-byte shared-memory staging of this build", n, ctx->max_smem_optin);
     CK(upload_vec(&ctx->d_wgeom, &ctx->cap_wgeom, soa.geom, ctx->stream));
     CK(upload_vec(&ctx->d_wma, &ctx->cap_wma, soa.mat_a, ctx->stream));
     CK(upload_vec(&ctx->d_wmb, &ctx->cap_wmb, soa.mat_b, ctx->stream));
@@ -256,7 +254,8 @@ int rt_whitted_launch(rt_ctx *ctx) {
     p.pixels = ctx->peer_wpixels ? ctx->peer_wpixels : ctx->d_wpixels;     // fused gather: store straight into rank 0's frame
     p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
     p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
-    p.stage_materials = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 1) <= 32 * 1024 ? 1 : 0;
+    p.stage_mode = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 2) <= RTK_WHITTED_STAGE_LIMIT ? 2
+                 : rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 1) <= RTK_WHITTED_STAGE_LIMIT ? 1 : 0;
     p.sphere_lights = ctx->w_nl;
     for (int l : ctx->w_soa.lights) if (!(ctx->w_soa.flags[l] & W_FLAG_SPHERE)) p.sphere_lights = 0;
     p.order = nullptr; p.class_counts = nullptr;
@@ -307,7 +306,7 @@ int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, in
     auto &R = ctx->r306;
     build_r306_soa(prims, n, R.soa);
     build_r306_screen(w, h, R.h_sx, R.h_sy, &R.DX, &R.DY);
-    if (rtk_whitted_smem_bytes(n, (int)R.soa.lights.size(), (int)R.soa.runs.size() / 3, 1) > (size_t)ctx->max_smem_optin)
+    if (rtk_whitted_smem_bytes(n, (int)R.soa.lights.size(), (int)R.soa.runs.size() / 3, 2) > (size_t)ctx->max_smem_optin)
         return fail(ctx, RT_ERR_CAPACITY, "rt_r306_upload: %d primitives exceed the %d-byte shared-memory staging of this build", n, ctx->max_smem_optin);
     CK(upload_vec(&R.geom, &R.cap_geom, R.soa.geom, ctx->stream));
     CK(upload_vec(&R.ma, &R.cap_ma, R.soa.mat_a, ctx->stream));

@@ -143,30 +143,33 @@ __global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, 
 }
 
 // Stages the scene tables of a WFrame into shared memory and redirects the frame's pointers to the copies.
-// layout: geom[n] | mat_a[n] | mat_b[n] (optional) | flags[n] | runs[3*n_runs] | rrad[n] (optional) | lights[n_lights] (optional)
-// STAGED is a template parameter so that the compiler knows the material pointers are shared-memory pointers (LDS
-// instead of generic loads) in the common case.
-template <bool stage_materials>
-__device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, f4 *&s_geom, int *&s_runs) {
+// layout: geom[n] | mat_a[n] | mat_b[n] (MODE 2) | flags[n] | runs[3*n_runs] | rrad[n] (MODE 2) | lights[n_lights] (MODE 2)
+// MODE 2: everything on chip (small scenes; the compiler then knows the material pointers are shared-memory pointers:
+// LDS instead of generic loads).  MODE 1: geometry, flags and runs only.  MODE 0: nothing is staged -- a scene larger
+// than the per-CTA share of shared memory is read through L1 / L2 (every lane of a warp reads the same record).
+template <int MODE>
+__device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, const f4 *&s_geom_out, const int *&s_runs_out) {
+    if (MODE == 0) { s_geom_out = F.geom; s_runs_out = F.runs; return; }
     const int n = F.n;
-    s_geom = s_raw;
+    f4 *s_geom = s_raw;
     f4 *s_ma = s_geom + n, *s_mb = s_ma + n;
-    int *ibase = stage_materials ? (int *)(s_mb + n) : (int *)(s_geom + n);
+    int *ibase = MODE == 2 ? (int *)(s_mb + n) : (int *)(s_geom + n);
     int *s_flags = ibase;
-    s_runs = ibase + n;
+    int *s_runs = ibase + n;
     float *s_rr = (float *)(s_runs + 3 * F.n_runs);
     int *s_li = (int *)(s_rr + n);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         s_geom[i] = F.geom[i];
         s_flags[i] = F.flags[i];
-        if (stage_materials) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; }
+        if (MODE == 2) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; }
     }
     for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) s_runs[i] = F.runs[i];
-    if (stage_materials)
+    if (MODE == 2)
         for (int i = threadIdx.x; i < F.n_lights; i += blockDim.x) s_li[i] = F.lights[i];
     __syncthreads();
     F.geom = s_geom; F.flags = s_flags;
-    if (stage_materials) { F.mat_a = s_ma; F.mat_b = s_mb; F.rrad = s_rr; F.lights = s_li; }
+    if (MODE == 2) { F.mat_a = s_ma; F.mat_b = s_mb; F.rrad = s_rr; F.lights = s_li; }
+    s_geom_out = s_geom; s_runs_out = s_runs;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -175,13 +178,13 @@ __device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, f4 *&s_geom, i
 // 64-slot x 80-byte ray queue in private memory; here the primitives are SoA float4 in shared memory
 // and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
 // NL > 0: the scene has exactly NL lights and all of them are spheres (straight-line shadow set-up, one batch).
-template <bool COUNT, bool STAGED, int NL>
+template <bool COUNT, int STAGED, int NL>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
                uint32_t *pixels, unsigned *work_counter, unsigned long long *counters) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
-    f4 *s_geom; int *s_runs;
+    const f4 *s_geom; const int *s_runs;
     stage_scene<STAGED>(F, s_raw, s_geom, s_runs);
 
     f4 queue[3 * W_QUEUE_SLOTS];
@@ -240,8 +243,8 @@ __global__ void __launch_bounds__(W_THREADS)
 r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *work_counter) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
-    f4 *s_geom; int *s_runs;
-    stage_scene<true>(F.W, s_raw, s_geom, s_runs);
+    const f4 *s_geom; const int *s_runs;
+    stage_scene<2>(F.W, s_raw, s_geom, s_runs);
 
     R306Tree T;
     R306Lane L;
@@ -287,13 +290,18 @@ r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *wo
 // It changes WHEN a pixel is rendered, never what is computed for it.
 #define W_COST_CLASSES 3
 __global__ void __launch_bounds__(W_THREADS)
-whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* W_COST_CLASSES x n_items */, unsigned *class_counts) {
+whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* W_COST_CLASSES x n_items */, unsigned *class_counts, int staged) {
     extern __shared__ f4 s_raw[];
-    f4 *s_geom = s_raw;
-    int *s_runs = (int *)(s_geom + F.n);
-    for (int i = threadIdx.x; i < F.n; i += blockDim.x) s_geom[i] = F.geom[i];
-    for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) s_runs[i] = F.runs[i];
-    __syncthreads();
+    const f4 *s_geom = F.geom;
+    const int *s_runs = F.runs;
+    if (staged) {
+        f4 *g = s_raw;
+        int *r = (int *)(g + F.n);
+        for (int i = threadIdx.x; i < F.n; i += blockDim.x) g[i] = F.geom[i];
+        for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) r[i] = F.runs[i];
+        __syncthreads();
+        s_geom = g; s_runs = r;
+    }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t per_pass = gridDim.x * blockDim.x;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n_items; base += per_pass) {   // warp-uniform trip count
@@ -387,7 +395,7 @@ cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigne
 }
 
 cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
-    const size_t smem = rtk_whitted_smem_bytes(p.frame.W.n, p.frame.W.n_lights, p.frame.W.n_runs, 1);
+    const size_t smem = rtk_whitted_smem_bytes(p.frame.W.n, p.frame.W.n_lights, p.frame.W.n_runs, 2);
     cudaError_t e = cudaFuncSetAttribute(r306_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int nb = blocks_per_sm(r306_kernel, W_THREADS, smem);
@@ -399,18 +407,20 @@ cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_materials) {
+size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode) {
+    if (stage_mode == 0) return 16;
     size_t b = (size_t)n * (sizeof(f4) + sizeof(int)) + (size_t)n_runs * 3 * sizeof(int);
-    if (stage_materials) b += (size_t)n * (2 * sizeof(f4) + sizeof(float)) + (size_t)n_lights * sizeof(int);
+    if (stage_mode == 2) b += (size_t)n * (2 * sizeof(f4) + sizeof(float)) + (size_t)n_lights * sizeof(int);
     return b < 16 ? 16 : b;
 }
 
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
-    const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_materials);
+    const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_mode);
     typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *);
-    kern_t k = !p.stage_materials ? (p.count ? whitted_kernel<true, false, 0> : whitted_kernel<false, false, 0>)
-             : p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, true, 3> : whitted_kernel<false, true, 3>)
-                                    : (p.count ? whitted_kernel<true, true, 0> : whitted_kernel<false, true, 0>);
+    kern_t k = p.stage_mode == 0 ? (p.count ? whitted_kernel<true, 0, 0> : whitted_kernel<false, 0, 0>)
+             : p.stage_mode == 1 ? (p.count ? whitted_kernel<true, 1, 0> : whitted_kernel<false, 1, 0>)
+             : p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, 2, 3> : whitted_kernel<false, 2, 3>)
+                                    : (p.count ? whitted_kernel<true, 2, 0> : whitted_kernel<false, 2, 0>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int nb = blocks_per_sm(k, W_THREADS, smem);
@@ -422,7 +432,7 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     uint32_t n_work = p.n_items;
     if (p.order) {
         // scheduling pre-pass: order[] = expensive pixels first; the number of valid entries is known on the host
-        size_t csmem = (size_t)p.frame.n * sizeof(f4) + (size_t)p.frame.n_runs * 3 * sizeof(int);
+        size_t csmem = p.stage_mode ? (size_t)p.frame.n * sizeof(f4) + (size_t)p.frame.n_runs * 3 * sizeof(int) : 16;
         if (csmem < 16) csmem = 16;
         e = cudaFuncSetAttribute(whitted_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
         if (e != cudaSuccess) return e;
@@ -430,7 +440,7 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         long cgrid = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
         if (cgrid > (long)p.sm_count * 16) cgrid = (long)p.sm_count * 16;
-        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame, p.shard, p.n_items, p.order, p.class_counts);
+        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame, p.shard, p.n_items, p.order, p.class_counts, p.stage_mode != 0);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         n_work = p.n_valid;
     }

@@ -53,7 +53,8 @@ struct WLaunch {
     uint32_t n_items;
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
-    int count, sm_count, stage_materials, max_blocks_per_sm;
+    int count, sm_count, max_blocks_per_sm;
+    int stage_mode;             // 2: scene tables + materials in shared memory, 1: geometry / flags / runs only, 0: read through L1 / L2
     int sphere_lights;          // number of lights when all of them are spheres, else 0
     uint32_t *order;            // NULL: screen order; else scratch of 3 x n_items entries: one work list per cost class
     unsigned *class_counts;     // 3 x u32 scratch: entries in each list
@@ -73,5 +74,6 @@ cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream);
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream);
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);
-size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_materials);
+size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode);
+#define RTK_WHITTED_STAGE_LIMIT (18 * 1024)      /* per-CTA share of shared memory with 12 resident CTAs per SM */
 cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigned long long n, int sm_count, cudaStream_t stream);

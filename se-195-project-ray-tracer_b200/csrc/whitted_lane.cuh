@@ -328,10 +328,8 @@ RT_HD void w_pop(const f4 *q, WLane &L) {
 }
 
 // Diffuse + specular contribution of light `l` (RNO:242-276); Lx.. is the unit vector to the light.
-RT_HD void w_shade(WLane &L, const WFrame &F, int l, float Lx, float Ly, float Lz, float lit) {
-    const f4 ma = F.mat_a[L.hit], mb = F.mat_b[L.hit], lc = F.mat_a[l];
-    float nx, ny, nz;
-    w_normal(F, L.hit, L.px, L.py, L.pz, nx, ny, nz);
+// (ma, mb) = material of the hit primitive, (nx, ny, nz) its normal at the hit point, lc = the light's colour.
+RT_HD void w_shade_with(WLane &L, const f4 ma, const f4 mb, const f4 lc, float nx, float ny, float nz, float Lx, float Ly, float Lz, float lit) {
     if (mb.x > 0.f) {
         const float nl = dot3(nx, ny, nz, Lx, Ly, Lz);
         if (nl > 0.f) {
@@ -355,6 +353,11 @@ RT_HD void w_shade(WLane &L, const WFrame &F, int l, float Lx, float Ly, float L
             L.cb = f_add(L.cb, f_mul(k, lc.z));
         }
     }
+}
+RT_HD void w_shade(WLane &L, const WFrame &F, int l, float Lx, float Ly, float Lz, float lit) {
+    float nx, ny, nz;
+    w_normal(F, L.hit, L.px, L.py, L.pz, nx, ny, nz);
+    w_shade_with(L, F.mat_a[L.hit], F.mat_b[L.hit], F.mat_a[l], nx, ny, nz, Lx, Ly, Lz, lit);
 }
 
 // Sets up the next batch of shadow rays (lights li, li+1, ... in index order, RNO:206-241), or marks the
@@ -440,12 +443,19 @@ template <bool COUNT, int NL = 0>
 RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
     if (COUNT) L.c_shadow += (uint32_t)L.ns;
     if (NL > 0) {
+        const f4 ma = F.mat_a[L.hit], mb = F.mat_b[L.hit];                // once per hit, not per light
+        float nx, ny, nz;
+        w_normal(F, L.hit, L.px, L.py, L.pz, nx, ny, nz);
+#ifdef W_UNROLL_SHADE
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
         for (int k = 0; k < NL; k++) {        // one copy of the shading code; k-th ray picked with selects
             const float Lx = k == 0 ? L.slx[0] : (k == 1 ? L.slx[NL > 1 ? 1 : 0] : L.slx[NL > 2 ? 2 : 0]);
             const float Ly = k == 0 ? L.sly[0] : (k == 1 ? L.sly[NL > 1 ? 1 : 0] : L.sly[NL > 2 ? 2 : 0]);
             const float Lz = k == 0 ? L.slz[0] : (k == 1 ? L.slz[NL > 1 ? 1 : 0] : L.slz[NL > 2 ? 2 : 0]);
-            if (!((L.sblk >> k) & 1)) w_shade(L, F, F.lights[k], Lx, Ly, Lz, 1.0f);
+            if (!((L.sblk >> k) & 1)) w_shade_with(L, ma, mb, F.mat_a[F.lights[k]], nx, ny, nz, Lx, Ly, Lz, 1.0f);
         }
         L.phase = PH_FINAL;
         return;

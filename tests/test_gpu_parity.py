@@ -111,10 +111,14 @@ def test_whitted_scene1_and_open_scene(gpu, orc, rt):
 def test_whitted_on_generated_sphere_scenes(gpu, orc, rt, tmp_path):
     """the Whitted tracer on .scn scenes -- the shipped complex.scn (783 spheres, one long run of equal
     type) and the Cornell box (spheres as walls: every ray starts inside primitives) converted by rt_whitted_from_spheres:
-    pixels and hit IDs equal the oracle's.  A scene that cannot be staged on chip is refused with a code."""
+    pixels and hit IDs equal the oracle's.  The 3 908- and 19 533-sphere scenes do not fit the per-CTA share of shared
+    memory: geometry-only staging, then no staging at all (tables read through L1 / L2) -- same parity bar."""
     p = tmp_path / "c4.scn"
     rt.write_complex_scene(str(p), 4)
-    for path, (w, h) in [(str(p), (40, 30)), (None, (64, 48))]:
+    p5, p6 = tmp_path / "c5.scn", tmp_path / "c6.scn"
+    rt.write_complex_scene(str(p5), 5)
+    rt.write_complex_scene(str(p6), 6)
+    for path, (w, h) in [(str(p), (40, 30)), (None, (64, 48)), (str(p5), (32, 24)), (str(p6), (24, 18))]:
         spheres, cam = rt.read_scene(path, w, h) if path else (load_smallpt_golden(rt, "cornell")[k] for k in ("spheres", "camera"))
         prims = rt.whitted_from_spheres(spheres, cam)
         px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
@@ -122,11 +126,6 @@ def test_whitted_on_generated_sphere_scenes(gpu, orc, rt, tmp_path):
         orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 16, None)
         assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o), prims.size
         assert (px[..., :3].sum(-1) > 0).mean() > 0.15 and len(np.unique(hits)) > 4
-    big = np.zeros(20000, rt.PRIMITIVE_DTYPE)
-    big["type"] = 1; big["radius"] = 1; big["sq_radius"] = 1; big["r_radius"] = 1
-    with pytest.raises(rt.RtError) as e:
-        gpu.whitted_render(big, 16, 16)
-    assert e.value.code == rt.RT_ERR_CAPACITY
 
 
 def test_whitted_cost_ordered_schedule_changes_nothing(gpu, rt):

@@ -4,11 +4,8 @@ set -e
 cd "$(dirname "$0")/../se-195-project-ray-tracer_b200"
 rm -f ../variants/*.so
 build() { tag=$1; shift; nvcc "$@" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -std=c++17 -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off -shared -o ../variants/librt_$tag.so csrc/rt_kernels.cu csrc/rt_api.cu host/scene_io.cpp & }
-build w64b12x -DW_THREADS=64 -DW_MIN_BLOCKS=12
-build w64b11 -DW_THREADS=64 -DW_MIN_BLOCKS=11
-build w64b13 -DW_THREADS=64 -DW_MIN_BLOCKS=13
-build w64b14 -DW_THREADS=64 -DW_MIN_BLOCKS=14
-build w64b16 -DW_THREADS=64 -DW_MIN_BLOCKS=16
-build w64b12x -DW_THREADS=64 -DW_MIN_BLOCKS=12
+build base
+build unroll -DW_UNROLL_SHADE
+build base
 wait
 ls ../variants
