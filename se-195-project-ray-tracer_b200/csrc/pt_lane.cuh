@@ -73,12 +73,16 @@ RT_HD void pt_test(PtLane &L, const f4 g, int i, bool live) {
     const float opx = f_sub(g.x, L.ox), opy = f_sub(g.y, L.oy), opz = f_sub(g.z, L.oz);
     const float b = dot3(opx, opy, opz, L.dx, L.dy, L.dz);
     const float det = f_add(f_sub(f_mul(b, b), dot3(opx, opy, opz, opx, opy, opz)), g.w);
-    const bool cand = live && !(det < 0.f);
+    const bool cand = live & !(det < 0.f);
     if (warp_any(cand)) {
-        const float sq = f_sqrt(det);
+        const float dv[1] = { det };
+        const bool need[1] = { cand };
+        float sqv[1];
+        sqrt_group<1>(dv, need, sqv);
+        const float sq = sqv[0];
         const float t1 = f_sub(b, sq), t2 = f_add(b, sq);
         const float t = t1 > PT_EPS ? t1 : t2;                 // first root if beyond EPSILON, else the second
-        if (cand && t > PT_EPS && t < L.cumu) { L.cumu = t; L.hit = i; }
+        if (cand & (t > PT_EPS) & (t < L.cumu)) { L.cumu = t; L.hit = i; }
     }
 }
 
@@ -96,12 +100,12 @@ RT_HD void pt_test4(PtLane &L, const f4 *g, int i, bool live) {
         const float opx = f_sub(s.x, L.ox), opy = f_sub(s.y, L.oy), opz = f_sub(s.z, L.oz);
         b[k] = dot3(opx, opy, opz, L.dx, L.dy, L.dz);
         det[k] = f_add(f_sub(f_mul(b[k], b[k]), dot3(opx, opy, opz, opx, opy, opz)), s.w);
-        cand[k] = live && !(det[k] < 0.f);
-        any = any || cand[k];
+        cand[k] = live & !(det[k] < 0.f);
+        any = any | cand[k];
     }
     if (warp_any(any)) {
         float t[4], sq[4];
-        sqrt_group<4>(det, sq);
+        sqrt_group<4>(det, cand, sq);              // a negative discriminant of a lane that is not a candidate must not cost the slow path
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const float t1 = f_sub(b[k], sq[k]), t2 = f_add(b[k], sq[k]);
@@ -110,7 +114,7 @@ RT_HD void pt_test4(PtLane &L, const f4 *g, int i, bool live) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (COUNT && live && L.phase == PH_SHADOW && L.hit < 0) L.c_tests++;
-            if (cand[k] && t[k] > PT_EPS && t[k] < L.cumu) { L.cumu = t[k]; L.hit = i - k; }
+            if (cand[k] & (t[k] > PT_EPS) & (t[k] < L.cumu)) { L.cumu = t[k]; L.hit = i - k; }
         }
     } else if (COUNT && live && L.phase == PH_SHADOW && L.hit < 0) L.c_tests += 4;
 }

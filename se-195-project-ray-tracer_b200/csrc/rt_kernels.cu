@@ -420,6 +420,8 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     kern_t k = p.stage_mode == 0 ? (p.count ? whitted_kernel<true, 0, 0> : whitted_kernel<false, 0, 0>)
              : p.stage_mode == 1 ? (p.count ? whitted_kernel<true, 1, 0> : whitted_kernel<false, 1, 0>)
              : p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, 2, 3> : whitted_kernel<false, 2, 3>)
+             : p.sphere_lights == 2 ? (p.count ? whitted_kernel<true, 2, 2> : whitted_kernel<false, 2, 2>)
+             : p.sphere_lights == 1 ? (p.count ? whitted_kernel<true, 2, 1> : whitted_kernel<false, 2, 1>)
                                     : (p.count ? whitted_kernel<true, 2, 0> : whitted_kernel<false, 2, 0>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
