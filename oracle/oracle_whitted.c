@@ -169,6 +169,10 @@ void oracle_whitted_rows(uint8_t *pixels, int32_t *hit_ids, int w, int h, int y0
                     while (head < tail) {
                         if (ctr && (uint32_t)(tail - head) > ctr->queue_high_water) ctr->queue_high_water = tail - head;
                         const wray cur = fifo[head++];
+                        /* `at` stays (0,0,0) when the ray hits a light: the reference leaves point_intersect
+                         * uninitialised there (RNO:197-200) yet spawns children from it if the light's material
+                         * reflects or refracts (RNO:370-431).  Defined here as the origin; no shipped scene has
+                         * such a light. */
                         v3 col = { 0, 0, 0 }, at = { 0, 0, 0 };
                         float dist; int kind = 0;
                         int hit = trace_one(&cur, prims, n, &col, &dist, &at, &kind, ctr);

@@ -14,13 +14,23 @@ extern "C" {
 
 // Renders one frame into dest (w*h Pixels, 0x00RRGGBB; rows outside 20..529 are left untouched).
 void ref_r306_render(unsigned int *dest, int w, int h) {
-    static bool ready = false;
-    if (!ready) {
-        Engine_Constructor();
-        TracedRays_init();
-        Scene_InitScene();
-        ready = true;
-    }
+    Engine_Constructor();
+    TracedRays_init();
+    Scene_InitScene();
+    Engine_SetTarget((Pixel *)dest, w, h);
+    Engine_InitRender();
+    Engine_Render();
+}
+
+// The same with a caller-supplied scene table (n reference Primitive records of 96 bytes) instead of Scene_InitScene's.
+void ref_r306_render_scene(unsigned int *dest, int w, int h, const void *prims, int n) {
+    static Primitive table[256];
+    Engine_Constructor();
+    TracedRays_init();
+    m_Scene = (Scene *)malloc(sizeof(Scene));
+    memcpy(table, prims, sizeof(Primitive) * (size_t)(n > 256 ? 256 : n));
+    m_Scene->m_Primitive = table;
+    m_Scene->m_Primitives = n > 256 ? 256 : n;
     Engine_SetTarget((Pixel *)dest, w, h);
     Engine_InitRender();
     Engine_Render();

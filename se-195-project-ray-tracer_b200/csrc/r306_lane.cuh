@@ -126,8 +126,11 @@ RT_HD void r306_next_shadow_batch(R306Lane &L, const R306Frame &F) {
         if (q.li >= F.W.n_lights) { q.phase = PH_FINAL; return; }
         const int l = F.W.lights[q.li];
         if (F.W.flags[l] & W_FLAG_SPHERE) break;
-        float Lx, Ly, Lz, len;
-        r306_light_vector(F, q, l, Lx, Ly, Lz, len);
+        const f4 lg = F.W.lcenter[q.li];                           // m_Centre of a light that is not a sphere (R306:123-135)
+        const float ex = f_sub(lg.x, q.px), ey = f_sub(lg.y, q.py), ez = f_sub(lg.z, q.pz);
+        const float len = f_sqrt(f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(ez, ez)));
+        const float inv = f_rcp(len);
+        float Lx = f_mul(ex, inv), Ly = f_mul(ey, inv), Lz = f_mul(ez, inv);
         if (!(len > 0.f)) Lx = Ly = Lz = 0.f;
         r306_shade(L, F, l, Lx, Ly, Lz);
         q.li++;

@@ -37,7 +37,7 @@ struct rt_ctx {
     unsigned *d_wclass = nullptr;
     // Whitted
     int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_nr = 0, w_want_hits = 0;
-    f4 *d_wgeom = nullptr, *d_wma = nullptr, *d_wmb = nullptr;
+    f4 *d_wgeom = nullptr, *d_wma = nullptr, *d_wmb = nullptr, *d_wlcenter = nullptr; size_t cap_wlcenter = 0;
     int *d_wflags = nullptr, *d_wlights = nullptr, *d_wruns = nullptr, *d_wruns_hot = nullptr; size_t cap_wruns_hot = 0; int w_nr_hot = 0;
     float *d_wrrad = nullptr;
     uint32_t *d_wpixels = nullptr;
@@ -47,7 +47,7 @@ struct rt_ctx {
     size_t cap_pgeom = 0, cap_pemis = 0, cap_pcolr = 0, cap_plights = 0;
     // raytracer3.0.06 frame (config 1)
     struct {
-        f4 *geom = nullptr, *ma = nullptr, *mb = nullptr; int *flags = nullptr, *lights = nullptr, *runs = nullptr; float *rrad = nullptr, *sx = nullptr, *sy = nullptr;
+        f4 *geom = nullptr, *ma = nullptr, *mb = nullptr; int *flags = nullptr, *lights = nullptr, *runs = nullptr; float *rrad = nullptr, *sx = nullptr, *sy = nullptr; f4 *lcenter = nullptr; size_t cap_lcenter = 0;
         size_t cap_geom = 0, cap_ma = 0, cap_mb = 0, cap_flags = 0, cap_lights = 0, cap_runs = 0, cap_rrad = 0, cap_sx = 0, cap_sy = 0;
         uint32_t *dest = nullptr; size_t dest_cap = 0;
         int w = 0, h = 0, n = 0, nl = 0, nr = 0, ns = 0, np = 0;
@@ -142,11 +142,11 @@ void rt_destroy(rt_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->peer_wpixels) cudaIpcCloseMemHandle(ctx->peer_wpixels);
     if (ctx->peer_ppixels) cudaIpcCloseMemHandle(ctx->peer_ppixels);
-    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_worder, ctx->d_wclass,
+    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
     for (void *b : bufs) if (b) cudaFree(b);
-    void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest };
+    void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter };
     for (void *b : rbufs) if (b) cudaFree(b);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -214,6 +214,7 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(upload_vec(&ctx->d_wmb, &ctx->cap_wmb, soa.mat_b, ctx->stream));
     CK(upload_vec(&ctx->d_wflags, &ctx->cap_wflags, soa.flags, ctx->stream));
     CK(upload_vec(&ctx->d_wlights, &ctx->cap_wlights, soa.lights, ctx->stream));
+    CK(upload_vec(&ctx->d_wlcenter, &ctx->cap_wlcenter, soa.lcenter, ctx->stream));
     CK(upload_vec(&ctx->d_wrrad, &ctx->cap_wrrad, soa.rrad, ctx->stream));
     CK(upload_vec(&ctx->d_wruns, &ctx->cap_wruns, soa.runs, ctx->stream));
     CK(upload_vec(&ctx->d_wruns_hot, &ctx->cap_wruns_hot, soa.runs_hot, ctx->stream));
@@ -241,7 +242,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     WLaunch p;
     WFrame &F = p.frame;
-    F.geom = ctx->d_wgeom; F.mat_a = ctx->d_wma; F.mat_b = ctx->d_wmb; F.flags = ctx->d_wflags; F.lights = ctx->d_wlights;
+    F.geom = ctx->d_wgeom; F.mat_a = ctx->d_wma; F.mat_b = ctx->d_wmb; F.flags = ctx->d_wflags; F.lights = ctx->d_wlights; F.lcenter = ctx->d_wlcenter;
     if (ctx->counting) { F.runs = ctx->d_wruns; F.n_runs = ctx->w_nr; }            // every primitive, so that the test counters equal the oracle's
     else { F.runs = ctx->d_wruns_hot; F.n_runs = ctx->w_nr_hot; }
     F.rrad = ctx->d_wrrad; F.n = ctx->w_n; F.n_lights = ctx->w_nl; F.n_spheres = ctx->w_ns; F.n_planes = ctx->w_np;
@@ -313,6 +314,7 @@ int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, in
     CK(upload_vec(&R.mb, &R.cap_mb, R.soa.mat_b, ctx->stream));
     CK(upload_vec(&R.flags, &R.cap_flags, R.soa.flags, ctx->stream));
     CK(upload_vec(&R.lights, &R.cap_lights, R.soa.lights, ctx->stream));
+    CK(upload_vec(&R.lcenter, &R.cap_lcenter, R.soa.lcenter, ctx->stream));
     CK(upload_vec(&R.runs, &R.cap_runs, R.soa.runs_hot, ctx->stream));
     CK(upload_vec(&R.rrad, &R.cap_rrad, R.soa.rrad, ctx->stream));
     CK(upload_vec(&R.sx, &R.cap_sx, R.h_sx, ctx->stream));
@@ -336,7 +338,7 @@ int rt_r306_launch(rt_ctx *ctx) {
     CK(cudaSetDevice(ctx->device));
     R306Launch p;
     WFrame &F = p.frame.W;
-    F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.runs = R.runs; F.n_runs = R.nr;
+    F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.lcenter = R.lcenter; F.runs = R.runs; F.n_runs = R.nr;
     F.rrad = R.rrad; F.n = R.n; F.n_lights = R.nl; F.n_spheres = R.ns; F.n_planes = R.np;
     F.w = R.w; F.h = R.h; F.DX = R.DX; F.DY = R.DY; F.hit_ids = nullptr;
     p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;

@@ -36,6 +36,7 @@ inline void build_pt_soa(const rt_sphere *s, uint32_t n, PtSoA &out) {
 
 struct WSoA {
     std::vector<f4> geom, mat_a, mat_b;
+    std::vector<f4> lcenter;            // `center` of every light, in lights[] order
     std::vector<int> flags, lights, runs;
     std::vector<int> runs_hot;          // the same runs without primitives that can never be hit (timed launches use these)
     std::vector<float> rrad;
@@ -44,7 +45,7 @@ struct WSoA {
 
 inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
     out.geom.resize(n); out.mat_a.resize(n); out.mat_b.resize(n); out.flags.resize(n); out.rrad.resize(n);
-    out.lights.clear(); out.n_spheres = out.n_planes = 0;
+    out.lights.clear(); out.lcenter.clear(); out.n_spheres = out.n_planes = 0;
     for (int i = 0; i < n; i++) {
         int fl = 0;
         f4 g;
@@ -57,7 +58,11 @@ inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
         } else {                       // intersect() returns MISS for any other type (RNO:150-160): a plane that is never hit
             g.x = g.y = g.z = g.w = 0.f;
         }
-        if (p[i].is_light) { fl |= W_FLAG_LIGHT; out.lights.push_back(i); }
+        if (p[i].is_light) {
+            fl |= W_FLAG_LIGHT; out.lights.push_back(i);
+            f4 c = { p[i].center.x, p[i].center.y, p[i].center.z, 0.f };
+            out.lcenter.push_back(c);
+        }
         f4 a = { p[i].m_color.x, p[i].m_color.y, p[i].m_color.z, p[i].m_refl };
         f4 b = { p[i].m_diff, p[i].m_refr, p[i].m_refr_index, p[i].m_spec };
         out.geom[i] = g; out.mat_a[i] = a; out.mat_b[i] = b; out.flags[i] = fl; out.rrad[i] = p[i].r_radius;

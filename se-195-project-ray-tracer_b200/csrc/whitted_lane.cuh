@@ -35,6 +35,8 @@ enum { W_PRIMARY = 0, W_REFLECTED = 1, W_REFRACTED = 2 };   /* RNO:59-63 */
 struct WFrame {
     const f4 *geom, *mat_a, *mat_b;
     const int *flags, *lights;
+    const f4 *lcenter;          // lcenter[k] = the `center` field of light k (in lights[] order), whatever its type: a light that
+                                //  is not a sphere is shaded towards that point without a shadow ray (RNO:214-223); global memory
     const int *runs;            // maximal index runs of equal (type, is_light): triples (start, count, flags)
     const float *rrad;
     int n, n_lights, n_spheres, n_planes, n_runs;
@@ -372,17 +374,18 @@ RT_HD void w_light_vector(const WFrame &F, const WLane &L, int l, float &Lx, flo
     Lx = f_mul(inv, ex); Ly = f_mul(inv, ey); Lz = f_mul(inv, ez);
 }
 // A light that is not a sphere (none in the reference's scenes): shaded without a shadow ray.
-RT_HD void w_shade_unshadowed(WLane &L, const WFrame &F, int l) {
-    float Lx, Ly, Lz, reach;
-    w_light_vector(F, L, l, Lx, Ly, Lz, reach);
-    w_shade(L, F, l, Lx, Ly, Lz, 1.0f);
+RT_HD void w_shade_unshadowed(WLane &L, const WFrame &F, int l, int li) {
+    const f4 lg = F.lcenter[li];
+    const float ex = f_sub(lg.x, L.px), ey = f_sub(lg.y, L.py), ez = f_sub(lg.z, L.pz);
+    const float inv = f_rcp(f_sqrt(f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(ez, ez))));
+    w_shade(L, F, l, f_mul(inv, ex), f_mul(inv, ey), f_mul(inv, ez), 1.0f);
 }
 RT_HD void w_next_shadow_batch(WLane &L, const WFrame &F) {
     for (;;) {
         if (L.li >= F.n_lights) { L.phase = PH_FINAL; return; }
         const int l = F.lights[L.li];
         if (F.flags[l] & W_FLAG_SPHERE) break;
-        w_shade_unshadowed(L, F, l);
+        w_shade_unshadowed(L, F, l, L.li);
         L.li++;
     }
     L.ns = 0; L.sblk = 0;
@@ -426,6 +429,10 @@ RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
         if (F.flags[L.hit] & W_FLAG_LIGHT) {                           // RNO:197-200
             const f4 ma = F.mat_a[L.hit];
             L.cr = ma.x; L.cg = ma.y; L.cb = ma.z;
+            // The reference leaves point_intersect unwritten here, and its caller still spawns children from it when
+            // the light's material reflects or refracts (RNO:370-431) -- an uninitialised stack variable.  None of its
+            // scenes has such a light; the oracle and this kernel define the point as (0,0,0) in that case.
+            L.px = L.py = L.pz = 0.f;
         } else {
             L.px = f_add(L.qox, f_mul(L.qdx, L.dist));
             L.py = f_add(L.qoy, f_mul(L.qdy, L.dist));

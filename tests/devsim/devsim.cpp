@@ -42,7 +42,7 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     build_w_soa(prims, n, soa);
     WFrame F;
     F.geom = soa.geom.data(); F.mat_a = soa.mat_a.data(); F.mat_b = soa.mat_b.data();
-    F.flags = soa.flags.data(); F.lights = soa.lights.data(); F.rrad = soa.rrad.data();
+    F.flags = soa.flags.data(); F.lights = soa.lights.data(); F.lcenter = soa.lcenter.data(); F.rrad = soa.rrad.data();
     F.runs = soa.runs.data(); F.n_runs = (int)soa.runs.size() / 3;
     if (use_runs == 2) { F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3; }    // what timed launches walk
     F.n = n; F.n_lights = (int)soa.lights.size(); F.n_spheres = soa.n_spheres; F.n_planes = soa.n_planes;
@@ -86,7 +86,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
     R306Frame F;
     build_r306_screen(w, h, sx, sy, &F.W.DX, &F.W.DY);
     F.W.geom = soa.geom.data(); F.W.mat_a = soa.mat_a.data(); F.W.mat_b = soa.mat_b.data();
-    F.W.flags = soa.flags.data(); F.W.lights = soa.lights.data(); F.W.rrad = soa.rrad.data();
+    F.W.flags = soa.flags.data(); F.W.lights = soa.lights.data(); F.W.lcenter = soa.lcenter.data(); F.W.rrad = soa.rrad.data();
     F.W.runs = soa.runs_hot.data(); F.W.n_runs = (int)soa.runs_hot.size() / 3;
     F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
     F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;

@@ -108,6 +108,40 @@ def test_whitted_scene1_and_open_scene(gpu, orc, rt):
         assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
 
 
+@pytest.mark.parametrize("variant", ["no_lights", "one_light", "two_lights", "four_lights", "plane_light", "light_first", "single_sphere"])
+def test_whitted_light_configurations(gpu, orc, rt, variant):
+    """The kernel is specialised on the number of sphere lights (1, 2, 3) and has a general path for everything else
+    (no light, more than one shadow batch, a light that is not a sphere and therefore casts no shadow ray, RNO:223).
+    Each shape of the light list against the oracle, counters included."""
+    prims = rt.whitted_create_scene(0).copy()
+    lights = [13, 14, 15]
+    if variant == "no_lights":
+        prims["is_light"][lights] = 0
+    elif variant == "one_light":
+        prims["is_light"][[14, 15]] = 0
+    elif variant == "two_lights":
+        prims["is_light"][15] = 0
+    elif variant == "four_lights":
+        prims["is_light"][4] = 1                       # a sphere on the floor becomes a fourth light: two shadow batches
+    elif variant == "plane_light":
+        prims["is_light"][10] = 1                      # the ceiling plane as a light: shaded without a shadow ray
+    elif variant == "light_first":
+        prims = prims[[13, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 15, 16]]      # runs start with a light
+    elif variant == "single_sphere":
+        prims = prims[[13, 3]]                         # one light, one sphere, nothing else: most rays miss
+    w, h = 120, 90
+    gpu.set_counting(True)
+    px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+    c = gpu.counters()
+    gpu.set_counting(False)
+    px2, hits2 = gpu.whitted_render(prims, w, h, want_hit_ids=True)            # the timed (non-counting) kernel
+    px_o, hits_o, ctr_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32), np.zeros(5, np.uint64)
+    orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 8, vp(ctr_o))
+    assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o), variant
+    assert np.array_equal(hits2, hits_o) and np.array_equal(px2, px_o), variant
+    assert [c["nearest_queries"], c["shadow_queries"], c["sphere_tests"], c["plane_tests"]] == [int(v) for v in ctr_o[:4]], variant
+
+
 def test_whitted_on_generated_sphere_scenes(gpu, orc, rt, tmp_path):
     """the Whitted tracer on .scn scenes -- the shipped complex.scn (783 spheres, one long run of equal
     type) and the Cornell box (spheres as walls: every ray starts inside primitives) converted by rt_whitted_from_spheres:

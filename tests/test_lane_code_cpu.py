@@ -123,3 +123,16 @@ def test_r306_lanes_equal_the_reference_frame(devsim, rt):
         devsim.devsim_r306(vp(a), 97, 150, vp(prims), prims.size)
         L.ref_r306_render(vp(b), 97, 150)
         assert np.array_equal(a, b)
+        # other shapes of the scene table through the reference's own engine: one light, no light, a light that is not a
+        # sphere (shaded without a shadow ray towards its zero m_Centre), lights first, a primitive of unknown type
+        variants = []
+        v = prims.copy(); v["m_light"][[14, 15, 16]] = 0; variants.append(v)
+        v = prims.copy(); v["m_light"][:] = 0; variants.append(v)
+        v = prims.copy(); v["m_light"][11] = 1; variants.append(v)
+        variants.append(prims[[1, 14, 0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16]].copy())
+        v = prims.copy(); v["type"][5] = 3; variants.append(v)
+        for k, v in enumerate(variants):
+            a, b = np.zeros((131, 80), np.uint32), np.zeros((131, 80), np.uint32)
+            devsim.devsim_r306(vp(a), 80, 131, vp(v), v.size)
+            L.ref_r306_render_scene(vp(b), 80, 131, vp(v), v.size)
+            assert np.array_equal(a, b), k
