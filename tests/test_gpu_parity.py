@@ -284,6 +284,33 @@ def test_smallpt_cornell_equals_oracle(gpu, orc, rt, cornell, size, passes):
         assert np.array_equal(out["pixels"].reshape(-1), pix_o)
 
 
+def test_smallpt_step_aligned_and_plain_schedules_give_the_same_bits(gpu, orc, rt, cornell, tmp_path):
+    """RT_TUNE_PT_ALIGNED only changes which lanes of a warp run which shading step together; colours, pixels and RNG state
+    must not depend on it -- on the Cornell box (aligned by default) and on a 783-sphere scene (plain by default), both
+    integrators, and both must equal the oracle."""
+    p = tmp_path / "c4.scn"
+    rt.write_complex_scene(str(p), 4)
+    w, h = 72, 54
+    cam = cornell[1].copy(); rt.update_camera(cam, w, h)
+    scenes = [(cornell[0], cam, 6), (*rt.read_scene(str(p), w, h), 2)]
+    seeds = rt.reference_seeds(w, h, seed=33)
+    try:
+        for spheres, c, passes in scenes:
+            for integ in (0, 1):
+                col_o, sd_o, pix_o, _ = oracle_pt(orc, integ, spheres, c, w, h, seeds, passes)
+                for aligned in (1, 0, -1):
+                    gpu.set_tuning(rt.TUNE_PT_ALIGNED, aligned)
+                    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(c)
+                    out = gpu.pt_render(integ, passes)
+                    assert np.array_equal(out["seeds"].reshape(-1), sd_o), (spheres.size, integ, aligned)
+                    assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32)), (spheres.size, integ, aligned)
+                    assert np.array_equal(out["pixels"].reshape(-1), pix_o), (spheres.size, integ, aligned)
+    finally:
+        gpu.set_tuning(rt.TUNE_PT_ALIGNED, -1)
+    with pytest.raises(rt.RtError):
+        gpu.set_tuning(rt.TUNE_PT_ALIGNED, 5)
+
+
 def test_smallpt_progressive_calls_continue_the_sample_counter(gpu, orc, rt, cornell):
     """UpdateRenderingGPU semantics: repeated calls accumulate; scene/camera/resize reset currentSample."""
     spheres, cam = cornell
