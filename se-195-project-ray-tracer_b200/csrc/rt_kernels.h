@@ -29,9 +29,7 @@
 #ifndef W_MIN_BLOCKS
 #define W_MIN_BLOCKS 12
 #endif
-#ifndef W_PLANE_PAIRS
-#define W_PLANE_PAIRS 1
-#endif
+
 
 struct PtLaunch {
     rtb::PtFrame frame;
