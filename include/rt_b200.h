@@ -113,7 +113,9 @@ enum {
     RT_TUNE_PT_CHUNK_SPHERES = 1,       /* spheres per chunk in that mode */
     RT_TUNE_MAX_BLOCKS_PER_SM = 2,      /* cap on resident CTAs per SM (0 = as many as fit) */
     RT_TUNE_WHITTED_COST_ORDER = 3,     /* 1 (default): a pre-pass hands out expensive pixels first; 0: screen order.  Same image either way */
-    RT_TUNE_PT_ALIGNED = 4              /* path tracer: 1 = warps run the shading steps in lock-step, 0 = plain query loop, -1 (default) = by scene size.  Same image either way */
+    RT_TUNE_PT_ALIGNED = 4,             /* path tracer: 1 = warps run the shading steps in lock-step, 0 = plain query loop, -1 (default) = by scene size.  Same image either way */
+    RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
+                                           reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };
 int rt_set_tuning(rt_ctx *ctx, int key, int value);
 

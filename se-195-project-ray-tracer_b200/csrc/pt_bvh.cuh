@@ -1,0 +1,160 @@
+// pt_bvh.cuh -- exact culling for the sphere queries of the path tracer on large scenes (host/device).
+//
+// The reference tests every sphere against every ray (Intersect / IntersectP, SPT/geomfunc.h:71-110).  For the generated
+// many-sphere scenes (SPT/scene_build_complex.pl: 783 / 3 908 / 19 533 spheres) almost all of those tests are misses that a
+// bounding-volume hierarchy can rule out -- provided the hierarchy never rules out a test whose FLOAT result the
+// reference would have accepted.  This file is that hierarchy's traversal.  It changes which tests are executed, never
+// the arithmetic of a test (pt_bvh_sphere is SphereIntersect, operation for operation) nor the winner:
+//
+//   nearest query   result = the smallest non-zero d_i; among equal d_i the HIGHEST index (the reference scans
+//                   i = n-1 .. 0 with a strict '<', SPT/geomfunc.h:80-88).  Any visiting order gives that result with
+//                   the update rule "d < t, or d == t and i > id", as long as every sphere with d_i <= final t is visited.
+//   shadow query    result = "some d_i != 0 is < maxt" (SPT/geomfunc.h:102-109): order-free.
+//
+// Conservative node test.  u = 2^-24.  For a sphere (centre c, float rad2 = fl(rad*rad)) the reference computes
+//   op = fl(c - o), b = fl(op.d), det = fl(fl(fl(b*b) - fl(op.op)) + rad2), and returns 0 when det < 0.
+// With B = op.d, OO = op.op as real numbers and |d|^2 = 1 + eps, standard rounding bounds give
+//   |det - (B*B - OO + rad2)| <= 12u * OO * max(1, |d|^2) + u * rad2,      B*B - OO = eps*OO - (1+eps)*rho^2,
+// rho = distance from c to the line through o' = c - op (|o' - o| <= u*|op| per component) along d.  Hence det >= 0 needs
+//   rho^2 <= rad2 + eta,   eta = (|eps| + 13u)(1 + 2|eps|) * OO + (2|eps| + 2u) * rad2:
+// the line passes through the sphere inflated to R' = sqrt(rad2 + eta) <= rad + eta / (2*rad).  The accepted distance is
+// fl(b -+ sqrt(det)), which lies within (|eps| + 10u) * |op| of the parametric entry / exit of that inflated sphere.
+// A node stores the box of its spheres, hinv = 0.5 / (smallest radius below it); the scene stores eta0 >= (2|eps|+2u) *
+// (largest radius)^2 for |eps| <= 2^-18.  For a ray, D_k = the largest |box corner - o| per axis bounds |op_k|, so with
+//   K1 = 2*e + 34u  (e = |fl(d.d) - 1| >= |eps| - 4u: TWICE the bound above),   eta = K1 * (Dx^2+Dy^2+Dz^2) + eta0,
+//   m  = eta * hinv + 1e-6 * (1 + Dx+Dy+Dz)                      (the last term covers o' - o and the slab roundings)
+// every sphere below the node that could return d != 0 has its inflated sphere inside the box grown by m; the slab test
+// on the grown box yields [te, tx], and no accepted distance below the node is smaller than te - kT*(Dx+Dy+Dz) or larger
+// than tx + kT*(Dx+Dy+Dz), kT = 2*e + 40u.  A node is skipped only if the grown box is missed, lies behind the origin or
+// lies beyond the current limit by those margins; every comparison is written so that a NaN (0 * inf on a slab face)
+// means "visit".  A ray whose direction is not a unit vector to within 2^-18 (never produced by the tracer) gets
+// K1 = kT = inf: it visits everything.  Spheres that are much larger than the rest (the 10 000-unit floor) or not
+// finite are not in the tree at all: they form a short list that every query tests first.
+// tests/: the traversal against the plain loop on the lane simulator (CPU), and against the brute-force kernel on the
+// GPU at full size -- colours, RNG state and pixels bit-identical.
+#pragma once
+#include "pt_lane.cuh"
+
+namespace rtb {
+
+#define PT_BVH_STACK 64
+#define PT_BVH_LEAF_MAX 4
+#define PT_BVH_NONE 0x7fffffff
+#define PT_BVH_U 5.9604644775390625e-8f          /* 2^-24 */
+#define PT_BVH_MAX_EPS 3.814697265625e-6f        /* 2^-18 */
+
+// Inner node i = nodes[4i .. 4i+3]:
+//   [0] = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   [1] = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   [2] = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   [3] = (bits child0, bits child1, hinv0, hinv1)
+// child >= 0: inner node index; child < 0: leaf ~((first << 3) | (count - 1)) over geom[] / index[].
+struct PtBvh {
+    const f4 *nodes;
+    const f4 *geom;          // (p, rad^2) in leaf order; entries [0, n_big) are the always-tested spheres
+    const int *index;        // original sphere index of each entry
+    int n_big;
+    int root;                // child code of the root, PT_BVH_NONE when every sphere is in the always-tested list
+    float root_hinv;
+    float root_lo[3], root_hi[3];
+    float eta0;
+};
+
+RT_HD int pt_bvh_leaf_code(int first, int count) { return ~((first << 3) | (count - 1)); }
+
+// SphereIntersect (SPT/geomfunc.h:32-59) + the acceptance of Intersect / IntersectP, for ONE lane (no warp votes: the
+// traversal is per lane).  Same operations in the same order as pt_test.
+template <bool COUNT>
+RT_HD void pt_bvh_sphere(PtLane &L, const f4 g, int idx) {
+    if (COUNT) L.c_tests++;                      // tests actually executed (the reference's count is n per query)
+    const float opx = f_sub(g.x, L.ox), opy = f_sub(g.y, L.oy), opz = f_sub(g.z, L.oz);
+    const float b = dot3(opx, opy, opz, L.dx, L.dy, L.dz);
+    const float det = f_add(f_sub(f_mul(b, b), dot3(opx, opy, opz, opx, opy, opz)), g.w);
+    if (det < 0.f) return;
+    const float sq = f_sqrt(det);
+    const float t1 = f_sub(b, sq), t2 = f_add(b, sq);
+    const float t = t1 > PT_EPS ? t1 : t2;
+    if (!(t > PT_EPS)) return;
+    if (L.phase == PH_SHADOW) { if (t < L.cumu) L.hit = idx; }
+    else if (t < L.cumu || (t == L.cumu && idx > L.hit)) { L.cumu = t; L.hit = idx; }
+}
+
+struct PtBvhRay { float ix, iy, iz, K1, kT; };
+
+RT_HD PtBvhRay pt_bvh_ray(const PtLane &L) {
+    PtBvhRay R;
+    const float dd = dot3(L.dx, L.dy, L.dz, L.dx, L.dy, L.dz);
+    const float e = fabsf(f_sub(dd, 1.f));
+    if (e <= PT_BVH_MAX_EPS) { R.K1 = 2.f * e + 34.f * PT_BVH_U; R.kT = 2.f * e + 40.f * PT_BVH_U; }
+    else R.K1 = R.kT = INFINITY;                   // not a unit direction (or NaN): no culling
+    R.ix = 1.f / L.dx; R.iy = 1.f / L.dy; R.iz = 1.f / L.dz;
+    return R;
+}
+
+// Conservative "may some sphere below this box return an accepted distance" + the entry parameter for ordering.
+RT_HD bool pt_bvh_box(const PtLane &L, const PtBvhRay &R, float lox, float hix, float loy, float hiy, float loz, float hiz,
+                      float hinv, float eta0, float &lb_out) {
+    const float a0x = lox - L.ox, a1x = hix - L.ox, a0y = loy - L.oy, a1y = hiy - L.oy, a0z = loz - L.oz, a1z = hiz - L.oz;
+    const float Dx = fmaxf(fabsf(a0x), fabsf(a1x)), Dy = fmaxf(fabsf(a0y), fabsf(a1y)), Dz = fmaxf(fabsf(a0z), fabsf(a1z));
+    const float D1 = Dx + Dy + Dz;
+    const float D2 = Dx * Dx + Dy * Dy + Dz * Dz;
+    const float eta = R.K1 * D2 + eta0;
+    const float m = eta * hinv + 1e-6f * (1.f + D1);
+    const float t0x = (a0x - m) * R.ix, t1x = (a1x + m) * R.ix;
+    const float t0y = (a0y - m) * R.iy, t1y = (a1y + m) * R.iy;
+    const float t0z = (a0z - m) * R.iz, t1z = (a1z + m) * R.iz;
+    const float te = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    const float tx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    const float slack = R.kT * D1;
+    lb_out = te - slack;                   // no accepted distance below this box is smaller (NaN: compares false = keep)
+    const bool missed = (te - tx) > 1e-6f * (fabsf(te) + fabsf(tx));
+    const bool behind = (tx + slack) < 0.f;
+    const bool beyond = (te - slack) > L.cumu;
+    return !(missed | behind | beyond);
+}
+
+// One query of the lane (nearest or shadow, by L.phase) through the hierarchy.  Replaces pt_query_range.
+template <bool COUNT>
+RT_HD void pt_query_bvh(PtLane &L, const PtBvh &B) {
+    const bool shadow = L.phase == PH_SHADOW;
+    for (int j = 0; j < B.n_big; j++) {
+        pt_bvh_sphere<COUNT>(L, B.geom[j], B.index[j]);
+        if (shadow && L.hit >= 0) return;
+    }
+    if (B.root == PT_BVH_NONE) return;
+    const PtBvhRay R = pt_bvh_ray(L);
+    float lb;
+    if (!pt_bvh_box(L, R, B.root_lo[0], B.root_hi[0], B.root_lo[1], B.root_hi[1], B.root_lo[2], B.root_hi[2], B.root_hinv, B.eta0, lb)) return;
+    int stack[PT_BVH_STACK];
+    float stack_t[PT_BVH_STACK];          // te - slack of the pushed child: re-checked against the limit when it is popped
+    int sp = 0;
+    int node = B.root;
+    for (;;) {
+        if (node >= 0) {
+            const f4 n0 = B.nodes[4 * node], n1 = B.nodes[4 * node + 1], n2 = B.nodes[4 * node + 2], n3 = B.nodes[4 * node + 3];
+            float lb0, lb1;
+            const bool h0 = pt_bvh_box(L, R, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, n3.z, B.eta0, lb0);
+            const bool h1 = pt_bvh_box(L, R, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, n3.w, B.eta0, lb1);
+            const int c0 = (int)f_bits(n3.x), c1 = (int)f_bits(n3.y);
+            if (h0 & h1) {
+                const bool swap = lb1 < lb0;                 // nearer child first (any order is correct)
+                stack[sp] = swap ? c0 : c1;
+                stack_t[sp++] = swap ? lb0 : lb1;
+                node = swap ? c1 : c0;
+                continue;
+            }
+            if (h0 | h1) { node = h0 ? c0 : c1; continue; }
+        } else {
+            const int code = ~node;
+            const int first = code >> 3, count = (code & 7) + 1;
+            for (int j = 0; j < count; j++) pt_bvh_sphere<COUNT>(L, B.geom[first + j], B.index[first + j]);
+            if (shadow && L.hit >= 0) return;
+        }
+        for (;;) {                                           // pop; a child that is now beyond the limit is dropped
+            if (sp == 0) return;
+            --sp;
+            if (!(stack_t[sp] > L.cumu)) break;
+        }
+        node = stack[sp];
+    }
+}
+
+}  // namespace rtb

@@ -10,6 +10,7 @@
 #include <stdarg.h>
 #include "../../include/rt_b200.h"
 #include "scene_soa.h"
+#include "pt_bvh_build.h"
 #include "rt_kernels.h"
 
 using namespace rtb;
@@ -32,6 +33,7 @@ struct rt_ctx {
     int max_blocks_per_sm = 0;
     int whitted_sort = 1;                          // cost-sorted work order (scheduling pre-pass)
     int pt_aligned = -1;                           // step-aligned path-tracer warps: -1 by scene size, 0 off, 1 on
+    int pt_bvh = -1;                               // exact hierarchy for the sphere queries: -1 by scene size, 0 off, 1 on
     uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
     unsigned *d_wclass = nullptr;
@@ -63,6 +65,10 @@ struct rt_ctx {
     uint32_t *d_seeds = nullptr, *d_ppixels = nullptr;
     f4 *d_pgeom = nullptr, *d_pemis = nullptr, *d_pcolr = nullptr;
     int *d_plights = nullptr;
+    PtBvhHost p_bvh;                               // hierarchy over the current scene (csrc/pt_bvh_build.h); built on first use
+    bool p_bvh_ready = false;
+    f4 *d_bnodes = nullptr, *d_bgeom = nullptr; int *d_bindex = nullptr;
+    size_t cap_bnodes = 0, cap_bgeom = 0, cap_bindex = 0;
     rt_camera cam;
     bool have_cam = false, have_scene = false, have_size = false;
     int current_sample = 0, sum_mode = 0;
@@ -144,7 +150,7 @@ void rt_destroy(rt_ctx *ctx) {
     if (ctx->peer_ppixels) cudaIpcCloseMemHandle(ctx->peer_ppixels);
     void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
-                     ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights };
+                     ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex };
     for (void *b : bufs) if (b) cudaFree(b);
     void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter };
     for (void *b : rbufs) if (b) cudaFree(b);
@@ -196,6 +202,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_MAX_BLOCKS_PER_SM: if (value < 0) break; ctx->max_blocks_per_sm = value; return RT_OK;
         case RT_TUNE_WHITTED_COST_ORDER: ctx->whitted_sort = value ? 1 : 0; return RT_OK;
         case RT_TUNE_PT_ALIGNED: if (value < -1 || value > 1) break; ctx->pt_aligned = value; return RT_OK;
+        case RT_TUNE_PT_BVH: if (value < -1 || value > 1) break; ctx->pt_bvh = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -421,6 +428,7 @@ int rt_pt_set_scene(rt_ctx *ctx, const rt_sphere *spheres, uint32_t n) {
     CK(upload_vec(&ctx->d_plights, &ctx->cap_plights, soa.lights, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->p_n = (int)n; ctx->p_nl = (int)soa.lights.size(); ctx->have_scene = true; ctx->current_sample = 0;
+    ctx->p_bvh_ready = false;
     return RT_OK;
 }
 
@@ -465,6 +473,18 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
     p.chunk_spheres = ctx->pt_chunk_spheres;
     p.max_blocks_per_sm = ctx->max_blocks_per_sm;
     p.aligned = ctx->pt_aligned;
+    p.use_bvh = !ctx->counting && (ctx->pt_bvh > 0 || (ctx->pt_bvh < 0 && ctx->p_n >= PT_BVH_MIN_SPHERES));
+    if (p.use_bvh) {
+        if (!ctx->p_bvh_ready) {           // built from the scene tables of the last rt_pt_set_scene, once
+            build_pt_bvh(ctx->p_soa.geom, ctx->p_soa.colr, ctx->p_bvh);
+            CK(upload_vec(&ctx->d_bnodes, &ctx->cap_bnodes, ctx->p_bvh.nodes, ctx->stream));
+            CK(upload_vec(&ctx->d_bgeom, &ctx->cap_bgeom, ctx->p_bvh.geom, ctx->stream));
+            CK(upload_vec(&ctx->d_bindex, &ctx->cap_bindex, ctx->p_bvh.index, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->p_bvh_ready = true;
+        }
+        p.bvh = ctx->p_bvh.view(ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex);
+    }
     CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches++; }

@@ -132,6 +132,41 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
     }
 }
 
+// smallpt on a large scene: the same lane state machine, but every lane walks the exact hierarchy of pt_bvh.cuh instead
+// of all spheres (19 533 spheres: ~4 sphere tests per query instead of 19 533; same colours, RNG state and pixels).  The
+// traversal is per lane (its own stack in local memory, nodes and spheres read through L1 / L2), so the warp is only
+// synchronised around the refill; the reference-order loop of pt_kernel remains the path of small scenes, where the
+// whole array sits in shared memory and a test costs less than a node visit, and of counting launches.
+__global__ void __launch_bounds__(PT_THREADS, PT_BVH_MIN_BLOCKS)
+pt_bvh_kernel(PtFrame F, PtBvh B, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, uint32_t *pixels, unsigned *work_counter) {
+    const uint32_t lane = threadIdx.x & 31u;
+    PtLane L;
+    L.phase = PH_IDLE;
+    L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_tests = 0;
+    bool exhausted = false;
+    for (;;) {
+        const bool need = (L.phase == PH_IDLE) && !exhausted;
+        const uint32_t item = fetch_items(work_counter, need, lane);
+        if (need) {
+            if (item < n_items) {
+                int x, y;
+                if (item_to_pixel(S, F.w, item, x, y)) pt_begin_pixel(L, F, x, y, colors, seeds);
+            } else exhausted = true;
+        }
+        const bool active = L.phase != PH_IDLE;
+        if (!__any_sync(FULL_MASK, active || !exhausted)) break;
+        if (active) {
+            pt_query_bvh<false>(L, B);
+            if (pt_advance<false>(L, F)) {
+                const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
+                colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
+                seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
+                if (!F.sum_mode) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
+            }
+        }
+    }
+}
+
 // Sample-sharded mode: colors hold sums; divide and write the 8-bit pixels.
 __global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, int h, float inv_total) {
     const size_t n = (size_t)w * h;
@@ -357,6 +392,16 @@ static int blocks_per_sm(K kernel, int threads, size_t smem) {
 }
 
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
+    if (p.use_bvh && !p.count) {
+        int nb = blocks_per_sm(pt_bvh_kernel, PT_THREADS, 0);
+        if (nb < 1) return cudaErrorLaunchOutOfResources;
+        if (p.max_blocks_per_sm > 0 && nb > p.max_blocks_per_sm) nb = p.max_blocks_per_sm;
+        long grid = (long)nb * p.sm_count;
+        const long need = ((long)p.n_items + PT_THREADS - 1) / PT_THREADS;
+        if (grid > need) grid = need > 0 ? need : 1;
+        pt_bvh_kernel<<<(unsigned)grid, PT_THREADS, 0, stream>>>(p.frame, p.bvh, p.shard, p.n_items, p.colors, p.seeds, p.pixels, p.work_counter);
+        return cudaGetLastError();
+    }
     const size_t geom_bytes = (size_t)p.frame.n * sizeof(f4);
     const bool chunked = geom_bytes > (size_t)p.max_smem_geom;
     int chunk = p.frame.n;

@@ -5,6 +5,7 @@
 #include "pt_lane.cuh"
 #include "whitted_lane.cuh"
 #include "r306_lane.cuh"
+#include "pt_bvh.cuh"
 
 // Launch shape (overridable with -D for the A/B builds of tools/variants.sh).
 // smallpt: 128-thread CTAs capped at 64 registers (8 CTAs = 32 warps per SM) measured 6 % faster on Cornell than
@@ -22,6 +23,14 @@
 // Scenes of up to this many spheres run the step-aligned path tracer (see pt_kernel); larger ones are loop-bound.
 #ifndef PT_ALIGNED_MAX_SPHERES
 #define PT_ALIGNED_MAX_SPHERES 64
+#endif
+// Large scenes (pt_bvh_kernel): per-lane traversal; the register cap that measured best (profiles/).
+#ifndef PT_BVH_MIN_BLOCKS
+#define PT_BVH_MIN_BLOCKS 6
+#endif
+// Scenes with at least this many spheres walk the hierarchy (RT_TUNE_PT_BVH = -1).
+#ifndef PT_BVH_MIN_SPHERES
+#define PT_BVH_MIN_SPHERES 128
 #endif
 #ifndef W_THREADS
 #define W_THREADS 64
@@ -43,6 +52,8 @@ struct PtLaunch {
     int chunk_spheres;          // spheres per chunk in that case
     int max_blocks_per_sm;      // 0 = whatever fits
     int aligned;                // -1: by scene size, 0: plain query loop, 1: step-aligned warps
+    int use_bvh;                // 1: walk the hierarchy `bvh` (device pointers) instead of every sphere; ignored by counting launches
+    rtb::PtBvh bvh;
 };
 
 struct WLaunch {

@@ -11,6 +11,7 @@
 #include <string.h>
 #include "../../se-195-project-ray-tracer_b200/csrc/scene_soa.h"
 #include "../../se-195-project-ray-tracer_b200/csrc/r306_lane.cuh"
+#include "../../se-195-project-ray-tracer_b200/csrc/pt_bvh_build.h"
 
 using namespace rtb;
 
@@ -114,7 +115,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
 // smallpt passes through the lane state machine.  colors/seeds updated in place (CPU-twin indexing).
 void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera *cam, int w, int h,
                int pass0, int n_passes, int sum_mode, float *colors, uint32_t *seeds, uint32_t *pixels,
-               int rank, int world, int tile_rows, uint64_t *counters5, int chunk /* <=0: plain per-sphere loop */) {
+               int rank, int world, int tile_rows, uint64_t *counters5, int chunk /* -2: hierarchy (pt_bvh.cuh); <=0: plain per-sphere loop */) {
     PtSoA soa;
     build_pt_soa(sph, n, soa);
     PtFrame F;
@@ -129,6 +130,9 @@ void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera
     uint32_t n_items;
     Shard S = make_shard(w, h, rank, world, tile_rows, &n_items);
     uint64_t c[5] = {0, 0, 0, 0, 0};
+    PtBvhHost bh;
+    if (chunk == -2) build_pt_bvh(soa.geom, soa.colr, bh);
+    const PtBvh B = bh.view(bh.nodes.data(), bh.geom.data(), bh.index.data());
     for (uint32_t it = 0; it < n_items; it++) {
         int x, y;
         if (!item_to_pixel(S, w, it, x, y)) continue;
@@ -136,12 +140,19 @@ void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera
         memset(&L, 0, sizeof L);
         pt_begin_pixel(L, F, x, y, colors, seeds);
         for (;;) {
-            if (chunk <= 0) for (int i = F.n - 1; i >= 0; --i) pt_test<true>(L, soa.geom[i], i, true);   // plain loop
+            if (chunk == -2) pt_query_bvh<true>(L, B);                                                         // the hierarchy of pt_bvh.cuh
+            else if (chunk <= 0) for (int i = F.n - 1; i >= 0; --i) pt_test<true>(L, soa.geom[i], i, true);   // plain loop
             else for (int hi = F.n; hi > 0; hi -= chunk) {                                               // the kernel's loops
                 const int lo = hi > chunk ? hi - chunk : 0;
                 pt_query_range<true>(L, soa.geom.data() + lo, lo, hi, true);
             }
-            if (pt_advance<true>(L, F)) break;
+            if (chunk == -2) {      // counters[2] = sphere tests actually executed (pt_advance would add the reference's n per query)
+                const uint64_t executed = L.c_tests;
+                const bool done = pt_advance<true>(L, F);
+                L.c_tests = executed;
+                if (done) break;
+            }
+            else if (pt_advance<true>(L, F)) break;
         }
         const size_t i = (size_t)(h - y - 1) * w + x;
         colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
@@ -150,6 +161,20 @@ void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera
         c[0] += L.c_nearest; c[1] += L.c_shadow; c[2] += L.c_tests; c[4] += L.c_samples;
     }
     if (counters5) for (int k = 0; k < 5; k++) counters5[k] += c[k];
+}
+
+// Shape of the hierarchy build_pt_bvh makes for a scene: out5 = (inner nodes, entries, always-tested spheres, depth, leaves).
+void devsim_bvh_stats(const rt_sphere *sph, uint32_t n, int32_t *out5) {
+    PtSoA soa;
+    build_pt_soa(sph, n, soa);
+    PtBvhHost bh;
+    build_pt_bvh(soa.geom, soa.colr, bh);
+    out5[0] = bh.root == PT_BVH_NONE ? 0 : (int)bh.nodes.size() / 4; out5[1] = (int)bh.geom.size(); out5[2] = bh.n_big; out5[3] = bh.depth;
+    int leaves = 0;
+    if (bh.root != PT_BVH_NONE && bh.root < 0) leaves = 1;
+    if (bh.root != PT_BVH_NONE && bh.root >= 0)
+        for (size_t i = 0; i < bh.nodes.size() / 4; i++) { int a, b; memcpy(&a, &bh.nodes[4 * i + 3].x, 4); memcpy(&b, &bh.nodes[4 * i + 3].y, 4); leaves += (a < 0) + (b < 0); }
+    out5[4] = leaves;
 }
 
 }  // extern "C"

@@ -386,6 +386,80 @@ def test_smallpt_chunked_staging_equals_resident(gpu, orc, rt, tmp_path):
         gpu.set_tuning(rt.TUNE_PT_CHUNK_SPHERES, 3072)
 
 
+@pytest.mark.parametrize("depth,w,h,passes", [(4, 640, 360, 4), (5, 480, 270, 2), (6, 320, 180, 2)])
+def test_smallpt_exact_hierarchy_equals_the_loop_over_every_sphere(gpu, orc, rt, tmp_path, depth, w, h, passes):
+    """Large scenes walk an exact bounding-volume hierarchy (csrc/pt_bvh.cuh) instead of every sphere: colours, RNG state
+    and pixels must be bit-identical to the reference-order loop (RT_TUNE_PT_BVH 0), both integrators, 783 / 3 908 /
+    19 533 spheres -- and to the oracle where it finishes in seconds."""
+    p = tmp_path / f"c{depth}.scn"
+    rt.write_complex_scene(str(p), depth)
+    spheres, cam = rt.read_scene(str(p), w, h)
+    seeds = rt.reference_seeds(w, h, seed=depth)
+    try:
+        for integ in (0, 1):
+            outs = []
+            for bvh in (1, 0):
+                gpu.set_tuning(rt.TUNE_PT_BVH, bvh)
+                gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+                outs.append(gpu.pt_render(integ, passes))
+            for k in ("seeds", "colors", "pixels"):
+                assert np.array_equal(outs[0][k].reshape(-1).view(np.uint32), outs[1][k].reshape(-1).view(np.uint32)), (depth, integ, k)
+        if depth == 4:
+            sw, sh = 96, 72
+            sph2, cam2 = rt.read_scene(str(p), sw, sh)
+            sd = rt.reference_seeds(sw, sh, seed=9)
+            col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, sph2, cam2, sw, sh, sd, 2)
+            gpu.set_tuning(rt.TUNE_PT_BVH, 1)
+            gpu.pt_resize(sw, sh, sd); gpu.pt_set_scene(sph2); gpu.pt_set_camera(cam2)
+            out = gpu.pt_render(0, 2)
+            assert np.array_equal(out["seeds"], sd_o) and np.array_equal(out["pixels"].reshape(-1), pix_o)
+            assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32))
+    finally:
+        gpu.set_tuning(rt.TUNE_PT_BVH, -1)
+
+
+def test_smallpt_exact_hierarchy_tie_rule_and_mixed_scenes(gpu, rt, tmp_path):
+    """Duplicated spheres (exact ties: the higher index wins), mirrors / glass among them, a zero-radius sphere, random
+    clouds with huge spheres and several lights, a camera inside the cloud: hierarchy == loop, bit for bit."""
+    p = tmp_path / "c3.scn"
+    rt.write_complex_scene(str(p), 3)
+    w, h = 160, 120
+    sph, cam = rt.read_scene(str(p), w, h)
+    rs = np.random.RandomState(7)
+    extra = sph[2:].copy(); rs.shuffle(extra)
+    dup = extra[:60].copy(); dup["c"] = (0.9, 0.1, 0.1)
+    scene = np.concatenate([sph, dup, dup[:20]])
+    scene["refl"][10:40:3] = 1; scene["refl"][11:40:3] = 2
+    scene["rad"][50] = 0.0
+    scene["p"][60] = scene["p"][61]
+    scene = scene[np.concatenate([[0, 1], 2 + rs.permutation(scene.size - 2)])].copy()
+    cases = [(scene, cam)]
+    c2 = cam.copy(); c2["orig"] = (3.0, 21.0, 4.0); rt.update_camera(c2, w, h)
+    cases.append((scene, c2))
+    for n in (37, 300, 2000):
+        _, ccam = rt.cornell_scene(w, h)
+        cl = np.zeros(n, sph.dtype)
+        cl["p"] = np.stack([rs.uniform(0, 100, n), rs.uniform(0, 80, n), rs.uniform(0, 150, n)], 1)
+        cl["rad"] = np.exp(rs.uniform(np.log(0.05), np.log(9.0), n))
+        cl["c"] = rs.uniform(0.2, 0.9, (n, 3)); cl["refl"] = rs.randint(0, 3, n)
+        cl["e"][rs.choice(n, max(1, n // 40), replace=False)] = 12
+        cl["rad"][:2] = (600.0, 5000.0); cl["p"][1, 1] = -5000.0
+        cases.append((cl, ccam))
+    try:
+        for k, (sc, cm) in enumerate(cases):
+            seeds = rt.reference_seeds(w, h, seed=20 + k)
+            for integ in (0, 1):
+                outs = []
+                for bvh in (1, 0):
+                    gpu.set_tuning(rt.TUNE_PT_BVH, bvh)
+                    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(sc); gpu.pt_set_camera(cm)
+                    outs.append(gpu.pt_render(integ, 3))
+                for key in ("seeds", "colors", "pixels"):
+                    assert np.array_equal(outs[0][key].reshape(-1).view(np.uint32), outs[1][key].reshape(-1).view(np.uint32)), (k, integ, key)
+    finally:
+        gpu.set_tuning(rt.TUNE_PT_BVH, -1)
+
+
 def test_smallpt_row_tile_sharding_is_bit_identical(gpu, rt, cornell):
     spheres, cam = cornell
     w, h = 100, 75

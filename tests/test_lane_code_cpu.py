@@ -136,3 +136,82 @@ def test_r306_lanes_equal_the_reference_frame(devsim, rt):
             devsim.devsim_r306(vp(a), 80, 131, vp(v), v.size)
             L.ref_r306_render_scene(vp(b), 80, 131, vp(v), v.size)
             assert np.array_equal(a, b), k
+
+
+def _devsim_pt(devsim, integ, sph, cam, w, h, passes, seeds, mode):
+    col, sd, pix = np.zeros(3 * w * h, np.float32), seeds.copy(), np.zeros(w * h, np.uint32)
+    devsim.devsim_pt(integ, vp(sph), sph.size, vp(cam), w, h, 0, passes, 0, vp(col), vp(sd), vp(pix), 0, 1, 8, None, mode)
+    return col.view(np.uint32), sd, pix
+
+
+def _complex_scene(rt, tmp_path, depth, w, h):
+    path = str(tmp_path / f"complex{depth}.scn")
+    rt.write_complex_scene(path, depth)
+    return rt.read_scene(path, w, h)
+
+
+@pytest.mark.parametrize("depth,w,h,passes", [(2, 64, 48, 3), (3, 48, 36, 2), (4, 40, 30, 2)])
+def test_bvh_traversal_equals_the_plain_sphere_loop_on_generated_scenes(devsim, rt, tmp_path, depth, w, h, passes):
+    """pt_query_bvh (exact culling, csrc/pt_bvh.cuh) against the reference-order loop over every sphere: colours, RNG state
+    and pixels bit-identical, both integrators.  The plain loop itself equals the reference (fixtures above)."""
+    sph, cam = _complex_scene(rt, tmp_path, depth, w, h)
+    seeds = rt.reference_seeds(w, h)
+    st = np.zeros(5, np.int32)
+    devsim.devsim_bvh_stats(vp(sph), sph.size, vp(st))
+    assert st[1] == sph.size and st[2] >= 1 and st[0] >= 1          # every sphere once; the floor is in the always-tested list
+    for integ in (0, 1):
+        a = _devsim_pt(devsim, integ, sph, cam, w, h, passes, seeds, -2)
+        b = _devsim_pt(devsim, integ, sph, cam, w, h, passes, seeds, 0)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), (depth, integ)
+
+
+def test_bvh_traversal_keeps_the_reference_tie_rule_and_odd_spheres(devsim, rt, tmp_path):
+    """Exact ties (duplicated spheres: the HIGHER index must win, SPT/geomfunc.h:80-88), mirrors and glass among the
+    small spheres, a zero-radius sphere, touching and nested spheres, a camera inside the cloud."""
+    sph, cam = _complex_scene(rt, tmp_path, 3, 40, 30)
+    rs = np.random.RandomState(7)
+    extra = sph[2:].copy()
+    rs.shuffle(extra)
+    dup = extra[:60].copy()                                   # exact copies at other indices, other colours
+    dup["c"] = (0.9, 0.1, 0.1)
+    scene = np.concatenate([sph, dup, dup[:20]])
+    scene["refl"][10:40:3] = 1
+    scene["refl"][11:40:3] = 2
+    scene["rad"][50] = 0.0
+    scene["p"][60] = scene["p"][61]
+    perm = np.concatenate([[0, 1], 2 + rs.permutation(scene.size - 2)])
+    scene = scene[perm].copy()
+    for cam_pos in (None, (3.0, 21.0, 4.0)):
+        c = cam.copy()
+        if cam_pos:
+            c["orig"] = cam_pos
+            rt.update_camera(c, 40, 30)
+        seeds = rt.reference_seeds(40, 30, seed=3)
+        for integ in (0, 1):
+            a = _devsim_pt(devsim, integ, scene, c, 40, 30, 3, seeds, -2)
+            b = _devsim_pt(devsim, integ, scene, c, 40, 30, 3, seeds, 0)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (cam_pos, integ)
+
+
+def test_bvh_traversal_on_random_clouds(devsim, rt):
+    """Random sphere clouds of mixed sizes (no floor, several lights, a few huge spheres), rays that leave the scene."""
+    rs = np.random.RandomState(11)
+    for n in (5, 37, 300):
+        sph, cam = rt.cornell_scene(32, 24)
+        scene = np.zeros(n, sph.dtype)
+        scene["p"] = np.stack([rs.uniform(0, 100, n), rs.uniform(0, 80, n), rs.uniform(0, 150, n)], 1)
+        scene["rad"] = np.exp(rs.uniform(np.log(0.05), np.log(9.0), n))
+        scene["c"] = rs.uniform(0.2, 0.9, (n, 3))
+        scene["refl"] = rs.randint(0, 3, n)
+        lights = rs.choice(n, max(1, n // 40), replace=False)
+        scene["e"][lights] = 12
+        if n > 30:
+            scene["rad"][:2] = (600.0, 5000.0); scene["p"][1, 1] = -5000.0
+        seeds = rt.reference_seeds(32, 24, seed=n)
+        for integ in (0, 1):
+            a = _devsim_pt(devsim, integ, scene, cam, 32, 24, 4, seeds, -2)
+            b = _devsim_pt(devsim, integ, scene, cam, 32, 24, 4, seeds, 0)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (n, integ)

@@ -17,16 +17,25 @@ def pt_case(tag, spheres, cam, w, h, spp, integ=0):
     r.pt_resize(w, h, seeds); r.pt_set_scene(spheres); r.pt_set_camera(cam)
     r.set_counting(True); r.pt_launch(integ, 1); c = r.counters(); r.set_counting(False)
     per = {k: v / max(c["samples"], 1) for k, v in c.items()}
-    best = 1e30
-    for _ in range(2):
-        r.pt_resize(w, h, seeds); r.pt_set_camera(cam)
-        r.timer_begin(); r.pt_launch(integ, spp); best = min(best, r.timer_end())
     samples = w * h * spp
     # counters of pass 0 only: later passes have the same statistics (independent seeds)
     flop = 17.0 * per["sphere_tests"] * samples
-    print(f"{tag}: {spheres.size} spheres {w}x{h}x{spp}spp  {best:.1f} ms  {samples / best / 1e3:.1f} Msamples/s  "
-          f"{samples * (per['nearest_queries'] + per['shadow_queries']) / best / 1e3:.0f} Mrays/s  "
-          f"{per['sphere_tests']:.0f} tests/sample  {flop / best / 1e9:.2f} TFLOP/s algorithmic = {100 * flop / (best * 1e-3) / peak:.1f}% of FP32 peak", flush=True)
+    for mode, name in ((0, "loop over every sphere"), (1, "exact hierarchy")):
+        if mode == 1 and spheres.size < 64:
+            continue
+        r.set_tuning(rt.TUNE_PT_BVH, mode)
+        best = 1e30
+        for _ in range(2):
+            r.pt_resize(w, h, seeds); r.pt_set_camera(cam)
+            r.timer_begin(); r.pt_launch(integ, spp); best = min(best, r.timer_end())
+        line = (f"{tag} [{name}]: {spheres.size} spheres {w}x{h}x{spp}spp  {best:.1f} ms  {samples / best / 1e3:.1f} Msamples/s  "
+                f"{samples * (per['nearest_queries'] + per['shadow_queries']) / best / 1e3:.0f} Mrays/s  {per['sphere_tests']:.0f} reference tests/sample")
+        if mode == 0:
+            line += f"  {flop / best / 1e9:.2f} TFLOP/s algorithmic = {100 * flop / (best * 1e-3) / peak:.1f}% of FP32 peak"
+        else:
+            line += f"  (reference-equivalent {flop / best / 1e9:.1f} TFLOP/s: the tests are culled, not executed)"
+        print(line, flush=True)
+    r.set_tuning(rt.TUNE_PT_BVH, -1)
 
 
 with tempfile.TemporaryDirectory() as d:
