@@ -38,7 +38,9 @@
 namespace rtb {
 
 #define PT_BVH_STACK 64
-#define PT_BVH_LEAF_MAX 4
+#ifndef PT_BVH_LEAF_MAX
+#define PT_BVH_LEAF_MAX 8                        /* 8 against 4: 24 ms against 29 ms on the 19 533-sphere scene at 4K (a shallower tree), equal on the smaller ones */
+#endif
 #define PT_BVH_NONE 0x7fffffff
 #define PT_BVH_U 5.9604644775390625e-8f          /* 2^-24 */
 #define PT_BVH_MAX_EPS 3.814697265625e-6f        /* 2^-18 */
@@ -79,13 +81,23 @@ RT_HD void pt_bvh_sphere(PtLane &L, const f4 g, int idx) {
 
 struct PtBvhRay { float ix, iy, iz, K1, kT; };
 
+// 1/x for the slab test: two units in the last place are enough (the slacks above allow for it), so the device uses
+// the fast reciprocal; a denormal component flushes to "parallel to the slab" like a zero one.
+RT_HD float bvh_rcp(float x) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(1.f, x);
+#else
+    return 1.f / x;
+#endif
+}
+
 RT_HD PtBvhRay pt_bvh_ray(const PtLane &L) {
     PtBvhRay R;
     const float dd = dot3(L.dx, L.dy, L.dz, L.dx, L.dy, L.dz);
     const float e = fabsf(f_sub(dd, 1.f));
     if (e <= PT_BVH_MAX_EPS) { R.K1 = 2.f * e + 34.f * PT_BVH_U; R.kT = 2.f * e + 40.f * PT_BVH_U; }
     else R.K1 = R.kT = INFINITY;                   // not a unit direction (or NaN): no culling
-    R.ix = 1.f / L.dx; R.iy = 1.f / L.dy; R.iz = 1.f / L.dz;
+    R.ix = bvh_rcp(L.dx); R.iy = bvh_rcp(L.dy); R.iz = bvh_rcp(L.dz);
     return R;
 }
 
@@ -111,49 +123,90 @@ RT_HD bool pt_bvh_box(const PtLane &L, const PtBvhRay &R, float lox, float hix, 
     return !(missed | behind | beyond);
 }
 
-// One query of the lane (nearest or shadow, by L.phase) through the hierarchy.  Replaces pt_query_range.
+// A query in flight: the ray's constants, the node to visit next and the stack depth.  The stacks themselves are two
+// caller-owned arrays of PT_BVH_STACK entries (local memory on the device).
+#define PT_BVH_DONE 0x7ffffffe
+struct PtTrav { PtBvhRay R; int node, sp; };
+
+// Starts the lane's query (nearest or shadow, by L.phase): the always-tested spheres, then the root box.
 template <bool COUNT>
-RT_HD void pt_query_bvh(PtLane &L, const PtBvh &B) {
+RT_HD void pt_bvh_begin(PtLane &L, const PtBvh &B, PtTrav &T) {
+    T.node = PT_BVH_DONE; T.sp = 0;
     const bool shadow = L.phase == PH_SHADOW;
     for (int j = 0; j < B.n_big; j++) {
         pt_bvh_sphere<COUNT>(L, B.geom[j], B.index[j]);
         if (shadow && L.hit >= 0) return;
     }
     if (B.root == PT_BVH_NONE) return;
-    const PtBvhRay R = pt_bvh_ray(L);
+    T.R = pt_bvh_ray(L);
     float lb;
-    if (!pt_bvh_box(L, R, B.root_lo[0], B.root_hi[0], B.root_lo[1], B.root_hi[1], B.root_lo[2], B.root_hi[2], B.root_hinv, B.eta0, lb)) return;
-    int stack[PT_BVH_STACK];
-    float stack_t[PT_BVH_STACK];          // te - slack of the pushed child: re-checked against the limit when it is popped
-    int sp = 0;
-    int node = B.root;
+    if (pt_bvh_box(L, T.R, B.root_lo[0], B.root_hi[0], B.root_lo[1], B.root_hi[1], B.root_lo[2], B.root_hi[2], B.root_hinv, B.eta0, lb)) T.node = B.root;
+}
+
+#ifdef PT_BVH_STATS          /* test-only visit counters of the host build (tests/devsim) */
+static long g_bvh_inner_visits = 0, g_bvh_leaf_visits = 0, g_bvh_hist[64] = {0};
+#define PT_BVH_STAT(x) ((x)++)
+#else
+#define PT_BVH_STAT(x) ((void)0)
+#endif
+RT_HD bool pt_bvh_at_inner(const PtTrav &T) { return (unsigned)T.node < (unsigned)PT_BVH_DONE; }
+RT_HD bool pt_bvh_at_leaf(const PtTrav &T) { return T.node < 0; }
+
+// Next node from the stack; a pushed child that is now beyond the limit is dropped.
+RT_HD void pt_bvh_pop(const PtLane &L, PtTrav &T, const int *stack, const float *stack_t) {
     for (;;) {
-        if (node >= 0) {
-            const f4 n0 = B.nodes[4 * node], n1 = B.nodes[4 * node + 1], n2 = B.nodes[4 * node + 2], n3 = B.nodes[4 * node + 3];
-            float lb0, lb1;
-            const bool h0 = pt_bvh_box(L, R, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, n3.z, B.eta0, lb0);
-            const bool h1 = pt_bvh_box(L, R, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, n3.w, B.eta0, lb1);
-            const int c0 = (int)f_bits(n3.x), c1 = (int)f_bits(n3.y);
-            if (h0 & h1) {
-                const bool swap = lb1 < lb0;                 // nearer child first (any order is correct)
-                stack[sp] = swap ? c0 : c1;
-                stack_t[sp++] = swap ? lb0 : lb1;
-                node = swap ? c1 : c0;
-                continue;
-            }
-            if (h0 | h1) { node = h0 ? c0 : c1; continue; }
-        } else {
-            const int code = ~node;
-            const int first = code >> 3, count = (code & 7) + 1;
-            for (int j = 0; j < count; j++) pt_bvh_sphere<COUNT>(L, B.geom[first + j], B.index[first + j]);
-            if (shadow && L.hit >= 0) return;
-        }
-        for (;;) {                                           // pop; a child that is now beyond the limit is dropped
-            if (sp == 0) return;
-            --sp;
-            if (!(stack_t[sp] > L.cumu)) break;
-        }
-        node = stack[sp];
+        if (T.sp == 0) { T.node = PT_BVH_DONE; return; }
+        --T.sp;
+        if (!(stack_t[T.sp] > L.cumu)) break;
+    }
+    T.node = stack[T.sp];
+}
+
+// One inner node: two box tests, descend into the nearer child that may matter, push the other.
+RT_HD void pt_bvh_inner(const PtLane &L, const PtBvh &B, PtTrav &T, int *stack, float *stack_t) {
+    PT_BVH_STAT(g_bvh_inner_visits);
+    const int node = T.node;
+    const f4 n0 = B.nodes[4 * node], n1 = B.nodes[4 * node + 1], n2 = B.nodes[4 * node + 2], n3 = B.nodes[4 * node + 3];
+    float lb0, lb1;
+    const bool h0 = pt_bvh_box(L, T.R, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, n3.z, B.eta0, lb0);
+    const bool h1 = pt_bvh_box(L, T.R, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, n3.w, B.eta0, lb1);
+    const int c0 = (int)f_bits(n3.x), c1 = (int)f_bits(n3.y);
+    if (h0 & h1) {
+        const bool swap = lb1 < lb0;                     // nearer child first (any order is correct)
+        stack[T.sp] = swap ? c0 : c1;
+        stack_t[T.sp++] = swap ? lb0 : lb1;
+        T.node = swap ? c1 : c0;
+    } else if (h0 | h1) T.node = h0 ? c0 : c1;
+    else pt_bvh_pop(L, T, stack, stack_t);
+}
+
+// One leaf: its spheres (exact tests), then the next node from the stack.
+template <bool COUNT>
+RT_HD void pt_bvh_leaf(PtLane &L, const PtBvh &B, PtTrav &T, const int *stack, const float *stack_t) {
+    PT_BVH_STAT(g_bvh_leaf_visits);
+    const int code = ~T.node;
+    const int first = code >> 3, count = (code & 7) + 1;
+#pragma unroll
+    for (int j = 0; j < PT_BVH_LEAF_MAX; j++)
+        if (j < count) pt_bvh_sphere<COUNT>(L, B.geom[first + j], B.index[first + j]);
+    if (L.phase == PH_SHADOW && L.hit >= 0) { T.node = PT_BVH_DONE; return; }
+    pt_bvh_pop(L, T, stack, stack_t);
+}
+
+// One whole query of one lane.  Replaces pt_query_range (tests/devsim; the kernel interleaves the steps of 32 lanes).
+template <bool COUNT>
+RT_HD void pt_query_bvh(PtLane &L, const PtBvh &B) {
+    int stack[PT_BVH_STACK];
+    float stack_t[PT_BVH_STACK];
+    PtTrav T;
+    pt_bvh_begin<COUNT>(L, B, T);
+#ifdef PT_BVH_STATS
+    const long v0 = g_bvh_inner_visits;
+    struct Tally { long v0; ~Tally() { long n = g_bvh_inner_visits - v0; g_bvh_hist[n > 63 ? 63 : n]++; } } tally{v0};
+#endif
+    while (T.node != PT_BVH_DONE) {
+        if (pt_bvh_at_inner(T)) pt_bvh_inner(L, B, T, stack, stack_t);
+        else pt_bvh_leaf<COUNT>(L, B, T, stack, stack_t);
     }
 }
 

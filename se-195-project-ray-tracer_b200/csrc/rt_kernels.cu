@@ -132,37 +132,62 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
     }
 }
 
-// smallpt on a large scene: the same lane state machine, but every lane walks the exact hierarchy of pt_bvh.cuh instead
-// of all spheres (19 533 spheres: ~4 sphere tests per query instead of 19 533; same colours, RNG state and pixels).  The
-// traversal is per lane (its own stack in local memory, nodes and spheres read through L1 / L2), so the warp is only
-// synchronised around the refill; the reference-order loop of pt_kernel remains the path of small scenes, where the
-// whole array sits in shared memory and a test costs less than a node visit, and of counting launches.
+// smallpt on a large scene: the same lane state machine, but a query walks the exact hierarchy of pt_bvh.cuh instead of
+// all spheres (19 533 spheres: ~4 sphere tests and ~10 node visits per query instead of 19 533 tests; same colours, RNG
+// state and pixels).  The traversal is per lane (its own stack in local memory, nodes and spheres read through L1 / L2)
+// and its length has a long tail (median 3 node visits, 1 % beyond 50), so a warp neither waits for its slowest query
+// nor shades lane by lane.  Every lane is in one of three states -- at an inner node, at a leaf, or holding a finished
+// query -- and each iteration the warp runs ONE kind of step, for all the lanes that are in that state:
+//   shade     once PT_BVH_SHADE_LANES lanes hold a finished query (or nothing else is left to do): the shading STEPS of
+//             pt_lane.cuh in lock-step (hit, light samples, bounce, end of sample) as in pt_kernel<ALIGNED>, then the refill
+//             of lanes whose pixel is complete, then the start of the new queries (always-tested spheres, root box);
+//   leaf      when more lanes wait at a leaf than at an inner node: the exact sphere tests of the leaf, then a pop;
+//   inner     otherwise: two box tests, descend / push / pop.
+// Lanes in the other states keep their state and wait.  The reference-order loop of pt_kernel remains the path of small
+// scenes, where the whole array sits in shared memory and a test costs less than a node visit, and of counting launches.
 __global__ void __launch_bounds__(PT_THREADS, PT_BVH_MIN_BLOCKS)
 pt_bvh_kernel(PtFrame F, PtBvh B, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, uint32_t *pixels, unsigned *work_counter) {
     const uint32_t lane = threadIdx.x & 31u;
+    int stack[PT_BVH_STACK];
+    float stack_t[PT_BVH_STACK];
     PtLane L;
+    PtTrav T;
+    T.node = PT_BVH_DONE; T.sp = 0;
     L.phase = PH_IDLE;
     L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_tests = 0;
     bool exhausted = false;
     for (;;) {
-        const bool need = (L.phase == PH_IDLE) && !exhausted;
-        const uint32_t item = fetch_items(work_counter, need, lane);
-        if (need) {
-            if (item < n_items) {
-                int x, y;
-                if (item_to_pixel(S, F.w, item, x, y)) pt_begin_pixel(L, F, x, y, colors, seeds);
-            } else exhausted = true;
-        }
-        const bool active = L.phase != PH_IDLE;
-        if (!__any_sync(FULL_MASK, active || !exhausted)) break;
-        if (active) {
-            pt_query_bvh<false>(L, B);
-            if (pt_advance<false>(L, F)) {
+        const bool inner = pt_bvh_at_inner(T), leaf = pt_bvh_at_leaf(T);
+        const bool fin = T.node == PT_BVH_DONE && L.phase != PH_IDLE;
+        const int ni = __popc(__ballot_sync(FULL_MASK, inner)), nl = __popc(__ballot_sync(FULL_MASK, leaf));
+        const int nf = __popc(__ballot_sync(FULL_MASK, fin));
+        if (nf >= PT_BVH_SHADE_LANES || ni + nl == 0) {
+            if (nf == 0 && !__any_sync(FULL_MASK, !exhausted)) break;              // nothing in flight, nothing left to fetch
+            if (fin && L.phase == PH_NEAREST) pt_hit<false>(L, F);
+            else if (fin && L.phase == PH_SHADOW) pt_light_done<false>(L, F);
+            while (__any_sync(FULL_MASK, fin && L.phase == PH_LIGHTS))
+                if (fin && L.phase == PH_LIGHTS) pt_light_step(L, F);             // -> PH_SHADOW (a query), the next light, or past the last one
+            if (fin && L.phase == PH_DIFFUSE) pt_diffuse_bounce(L);
+            if (fin && L.phase == PH_BOUNCE) pt_bounce(L);
+            if (fin && L.phase == PH_END && pt_end_sample<false>(L, F)) {
                 const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
                 colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
                 seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
                 if (!F.sum_mode) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
             }
+            const bool need = (L.phase == PH_IDLE) && !exhausted;
+            const uint32_t item = fetch_items(work_counter, need, lane);
+            if (need) {
+                if (item < n_items) {
+                    int x, y;
+                    if (item_to_pixel(S, F.w, item, x, y)) pt_begin_pixel(L, F, x, y, colors, seeds);
+                } else exhausted = true;
+            }
+            if ((fin || need) && (L.phase == PH_NEAREST || L.phase == PH_SHADOW)) pt_bvh_begin<false>(L, B, T);
+        } else if (nl > ni) {
+            if (leaf) pt_bvh_leaf<false>(L, B, T, stack, stack_t);
+        } else {
+            if (inner) pt_bvh_inner(L, B, T, stack, stack_t);
         }
     }
 }

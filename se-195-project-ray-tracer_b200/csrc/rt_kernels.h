@@ -26,7 +26,11 @@
 #endif
 // Large scenes (pt_bvh_kernel): per-lane traversal; the register cap that measured best (profiles/).
 #ifndef PT_BVH_MIN_BLOCKS
-#define PT_BVH_MIN_BLOCKS 6
+#define PT_BVH_MIN_BLOCKS 8
+#endif
+// The shading steps run once this many lanes of a warp hold a finished query (see pt_bvh_kernel).
+#ifndef PT_BVH_SHADE_LANES
+#define PT_BVH_SHADE_LANES 16
 #endif
 // Scenes with at least this many spheres walk the hierarchy (RT_TUNE_PT_BVH = -1).
 #ifndef PT_BVH_MIN_SPHERES

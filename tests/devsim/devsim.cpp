@@ -6,6 +6,7 @@
 // mapping and the FP64 replicas of glibc's float functions can be checked against the oracle on a
 // machine without a GPU.  It is not part of librt_b200.so, is never loaded by the product, and is not
 // a fallback: the product has none (rt_init fails without a CUDA device).
+#define PT_BVH_STATS 1
 #include <vector>
 #include <stdint.h>
 #include <string.h>
@@ -176,5 +177,8 @@ void devsim_bvh_stats(const rt_sphere *sph, uint32_t n, int32_t *out5) {
         for (size_t i = 0; i < bh.nodes.size() / 4; i++) { int a, b; memcpy(&a, &bh.nodes[4 * i + 3].x, 4); memcpy(&b, &bh.nodes[4 * i + 3].y, 4); leaves += (a < 0) + (b < 0); }
     out5[4] = leaves;
 }
+// Inner-node and leaf visits of the hierarchy since the last call (out2), then reset.
+void devsim_bvh_hist(int64_t *out64) { for (int i = 0; i < 64; i++) { out64[i] = g_bvh_hist[i]; g_bvh_hist[i] = 0; } }
+void devsim_bvh_visits(int64_t *out2) { out2[0] = g_bvh_inner_visits; out2[1] = g_bvh_leaf_visits; g_bvh_inner_visits = g_bvh_leaf_visits = 0; }
 
 }  // extern "C"

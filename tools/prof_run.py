@@ -17,5 +17,16 @@ if which in ("both", "pt"):
     for _ in range(2):
         r.pt_launch(0, 16)
     r.sync()
+if which == "bvh":           # the large-scene path tracer: 19 533 spheres, 1920x1080 x 4 spp, two launches
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "c6.scn")
+        rt.write_complex_scene(p, 6)
+        sph, cam = rt.read_scene(p, 1920, 1080)
+    seeds = rt.reference_seeds(1920, 1080)
+    r.pt_resize(1920, 1080, seeds); r.pt_set_scene(sph); r.pt_set_camera(cam)
+    for _ in range(2):
+        r.pt_launch(0, 4)
+    r.sync()
 r.close()
 print("prof_run ok")
