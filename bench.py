@@ -24,7 +24,8 @@ are a property of scene and resolution, identical in the oracle -- tests/test_gp
             the reference's OWN CPU code (oracle/_ref: raytracer_non_OpenCL.c compiled unmodified) on the
             box's host cores, one frame per thread on a bounded sample.
 
-Extra (not the headline): "pt" = BASELINE configs[2], smallpt cornell.scn 1024x768 x 256 spp, Msamples/s.
+Extra (not the headline): "pt" = BASELINE configs[2], smallpt cornell.scn 1024x768 x 256 spp, Msamples/s;
+"c4" = BASELINE configs[3], the 783-sphere generated scene at 3840x2160 x 16 spp (loop over every sphere and exact hierarchy).
 """
 import argparse
 import ctypes
@@ -339,6 +340,7 @@ def run_ours(args, rank, world, local_rank):
         mrays, ms, kind, sample = time_reference(rt, 2, 1, threads)
         out["cpu_baseline"] = {"value": round(mrays, 3), "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample}
         out["config1"] = time_config1(rt, r)
+        out["c4"] = bench_c4(rt, r, info, peaks, torch, stream)
     if rank == 0:
         print(json.dumps(out))
     r.close()
@@ -439,6 +441,67 @@ def bench_pt(rt, r, info, peaks, torch, stream):
     dt = time.perf_counter() - t0
     res["cpu_baseline"] = {"value": round(sw * sh * sp / dt / 1e6, 3), "unit": "Msamples/s", "cores": threads, "kind": kind,
                            "sample": f"cornell {sw}x{sh} x {sp} spp, rows split over {threads} host threads, reference RadiancePathTracing"}
+    return res
+
+
+def bench_c4(rt, r, info, peaks, torch, stream):
+    """BASELINE configs[3]: the scene_build_complex.pl scene ($maxDepth 4 = 783 spheres) at 3840x2160 x 16 spp, path tracing:
+    the reference-order loop over every sphere (shared-memory staging) and the exact hierarchy (csrc/pt_bvh.cuh), which gives
+    the same bits; the reference's own CPU code on a bounded sample next to them."""
+    import tempfile
+    w, h, spp = 3840, 2160, 16
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "complex4.scn")
+        rt.write_complex_scene(path, 4)
+        spheres, cam = rt.read_scene(path, w, h)
+        sw, sh, sp = 384, 216, 4
+        sph_s, cam_s = rt.read_scene(path, sw, sh)
+    seeds = rt.reference_seeds(w, h, seed=1)
+    r.pt_resize(w, h, seeds); r.pt_set_scene(spheres); r.pt_set_camera(cam)
+    r.set_counting(True); r.pt_launch(0, 1); c = r.counters(); r.set_counting(False)
+    per = {k: v / c["samples"] for k, v in c.items()}
+    samples = w * h * spp
+    flop = 17.0 * per["sphere_tests"] * samples
+    fp32_peak = info["sm_count"] * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+    res = {"workload": f"scene_build_complex.pl $maxDepth 4: {spheres.size} spheres, {w}x{h} x {spp} spp, path tracing, one launch",
+           "reference_sphere_tests_per_sample": round(per["sphere_tests"], 1), "rays_per_sample": round(per["nearest_queries"] + per["shadow_queries"], 3)}
+    pixels = {}
+    for mode, tag in ((0, "loop_over_every_sphere"), (1, "exact_hierarchy")):
+        r.set_tuning(rt.TUNE_PT_BVH, mode)
+        times = []
+        for it in range(3):
+            r.pt_resize(w, h, seeds); r.pt_set_camera(cam)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); r.pt_launch(0, spp); b.record(stream)
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        ms = min(times[1:])
+        pixels[tag] = r.pt_download(want=("colors",))["colors"].copy()
+        res[tag] = {"kernel_ms": round(ms, 2), "msamples_per_s": round(samples / ms / 1e3, 1),
+                    "mrays_per_s": round(samples * (per["nearest_queries"] + per["shadow_queries"]) / ms / 1e3, 1)}
+        if mode == 0:
+            res[tag]["fp32_tflops_algorithmic"] = round(flop / ms / 1e9, 2)
+            res[tag]["frac_of_fp32_peak"] = round(flop / ms / 1e9 / fp32_peak, 4)
+    r.set_tuning(rt.TUNE_PT_BVH, -1)
+    res["hierarchy_equals_loop"] = bool(np.array_equal(pixels["loop_over_every_sphere"].view(np.uint32), pixels["exact_hierarchy"].view(np.uint32)))
+    ref_path = os.path.join(graft.ORACLE_DIR, "_ref", "libref_smallpt.so")
+    threads = host_threads()
+    sd = rt.reference_seeds(sw, sh, seed=1)
+    col = np.zeros(3 * sw * sh, np.float32)
+    if os.path.exists(ref_path):
+        ref = ctypes.CDLL(ref_path)
+        ref.ref_pt_set_scene(vp(sph_s), sph_s.size, vp(cam_s), sw, sh)
+        t0 = time.perf_counter()
+        ref.ref_pt_render_mt(0, 0, sp, vp(col), vp(sd), None, threads)
+        kind = "reference"
+    else:
+        orc = graft.oracle()
+        t0 = time.perf_counter()
+        orc.oracle_pt_render(0, vp(sph_s), sph_s.size, vp(cam_s), sw, sh, 0, sp, vp(col), vp(sd), None, threads, None)
+        kind = "port"
+    dt = time.perf_counter() - t0
+    res["cpu_baseline"] = {"value": round(sw * sh * sp / dt / 1e6, 3), "unit": "Msamples/s", "cores": threads, "kind": kind,
+                           "sample": f"the same scene {sw}x{sh} x {sp} spp, rows split over {threads} host threads, reference RadiancePathTracing"}
     return res
 
 
