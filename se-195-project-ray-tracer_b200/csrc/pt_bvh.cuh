@@ -19,13 +19,15 @@
 //   rho^2 <= rad2 + eta,   eta = (|eps| + 13u)(1 + 2|eps|) * OO + (2|eps| + 2u) * rad2:
 // the line passes through the sphere inflated to R' = sqrt(rad2 + eta) <= rad + eta / (2*rad).  The accepted distance is
 // fl(b -+ sqrt(det)), which lies within (|eps| + 10u) * |op| of the parametric entry / exit of that inflated sphere.
-// A node stores the box of its spheres, hinv = 0.5 / (smallest radius below it); the scene stores eta0 >= (2|eps|+2u) *
-// (largest radius)^2 for |eps| <= 2^-18.  For a ray, D_k = the largest |box corner - o| per axis bounds |op_k|, so with
+// (and <= rad + sqrt(eta): far from the scene eta exceeds rad2 -- the reference's own det is noise there -- and the
+// first bound would grow without need).  A node stores the box of its spheres and hinv = 0.5 / (smallest radius below it);
+// the scene stores eta0 >= (2|eps|+2u) * (largest radius)^2 for |eps| <= 2^-18.  Per ray, D_k = the largest
+// |root box corner - o| per axis bounds |op_k| of every sphere of the tree (every node's box lies inside the root's), so with
 //   K1 = 2*e + 34u  (e = |fl(d.d) - 1| >= |eps| - 4u: TWICE the bound above),   eta = K1 * (Dx^2+Dy^2+Dz^2) + eta0,
-//   m  = eta * hinv + 1e-6 * (1 + Dx+Dy+Dz)                      (the last term covers o' - o and the slab roundings)
-// every sphere below the node that could return d != 0 has its inflated sphere inside the box grown by m; the slab test
-// on the grown box yields [te, tx], and no accepted distance below the node is smaller than te - kT*(Dx+Dy+Dz) or larger
-// than tx + kT*(Dx+Dy+Dz), kT = 2*e + 40u.  A node is skipped only if the grown box is missed, lies behind the origin or
+//   m  = min(eta * hinv, 1.001 * sqrt(eta)) + 1e-6 * (1 + Dx+Dy+Dz)     (the last term covers o' - o and the slab roundings)
+// every sphere below a node that could return d != 0 has its inflated sphere inside the node's box grown by m; the slab
+// test on the grown box yields [te, tx], and no accepted distance below the node is smaller than te - kT*(Dx+Dy+Dz) or
+// larger than tx + kT*(Dx+Dy+Dz), kT = 2*e + 40u.  A node is skipped only if the grown box is missed, lies behind the origin or
 // lies beyond the current limit by those margins; every comparison is written so that a NaN (0 * inf on a slab face)
 // means "visit".  A ray whose direction is not a unit vector to within 2^-18 (never produced by the tracer) gets
 // K1 = kT = inf: it visits everything.  Spheres that are much larger than the rest (the 10 000-unit floor) or not
@@ -79,7 +81,8 @@ RT_HD void pt_bvh_sphere(PtLane &L, const f4 g, int idx) {
     else if (t < L.cumu || (t == L.cumu && idx > L.hit)) { L.cumu = t; L.hit = idx; }
 }
 
-struct PtBvhRay { float ix, iy, iz, K1, kT; };
+// Per-ray constants of the node test: reciprocal direction, eta, 1.001*sqrt(eta), the additive term of m, the slack.
+struct PtBvhRay { float ix, iy, iz, eta, seta, c, slack; };
 
 // 1/x for the slab test: two units in the last place are enough (the slacks above allow for it), so the device uses
 // the fast reciprocal; a denormal component flushes to "parallel to the slab" like a zero one.
@@ -91,35 +94,39 @@ RT_HD float bvh_rcp(float x) {
 #endif
 }
 
-RT_HD PtBvhRay pt_bvh_ray(const PtLane &L) {
+RT_HD PtBvhRay pt_bvh_ray(const PtLane &L, const PtBvh &B) {
     PtBvhRay R;
     const float dd = dot3(L.dx, L.dy, L.dz, L.dx, L.dy, L.dz);
     const float e = fabsf(f_sub(dd, 1.f));
-    if (e <= PT_BVH_MAX_EPS) { R.K1 = 2.f * e + 34.f * PT_BVH_U; R.kT = 2.f * e + 40.f * PT_BVH_U; }
-    else R.K1 = R.kT = INFINITY;                   // not a unit direction (or NaN): no culling
+    float K1, kT;
+    if (e <= PT_BVH_MAX_EPS) { K1 = 2.f * e + 34.f * PT_BVH_U; kT = 2.f * e + 40.f * PT_BVH_U; }
+    else K1 = kT = INFINITY;                       // not a unit direction (or NaN): no culling
     R.ix = bvh_rcp(L.dx); R.iy = bvh_rcp(L.dy); R.iz = bvh_rcp(L.dz);
+    const float Dx = fmaxf(fabsf(B.root_lo[0] - L.ox), fabsf(B.root_hi[0] - L.ox));
+    const float Dy = fmaxf(fabsf(B.root_lo[1] - L.oy), fabsf(B.root_hi[1] - L.oy));
+    const float Dz = fmaxf(fabsf(B.root_lo[2] - L.oz), fabsf(B.root_hi[2] - L.oz));
+    const float D1 = Dx + Dy + Dz;
+    R.eta = K1 * (Dx * Dx + Dy * Dy + Dz * Dz) + B.eta0;
+    R.seta = 1.001f * sqrtf(R.eta);
+    R.c = 1e-6f * (1.f + D1);
+    R.slack = kT * D1;
     return R;
 }
 
-// Conservative "may some sphere below this box return an accepted distance" + the entry parameter for ordering.
+// Conservative "may some sphere below this box return an accepted distance" + a lower bound of such distances.
 RT_HD bool pt_bvh_box(const PtLane &L, const PtBvhRay &R, float lox, float hix, float loy, float hiy, float loz, float hiz,
-                      float hinv, float eta0, float &lb_out) {
+                      float hinv, float &lb_out) {
     const float a0x = lox - L.ox, a1x = hix - L.ox, a0y = loy - L.oy, a1y = hiy - L.oy, a0z = loz - L.oz, a1z = hiz - L.oz;
-    const float Dx = fmaxf(fabsf(a0x), fabsf(a1x)), Dy = fmaxf(fabsf(a0y), fabsf(a1y)), Dz = fmaxf(fabsf(a0z), fabsf(a1z));
-    const float D1 = Dx + Dy + Dz;
-    const float D2 = Dx * Dx + Dy * Dy + Dz * Dz;
-    const float eta = R.K1 * D2 + eta0;
-    const float m = eta * hinv + 1e-6f * (1.f + D1);
+    const float m = fminf(R.eta * hinv, R.seta) + R.c;
     const float t0x = (a0x - m) * R.ix, t1x = (a1x + m) * R.ix;
     const float t0y = (a0y - m) * R.iy, t1y = (a1y + m) * R.iy;
     const float t0z = (a0z - m) * R.iz, t1z = (a1z + m) * R.iz;
     const float te = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
     const float tx = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
-    const float slack = R.kT * D1;
-    lb_out = te - slack;                   // no accepted distance below this box is smaller (NaN: compares false = keep)
+    lb_out = te - R.slack;                 // no accepted distance below this box is smaller (NaN: compares false = keep)
     const bool missed = (te - tx) > 1e-6f * (fabsf(te) + fabsf(tx));
-    const bool behind = (tx + slack) < 0.f;
-    const bool beyond = (te - slack) > L.cumu;
+    const bool behind = (tx + R.slack) < 0.f;
+    const bool beyond = (te - R.slack) > L.cumu;
     return !(missed | behind | beyond);
 }
 
@@ -138,13 +145,14 @@ RT_HD void pt_bvh_begin(PtLane &L, const PtBvh &B, PtTrav &T) {
         if (shadow && L.hit >= 0) return;
     }
     if (B.root == PT_BVH_NONE) return;
-    T.R = pt_bvh_ray(L);
+    T.R = pt_bvh_ray(L, B);
     float lb;
-    if (pt_bvh_box(L, T.R, B.root_lo[0], B.root_hi[0], B.root_lo[1], B.root_hi[1], B.root_lo[2], B.root_hi[2], B.root_hinv, B.eta0, lb)) T.node = B.root;
+    if (pt_bvh_box(L, T.R, B.root_lo[0], B.root_hi[0], B.root_lo[1], B.root_hi[1], B.root_lo[2], B.root_hi[2], B.root_hinv, lb)) T.node = B.root;
 }
 
 #ifdef PT_BVH_STATS          /* test-only visit counters of the host build (tests/devsim) */
-static long g_bvh_inner_visits = 0, g_bvh_leaf_visits = 0, g_bvh_hist[64] = {0};
+static long g_bvh_inner_visits = 0, g_bvh_leaf_visits = 0, g_bvh_hist[64] = {0}, g_bvh_tail_visits = 0, g_bvh_max_visits = 0;
+static float g_bvh_max_ray[7] = {0};
 #define PT_BVH_STAT(x) ((x)++)
 #else
 #define PT_BVH_STAT(x) ((void)0)
@@ -168,8 +176,8 @@ RT_HD void pt_bvh_inner(const PtLane &L, const PtBvh &B, PtTrav &T, int *stack, 
     const int node = T.node;
     const f4 n0 = B.nodes[4 * node], n1 = B.nodes[4 * node + 1], n2 = B.nodes[4 * node + 2], n3 = B.nodes[4 * node + 3];
     float lb0, lb1;
-    const bool h0 = pt_bvh_box(L, T.R, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, n3.z, B.eta0, lb0);
-    const bool h1 = pt_bvh_box(L, T.R, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, n3.w, B.eta0, lb1);
+    const bool h0 = pt_bvh_box(L, T.R, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, n3.z, lb0);
+    const bool h1 = pt_bvh_box(L, T.R, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, n3.w, lb1);
     const int c0 = (int)f_bits(n3.x), c1 = (int)f_bits(n3.y);
     if (h0 & h1) {
         const bool swap = lb1 < lb0;                     // nearer child first (any order is correct)
@@ -202,7 +210,8 @@ RT_HD void pt_query_bvh(PtLane &L, const PtBvh &B) {
     pt_bvh_begin<COUNT>(L, B, T);
 #ifdef PT_BVH_STATS
     const long v0 = g_bvh_inner_visits;
-    struct Tally { long v0; ~Tally() { long n = g_bvh_inner_visits - v0; g_bvh_hist[n > 63 ? 63 : n]++; } } tally{v0};
+    struct Tally { long v0; const PtLane &L; ~Tally() { long n = g_bvh_inner_visits - v0; g_bvh_hist[n > 63 ? 63 : n]++; if (n >= 63) g_bvh_tail_visits += n;
+        if (n > g_bvh_max_visits) { g_bvh_max_visits = n; g_bvh_max_ray[0] = L.ox; g_bvh_max_ray[1] = L.oy; g_bvh_max_ray[2] = L.oz; g_bvh_max_ray[3] = L.dx; g_bvh_max_ray[4] = L.dy; g_bvh_max_ray[5] = L.dz; g_bvh_max_ray[6] = (float)L.phase; } } } tally{v0, L};
 #endif
     while (T.node != PT_BVH_DONE) {
         if (pt_bvh_at_inner(T)) pt_bvh_inner(L, B, T, stack, stack_t);

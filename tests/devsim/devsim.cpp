@@ -178,6 +178,7 @@ void devsim_bvh_stats(const rt_sphere *sph, uint32_t n, int32_t *out5) {
     out5[4] = leaves;
 }
 // Inner-node and leaf visits of the hierarchy since the last call (out2), then reset.
+void devsim_bvh_tail(int64_t *out2, float *ray7) { out2[0] = g_bvh_tail_visits; out2[1] = g_bvh_max_visits; for (int i = 0; i < 7; i++) ray7[i] = g_bvh_max_ray[i]; g_bvh_tail_visits = g_bvh_max_visits = 0; }
 void devsim_bvh_hist(int64_t *out64) { for (int i = 0; i < 64; i++) { out64[i] = g_bvh_hist[i]; g_bvh_hist[i] = 0; } }
 void devsim_bvh_visits(int64_t *out2) { out2[0] = g_bvh_inner_visits; out2[1] = g_bvh_leaf_visits; g_bvh_inner_visits = g_bvh_leaf_visits = 0; }
 

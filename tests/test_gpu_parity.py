@@ -436,6 +436,8 @@ def test_smallpt_exact_hierarchy_tie_rule_and_mixed_scenes(gpu, rt, tmp_path):
     cases = [(scene, cam)]
     c2 = cam.copy(); c2["orig"] = (3.0, 21.0, 4.0); rt.update_camera(c2, w, h)
     cases.append((scene, c2))
+    c3 = cam.copy(); c3["orig"] = (2100.0, 16000.0, 7700.0); rt.update_camera(c3, w, h)      # far away: the reference's det is mostly noise
+    cases.append((scene, c3))
     for n in (37, 300, 2000):
         _, ccam = rt.cornell_scene(w, h)
         cl = np.zeros(n, sph.dtype)

@@ -168,7 +168,8 @@ def test_bvh_traversal_equals_the_plain_sphere_loop_on_generated_scenes(devsim, 
 
 def test_bvh_traversal_keeps_the_reference_tie_rule_and_odd_spheres(devsim, rt, tmp_path):
     """Exact ties (duplicated spheres: the HIGHER index must win, SPT/geomfunc.h:80-88), mirrors and glass among the
-    small spheres, a zero-radius sphere, touching and nested spheres, a camera inside the cloud."""
+    small spheres, a zero-radius sphere, touching and nested spheres, a camera inside the cloud, and a camera so far away that the
+    reference's own discriminant is mostly rounding noise (the hierarchy must reproduce that noise, not the geometry)."""
     sph, cam = _complex_scene(rt, tmp_path, 3, 40, 30)
     rs = np.random.RandomState(7)
     extra = sph[2:].copy()
@@ -182,7 +183,7 @@ def test_bvh_traversal_keeps_the_reference_tie_rule_and_odd_spheres(devsim, rt, 
     scene["p"][60] = scene["p"][61]
     perm = np.concatenate([[0, 1], 2 + rs.permutation(scene.size - 2)])
     scene = scene[perm].copy()
-    for cam_pos in (None, (3.0, 21.0, 4.0)):
+    for cam_pos in (None, (3.0, 21.0, 4.0), (2100.0, 16000.0, 7700.0)):      # default, inside the cloud, 18 000 units away
         c = cam.copy()
         if cam_pos:
             c["orig"] = cam_pos
