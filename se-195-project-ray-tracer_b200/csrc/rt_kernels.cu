@@ -82,6 +82,8 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
         else         { if (!__any_sync(FULL_MASK, more)) break; }
 
         if (ALIGNED) {
+            // (One shared copy of the sphere loop for the nearest and the shadow round -- 30 KB of SASS instead of 35 KB -- was
+            // measured 4 % slower, 9.83 against 9.41 ms for 32 spp: the two inlined copies stay.)
             const bool nq = L.phase == PH_NEAREST;
             pt_query_range<COUNT>(L, s_geom, 0, F.n, nq);
             if (nq) pt_hit<COUNT>(L, F);

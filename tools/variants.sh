@@ -4,9 +4,7 @@ set -e
 cd "$(dirname "$0")/../se-195-project-ray-tracer_b200"
 rm -f ../variants/*.so
 build() { tag=$1; shift; nvcc "$@" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -std=c++17 -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off -shared -o ../variants/librt_$tag.so csrc/rt_kernels.cu csrc/rt_api.cu host/scene_io.cpp & }
-build rm0
-build rm1 -DPT_BVH_RAY_MARGIN=1
-build rm1_s12 -DPT_BVH_RAY_MARGIN=1 -DPT_BVH_SHADE_LANES=12
-build rm1_s20 -DPT_BVH_RAY_MARGIN=1 -DPT_BVH_SHADE_LANES=20
+build prod
+build leafunroll -DPT_BVH_LEAF_UNROLL=1
 wait
 ls ../variants
