@@ -462,6 +462,37 @@ def test_smallpt_exact_hierarchy_tie_rule_and_mixed_scenes(gpu, rt, tmp_path):
         gpu.set_tuning(rt.TUNE_PT_BVH, -1)
 
 
+def test_smallpt_exact_hierarchy_sharded_progressive_and_resumed(gpu, rt, tmp_path):
+    """The hierarchy kernel behind the same API features as the loop kernel: row-tile shards assemble to the unsharded
+    frame, and two progressive calls (2 + 3 passes) equal one call of 5."""
+    p = tmp_path / "c4.scn"
+    rt.write_complex_scene(str(p), 4)
+    w, h = 200, 150
+    spheres, cam = rt.read_scene(str(p), w, h)
+    seeds = rt.reference_seeds(w, h, seed=5)
+    try:
+        gpu.set_tuning(rt.TUNE_PT_BVH, 1)
+        gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+        full = gpu.pt_render(0, 5)
+        gpu.pt_resize(w, h, seeds); gpu.pt_set_camera(cam)
+        gpu.pt_launch(0, 2)
+        two = gpu.pt_render(0, 3)
+        for k in ("seeds", "colors", "pixels"):
+            assert np.array_equal(full[k].reshape(-1).view(np.uint32), two[k].reshape(-1).view(np.uint32)), k
+        world, tile = 3, 8
+        acc = {k: np.zeros_like(full[k]) for k in ("pixels",)}
+        for rank in range(world):
+            gpu.set_shard(rank, world, tile)
+            gpu.pt_resize(w, h, seeds); gpu.pt_set_camera(cam)
+            out = gpu.pt_render(0, 5)
+            rows = rt.owned_rows(h, rank, world, tile)
+            acc["pixels"].reshape(h, w)[rows] = out["pixels"].reshape(h, w)[rows]
+        assert np.array_equal(acc["pixels"], full["pixels"])
+    finally:
+        gpu.set_shard(0, 1, 8)
+        gpu.set_tuning(rt.TUNE_PT_BVH, -1)
+
+
 def test_smallpt_row_tile_sharding_is_bit_identical(gpu, rt, cornell):
     spheres, cam = cornell
     w, h = 100, 75
