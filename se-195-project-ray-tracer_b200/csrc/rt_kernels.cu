@@ -162,7 +162,7 @@ pt_bvh_kernel(PtFrame F, PtBvh B, Shard S, uint32_t n_items, float *colors, uint
         const bool inner = pt_bvh_at_inner(T), leaf = pt_bvh_at_leaf(T);
         const bool fin = T.node == PT_BVH_DONE && L.phase != PH_IDLE;
         const int ni = __popc(__ballot_sync(FULL_MASK, inner)), nl = __popc(__ballot_sync(FULL_MASK, leaf));
-        const int nf = __popc(__ballot_sync(FULL_MASK, fin));
+        const int nf = __popc(__ballot_sync(FULL_MASK, fin));        // (a separate quorum per kind of finished query was 12-20 % slower)
         if (nf >= PT_BVH_SHADE_LANES || ni + nl == 0) {
             if (nf == 0 && !__any_sync(FULL_MASK, !exhausted)) break;              // nothing in flight, nothing left to fetch
             if (fin && L.phase == PH_NEAREST) pt_hit<false>(L, F);
