@@ -117,7 +117,11 @@ RT_HD PtBvhRay pt_bvh_ray(const PtLane &L, const PtBvh &B) {
 RT_HD bool pt_bvh_box(const PtLane &L, const PtBvhRay &R, float lox, float hix, float loy, float hiy, float loz, float hiz,
                       float hinv, float &lb_out) {
     const float a0x = lox - L.ox, a1x = hix - L.ox, a0y = loy - L.oy, a1y = hiy - L.oy, a0z = loz - L.oz, a1z = hiz - L.oz;
+#ifdef PT_BVH_TEST_NO_MARGIN          /* tools/bvh_fuzz.py self-check: a hierarchy WITHOUT the rounding margins must be caught */
+    const float m = 0.f;
+#else
     const float m = fminf(R.eta * hinv, R.seta) + R.c;
+#endif
     const float t0x = (a0x - m) * R.ix, t1x = (a1x + m) * R.ix;
     const float t0y = (a0y - m) * R.iy, t1y = (a1y + m) * R.iy;
     const float t0z = (a0z - m) * R.iz, t1z = (a1z + m) * R.iz;

@@ -4,9 +4,6 @@ set -e
 cd "$(dirname "$0")/../se-195-project-ray-tracer_b200"
 rm -f ../variants/*.so
 build() { tag=$1; shift; nvcc "$@" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ftz=false -std=c++17 -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off -shared -o ../variants/librt_$tag.so csrc/rt_kernels.cu csrc/rt_api.cu host/scene_io.cpp & }
-build prod
-build k8 -DPT_BVH_SHADE_BY_KIND=1 -DPT_BVH_SHADE_LANES=8
-build k12 -DPT_BVH_SHADE_BY_KIND=1 -DPT_BVH_SHADE_LANES=12
-build k16 -DPT_BVH_SHADE_BY_KIND=1 -DPT_BVH_SHADE_LANES=16
+build nomargin -DPT_BVH_TEST_NO_MARGIN
 wait
 ls ../variants
