@@ -114,6 +114,8 @@ enum {
     RT_TUNE_MAX_BLOCKS_PER_SM = 2,      /* cap on resident CTAs per SM (0 = as many as fit) */
     RT_TUNE_WHITTED_COST_ORDER = 3,     /* 1 (default): a pre-pass hands out expensive pixels first; 0: screen order.  Same image either way */
     RT_TUNE_PT_ALIGNED = 4,             /* path tracer: 1 = warps run the shading steps in lock-step, 0 = plain query loop, -1 (default) = by scene size.  Same image either way */
+    RT_TUNE_WHITTED_BVH = 6,            /* Whitted tracer: the same hierarchy for the non-light spheres of large scenes (rt_whitted_from_spheres tables); planes,
+                                           lights and odd spheres are still tested by every query.  1 / 0 / -1 (default: by scene size).  Same image either way */
     RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
                                            reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };

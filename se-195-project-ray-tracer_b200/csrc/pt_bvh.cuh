@@ -21,16 +21,18 @@
 // fl(b -+ sqrt(det)), which lies within (|eps| + 10u) * |op| of the parametric entry / exit of that inflated sphere.
 // (and <= rad + sqrt(eta): far from the scene eta exceeds rad2 -- the reference's own det is noise there -- and the
 // first bound would grow without need).  A node stores the box of its spheres and hinv = 0.5 / (smallest radius below it);
-// the scene stores eta0 >= (2|eps|+2u) * (largest radius)^2 for |eps| <= 2^-18.  Per ray, D_k = the largest
+// the scene stores the largest radius r_max of the tree.  Per ray, D_k = the largest
 // |root box corner - o| per axis bounds |op_k| of every sphere of the tree (every node's box lies inside the root's), so with
-//   K1 = 2*e + 34u  (e = |fl(d.d) - 1| >= |eps| - 4u: TWICE the bound above),   eta = K1 * (Dx^2+Dy^2+Dz^2) + eta0,
+//   K1 = 2*e + 34u, K2 = 4*e + 24u  (e = |fl(d.d) - 1| >= |eps| - 4u: TWICE the bounds above),
+//   eta = K1 * (Dx^2+Dy^2+Dz^2) + K2 * r_max^2,
 //   m  = min(eta * hinv, 1.001 * sqrt(eta)) + 1e-6 * (1 + Dx+Dy+Dz)     (the last term covers o' - o and the slab roundings)
 // every sphere below a node that could return d != 0 has its inflated sphere inside the node's box grown by m; the slab
 // test on the grown box yields [te, tx], and no accepted distance below the node is smaller than te - kT*(Dx+Dy+Dz) or
 // larger than tx + kT*(Dx+Dy+Dz), kT = 2*e + 40u.  A node is skipped only if the grown box is missed, lies behind the origin or
 // lies beyond the current limit by those margins; every comparison is written so that a NaN (0 * inf on a slab face)
-// means "visit".  A ray whose direction is not a unit vector to within 2^-18 (never produced by the tracer) gets
-// K1 = kT = inf: it visits everything.  Spheres that are much larger than the rest (the 10 000-unit floor) or not
+// means "visit".  The bounds hold for any |eps| (a direction that is not exactly unit length -- the Whitted tracer's
+// reflections off computed sphere normals are off by ~1e-4 -- just sees slightly larger spheres, which is what the
+// reference's unit-length formula does with it); beyond |eps| = 2^-7 the ray gets K1 = kT = inf and visits everything.  Spheres that are much larger than the rest (the 10 000-unit floor) or not
 // finite are not in the tree at all: they form a short list that every query tests first.
 // tests/: the traversal against the plain loop on the lane simulator (CPU), and against the brute-force kernel on the
 // GPU at full size -- colours, RNG state and pixels bit-identical.
@@ -45,7 +47,7 @@ namespace rtb {
 #endif
 #define PT_BVH_NONE 0x7fffffff
 #define PT_BVH_U 5.9604644775390625e-8f          /* 2^-24 */
-#define PT_BVH_MAX_EPS 3.814697265625e-6f        /* 2^-18 */
+#define PT_BVH_MAX_EPS 0.0078125f                 /* 2^-7: directions further from unit length than this get no culling */
 
 // Inner node i = nodes[4i .. 4i+3]:
 //   [0] = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   [1] = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
@@ -59,7 +61,7 @@ struct PtBvh {
     int root;                // child code of the root, PT_BVH_NONE when every sphere is in the always-tested list
     float root_hinv;
     float root_lo[3], root_hi[3];
-    float eta0;
+    float rmax2;             // (largest radius in the tree)^2, rounded up
 };
 
 RT_HD int pt_bvh_leaf_code(int first, int count) { return ~((first << 3) | (count - 1)); }
@@ -94,29 +96,29 @@ RT_HD float bvh_rcp(float x) {
 #endif
 }
 
-RT_HD PtBvhRay pt_bvh_ray(const PtLane &L, const PtBvh &B) {
+RT_HD PtBvhRay bvh_ray(float ox, float oy, float oz, float dx, float dy, float dz, const PtBvh &B) {
     PtBvhRay R;
-    const float dd = dot3(L.dx, L.dy, L.dz, L.dx, L.dy, L.dz);
+    const float dd = dot3(dx, dy, dz, dx, dy, dz);
     const float e = fabsf(f_sub(dd, 1.f));
-    float K1, kT;
-    if (e <= PT_BVH_MAX_EPS) { K1 = 2.f * e + 34.f * PT_BVH_U; kT = 2.f * e + 40.f * PT_BVH_U; }
-    else K1 = kT = INFINITY;                       // not a unit direction (or NaN): no culling
-    R.ix = bvh_rcp(L.dx); R.iy = bvh_rcp(L.dy); R.iz = bvh_rcp(L.dz);
-    const float Dx = fmaxf(fabsf(B.root_lo[0] - L.ox), fabsf(B.root_hi[0] - L.ox));
-    const float Dy = fmaxf(fabsf(B.root_lo[1] - L.oy), fabsf(B.root_hi[1] - L.oy));
-    const float Dz = fmaxf(fabsf(B.root_lo[2] - L.oz), fabsf(B.root_hi[2] - L.oz));
+    float K1, K2, kT;
+    if (e <= PT_BVH_MAX_EPS) { K1 = 2.f * e + 34.f * PT_BVH_U; K2 = 4.f * e + 24.f * PT_BVH_U; kT = 2.f * e + 40.f * PT_BVH_U; }
+    else K1 = K2 = kT = INFINITY;                  // far from a unit direction (or NaN): no culling
+    R.ix = bvh_rcp(dx); R.iy = bvh_rcp(dy); R.iz = bvh_rcp(dz);
+    const float Dx = fmaxf(fabsf(B.root_lo[0] - ox), fabsf(B.root_hi[0] - ox));
+    const float Dy = fmaxf(fabsf(B.root_lo[1] - oy), fabsf(B.root_hi[1] - oy));
+    const float Dz = fmaxf(fabsf(B.root_lo[2] - oz), fabsf(B.root_hi[2] - oz));
     const float D1 = Dx + Dy + Dz;
-    R.eta = K1 * (Dx * Dx + Dy * Dy + Dz * Dz) + B.eta0;
+    R.eta = K1 * (Dx * Dx + Dy * Dy + Dz * Dz) + K2 * B.rmax2;
     R.seta = 1.001f * sqrtf(R.eta);
     R.c = 1e-6f * (1.f + D1);
     R.slack = kT * D1;
     return R;
 }
 
-// Conservative "may some sphere below this box return an accepted distance" + a lower bound of such distances.
-RT_HD bool pt_bvh_box(const PtLane &L, const PtBvhRay &R, float lox, float hix, float loy, float hiy, float loz, float hiz,
-                      float hinv, float &lb_out) {
-    const float a0x = lox - L.ox, a1x = hix - L.ox, a0y = loy - L.oy, a1y = hiy - L.oy, a0z = loz - L.oz, a1z = hiz - L.oz;
+// Conservative "may some sphere below this box return an accepted distance below `limit`" + a lower bound of such distances.
+RT_HD bool bvh_box(float ox, float oy, float oz, float limit, const PtBvhRay &R, float lox, float hix, float loy, float hiy, float loz, float hiz,
+                   float hinv, float &lb_out) {
+    const float a0x = lox - ox, a1x = hix - ox, a0y = loy - oy, a1y = hiy - oy, a0z = loz - oz, a1z = hiz - oz;
 #ifdef PT_BVH_TEST_NO_MARGIN          /* tools/bvh_fuzz.py self-check: a hierarchy WITHOUT the rounding margins must be caught */
     const float m = 0.f;
 #else
@@ -130,7 +132,7 @@ RT_HD bool pt_bvh_box(const PtLane &L, const PtBvhRay &R, float lox, float hix, 
     lb_out = te - R.slack;                 // no accepted distance below this box is smaller (NaN: compares false = keep)
     const bool missed = (te - tx) > 1e-6f * (fabsf(te) + fabsf(tx));
     const bool behind = (tx + R.slack) < 0.f;
-    const bool beyond = (te - R.slack) > L.cumu;
+    const bool beyond = (te - R.slack) > limit;
     return !(missed | behind | beyond);
 }
 
@@ -139,6 +141,7 @@ RT_HD bool pt_bvh_box(const PtLane &L, const PtBvhRay &R, float lox, float hix, 
 #define PT_BVH_DONE 0x7ffffffe
 struct PtTrav { PtBvhRay R; int node, sp; };
 
+RT_HD int bvh_root(float ox, float oy, float oz, float limit, const PtBvh &B, const PtBvhRay &R);
 // Starts the lane's query (nearest or shadow, by L.phase): the always-tested spheres, then the root box.
 template <bool COUNT>
 RT_HD void pt_bvh_begin(PtLane &L, const PtBvh &B, PtTrav &T) {
@@ -149,9 +152,8 @@ RT_HD void pt_bvh_begin(PtLane &L, const PtBvh &B, PtTrav &T) {
         if (shadow && L.hit >= 0) return;
     }
     if (B.root == PT_BVH_NONE) return;
-    T.R = pt_bvh_ray(L, B);
-    float lb;
-    if (pt_bvh_box(L, T.R, B.root_lo[0], B.root_hi[0], B.root_lo[1], B.root_hi[1], B.root_lo[2], B.root_hi[2], B.root_hinv, lb)) T.node = B.root;
+    T.R = bvh_ray(L.ox, L.oy, L.oz, L.dx, L.dy, L.dz, B);
+    T.node = bvh_root(L.ox, L.oy, L.oz, L.cumu, B, T.R);
 }
 
 #ifdef PT_BVH_STATS          /* test-only visit counters of the host build (tests/devsim) */
@@ -165,23 +167,29 @@ RT_HD bool pt_bvh_at_inner(const PtTrav &T) { return (unsigned)T.node < (unsigne
 RT_HD bool pt_bvh_at_leaf(const PtTrav &T) { return T.node < 0; }
 
 // Next node from the stack; a pushed child that is now beyond the limit is dropped.
-RT_HD void pt_bvh_pop(const PtLane &L, PtTrav &T, const int *stack, const float *stack_t) {
+RT_HD void bvh_pop(float limit, PtTrav &T, const int *stack, const float *stack_t) {
     for (;;) {
         if (T.sp == 0) { T.node = PT_BVH_DONE; return; }
         --T.sp;
-        if (!(stack_t[T.sp] > L.cumu)) break;
+        if (!(stack_t[T.sp] > limit)) break;
     }
     T.node = stack[T.sp];
 }
 
+// The root box: the node to start at, or PT_BVH_DONE.
+RT_HD int bvh_root(float ox, float oy, float oz, float limit, const PtBvh &B, const PtBvhRay &R) {
+    float lb;
+    return bvh_box(ox, oy, oz, limit, R, B.root_lo[0], B.root_hi[0], B.root_lo[1], B.root_hi[1], B.root_lo[2], B.root_hi[2], B.root_hinv, lb) ? B.root : PT_BVH_DONE;
+}
+
 // One inner node: two box tests, descend into the nearer child that may matter, push the other.
-RT_HD void pt_bvh_inner(const PtLane &L, const PtBvh &B, PtTrav &T, int *stack, float *stack_t) {
+RT_HD void bvh_inner(float ox, float oy, float oz, float limit, const PtBvh &B, PtTrav &T, int *stack, float *stack_t) {
     PT_BVH_STAT(g_bvh_inner_visits);
     const int node = T.node;
     const f4 n0 = B.nodes[4 * node], n1 = B.nodes[4 * node + 1], n2 = B.nodes[4 * node + 2], n3 = B.nodes[4 * node + 3];
     float lb0, lb1;
-    const bool h0 = pt_bvh_box(L, T.R, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, n3.z, lb0);
-    const bool h1 = pt_bvh_box(L, T.R, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, n3.w, lb1);
+    const bool h0 = bvh_box(ox, oy, oz, limit, T.R, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, n3.z, lb0);
+    const bool h1 = bvh_box(ox, oy, oz, limit, T.R, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, n3.w, lb1);
     const int c0 = (int)f_bits(n3.x), c1 = (int)f_bits(n3.y);
     if (h0 & h1) {
         const bool swap = lb1 < lb0;                     // nearer child first (any order is correct)
@@ -189,8 +197,9 @@ RT_HD void pt_bvh_inner(const PtLane &L, const PtBvh &B, PtTrav &T, int *stack, 
         stack_t[T.sp++] = swap ? lb0 : lb1;
         T.node = swap ? c1 : c0;
     } else if (h0 | h1) T.node = h0 ? c0 : c1;
-    else pt_bvh_pop(L, T, stack, stack_t);
+    else bvh_pop(limit, T, stack, stack_t);
 }
+RT_HD void pt_bvh_inner(const PtLane &L, const PtBvh &B, PtTrav &T, int *stack, float *stack_t) { bvh_inner(L.ox, L.oy, L.oz, L.cumu, B, T, stack, stack_t); }
 
 // One leaf: its spheres (exact tests), then the next node from the stack.
 template <bool COUNT>
@@ -201,7 +210,7 @@ RT_HD void pt_bvh_leaf(PtLane &L, const PtBvh &B, PtTrav &T, const int *stack, c
 #pragma unroll 1                                         /* rolled: 8 % faster than eight inlined copies of the test (8 KB less code) */
     for (int j = 0; j < count; j++) pt_bvh_sphere<COUNT>(L, B.geom[first + j], B.index[first + j]);
     if (L.phase == PH_SHADOW && L.hit >= 0) { T.node = PT_BVH_DONE; return; }
-    pt_bvh_pop(L, T, stack, stack_t);
+    bvh_pop(L.cumu, T, stack, stack_t);
 }
 
 // One whole query of one lane.  Replaces pt_query_range (tests/devsim; the kernel interleaves the steps of 32 lanes).

@@ -20,11 +20,11 @@ struct PtBvhHost {
     std::vector<f4> geom;
     std::vector<int> index;
     int n_big = 0, root = PT_BVH_NONE, depth = 0;
-    float root_hinv = 0.f, root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0}, eta0 = 0.f;
+    float root_hinv = 0.f, root_lo[3] = {0, 0, 0}, root_hi[3] = {0, 0, 0}, rmax2 = 0.f;
     PtBvh view(const f4 *nodes_p, const f4 *geom_p, const int *index_p) const {
         PtBvh B;
         B.nodes = nodes_p; B.geom = geom_p; B.index = index_p;
-        B.n_big = n_big; B.root = root; B.root_hinv = root_hinv; B.eta0 = eta0;
+        B.n_big = n_big; B.root = root; B.root_hinv = root_hinv; B.rmax2 = rmax2;
         for (int k = 0; k < 3; k++) { B.root_lo[k] = root_lo[k]; B.root_hi[k] = root_hi[k]; }
         return B;
     }
@@ -114,13 +114,15 @@ struct Builder {
 }  // namespace bvh_detail
 
 // geom[i] = (p.x, p.y, p.z, rad*rad) and rad[i] as in PtSoA (colr[i].w).
-inline void build_pt_bvh(const std::vector<f4> &geom, const std::vector<f4> &colr, PtBvhHost &out) {
+// skip (optional): entries with skip[i] != 0 are left out altogether (neither in the tree nor in the always-tested list).
+inline void build_pt_bvh(const std::vector<f4> &geom, const std::vector<f4> &colr, PtBvhHost &out, const std::vector<char> *skip = nullptr) {
     using namespace bvh_detail;
     const int n = (int)geom.size();
     out = PtBvhHost();
     std::vector<double> radii;
     std::vector<char> finite((size_t)n);
     for (int i = 0; i < n; i++) {
+        if (skip && (*skip)[i]) { finite[i] = 0; continue; }
         const double r = std::fabs((double)colr[i].w);
         finite[i] = std::isfinite(geom[i].x) && std::isfinite(geom[i].y) && std::isfinite(geom[i].z) && std::isfinite(geom[i].w) && std::isfinite(r) &&
                     std::fabs(geom[i].x) < 1e15f && std::fabs(geom[i].y) < 1e15f && std::fabs(geom[i].z) < 1e15f && r < 1e15;
@@ -134,6 +136,7 @@ inline void build_pt_bvh(const std::vector<f4> &geom, const std::vector<f4> &col
     std::vector<Item> items;
     std::vector<int> bigs;
     for (int i = 0; i < n; i++) {
+        if (skip && (*skip)[i]) continue;
         const double r = std::fabs((double)colr[i].w);
         // the test reads rad2 = geom.w = fl(rad*rad): its radius is sqrt(rad2); the box also covers the `rad` field
         const double reff = std::sqrt(std::max(0.0, (double)geom[i].w));
@@ -150,7 +153,7 @@ inline void build_pt_bvh(const std::vector<f4> &geom, const std::vector<f4> &col
     if (!items.empty()) {
         double rmax = 0;
         for (const Item &it : items) rmax = std::max(rmax, std::max(it.box.hi[0] - it.c[0], it.rad));
-        out.eta0 = up((2.0 * (double)PT_BVH_MAX_EPS + 12.0 * (double)PT_BVH_U) * rmax * rmax * 2.0);
+        out.rmax2 = up(rmax * rmax * (1.0 + 1e-6));
         Builder B(items, out);
         const Sub root = B.build(0, (int)items.size(), 0);
         out.root = root.code; out.depth = B.max_depth;

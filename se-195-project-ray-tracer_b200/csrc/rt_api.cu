@@ -34,6 +34,11 @@ struct rt_ctx {
     int whitted_sort = 1;                          // cost-sorted work order (scheduling pre-pass)
     int pt_aligned = -1;                           // step-aligned path-tracer warps: -1 by scene size, 0 off, 1 on
     int pt_bvh = -1;                               // exact hierarchy for the sphere queries: -1 by scene size, 0 off, 1 on
+    int w_bvh = -1;                                // the same for the Whitted tracer's non-light spheres
+    bool w_bvh_ready = false;
+    f4 *d_wbnodes = nullptr, *d_wbgeom = nullptr; int *d_wbindex = nullptr, *d_wruns_bvh = nullptr;
+    size_t cap_wbnodes = 0, cap_wbgeom = 0, cap_wbindex = 0, cap_wruns_bvh = 0;
+    std::vector<rt_primitive> w_prims;             // the last uploaded table (the hierarchy is built from it on first use)
     uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
     unsigned *d_wclass = nullptr;
@@ -150,7 +155,8 @@ void rt_destroy(rt_ctx *ctx) {
     if (ctx->peer_ppixels) cudaIpcCloseMemHandle(ctx->peer_ppixels);
     void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
-                     ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex };
+                     ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex,
+                     ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh };
     for (void *b : bufs) if (b) cudaFree(b);
     void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter };
     for (void *b : rbufs) if (b) cudaFree(b);
@@ -203,6 +209,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_WHITTED_COST_ORDER: ctx->whitted_sort = value ? 1 : 0; return RT_OK;
         case RT_TUNE_PT_ALIGNED: if (value < -1 || value > 1) break; ctx->pt_aligned = value; return RT_OK;
         case RT_TUNE_PT_BVH: if (value < -1 || value > 1) break; ctx->pt_bvh = value; return RT_OK;
+        case RT_TUNE_WHITTED_BVH: if (value < -1 || value > 1) break; ctx->w_bvh = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -216,6 +223,8 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(cudaSetDevice(ctx->device));
     WSoA &soa = ctx->w_soa;
     build_w_soa(prims, n, soa);
+    ctx->w_prims.assign(prims, prims + n);
+    ctx->w_bvh_ready = false;
     CK(upload_vec(&ctx->d_wgeom, &ctx->cap_wgeom, soa.geom, ctx->stream));
     CK(upload_vec(&ctx->d_wma, &ctx->cap_wma, soa.mat_a, ctx->stream));
     CK(upload_vec(&ctx->d_wmb, &ctx->cap_wmb, soa.mat_b, ctx->stream));
@@ -268,6 +277,24 @@ int rt_whitted_launch(rt_ctx *ctx) {
     for (int l : ctx->w_soa.lights) if (!(ctx->w_soa.flags[l] & W_FLAG_SPHERE)) p.sphere_lights = 0;
     p.order = nullptr; p.class_counts = nullptr;
     p.n_valid = (uint32_t)p.shard.local_rows * (uint32_t)ctx->w_w;
+    int tree_candidates = 0;
+    for (int i = 0; i < ctx->w_n; i++) tree_candidates += (ctx->w_soa.flags[i] & (W_FLAG_SPHERE | W_FLAG_LIGHT)) == W_FLAG_SPHERE;
+    p.use_bvh = !ctx->counting && (ctx->w_bvh > 0 || (ctx->w_bvh < 0 && tree_candidates >= W_BVH_MIN_SPHERES));
+    if (p.use_bvh) {
+        WSoA &soa = ctx->w_soa;
+        if (!ctx->w_bvh_ready) {           // built from the table of the last rt_whitted_upload, once
+            build_w_bvh(ctx->w_prims.data(), ctx->w_n, soa);
+            CK(upload_vec(&ctx->d_wbnodes, &ctx->cap_wbnodes, soa.bvh.nodes, ctx->stream));
+            CK(upload_vec(&ctx->d_wbgeom, &ctx->cap_wbgeom, soa.bvh.geom, ctx->stream));
+            CK(upload_vec(&ctx->d_wbindex, &ctx->cap_wbindex, soa.bvh.index, ctx->stream));
+            CK(upload_vec(&ctx->d_wruns_bvh, &ctx->cap_wruns_bvh, soa.runs_bvh, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->w_bvh_ready = true;
+        }
+        p.bvh = soa.bvh.view(ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex);
+        F.runs = ctx->d_wruns_bvh; F.n_runs = (int)soa.runs_bvh.size() / 3;
+        if (p.stage_mode == 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
+    } else memset(&p.bvh, 0, sizeof p.bvh);
     if (ctx->whitted_sort && p.n_items) {
         if (p.n_items > ctx->worder_cap) {
             if (ctx->d_worder) cudaFree(ctx->d_worder);

@@ -240,10 +240,12 @@ __device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, const f4 *&s_g
 // 64-slot x 80-byte ray queue in private memory; here the primitives are SoA float4 in shared memory
 // and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
 // NL > 0: the scene has exactly NL lights and all of them are spheres (straight-line shadow set-up, one batch).
-template <bool COUNT, int STAGED, int NL>
+// BVH: the run tables hold only what is not in the hierarchy B (planes, lights, odd spheres); after them every query
+// continues in the tree, lane by lane (whitted_bvh.cuh) -- scenes of hundreds to thousands of spheres.
+template <bool COUNT, int STAGED, int NL, bool BVH>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
-               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters) {
+               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     const f4 *s_geom; const int *s_runs;
@@ -276,10 +278,12 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
         // that hit a surface tests up to three shadow rays at once; then the finished rays are folded into their pixels.
         const bool nq = L.phase == PH_NEAREST;
         w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
+        if (BVH && nq) w_bvh_nearest(L, B);
         if (nq) w_after_nearest<COUNT, NL>(L, F);
         while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
             const bool sq = L.phase == PH_SHADOW;
             w_query_shadow<COUNT>(L, s_geom, s_runs, F.n_runs, sq);
+            if (BVH && sq) w_bvh_shadow(L, B);
             if (sq) w_after_shadow<COUNT, NL>(L, F);
         }
         if (L.phase == PH_FINAL && w_finalize<COUNT>(L, F, queue))
@@ -352,7 +356,7 @@ r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *wo
 // It changes WHEN a pixel is rendered, never what is computed for it.
 #define W_COST_CLASSES 3
 __global__ void __launch_bounds__(W_THREADS)
-whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* W_COST_CLASSES x n_items */, unsigned *class_counts, int staged) {
+whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* W_COST_CLASSES x n_items */, unsigned *class_counts, int staged, int use_bvh, PtBvh B) {
     extern __shared__ f4 s_raw[];
     const f4 *s_geom = F.geom;
     const int *s_runs = F.runs;
@@ -375,6 +379,7 @@ whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* 
         L.qox = L.qoy = L.qoz = 0.f; L.qdx = L.qdy = L.qdz = 0.f;
         if (valid) { L.x = x; L.y = y; L.sub = 4; w_start_subsample(L, F); }
         w_query_nearest<false>(L, s_geom, s_runs, F.n_runs, valid);
+        if (use_bvh && valid) w_bvh_nearest(L, B);
         int cls = W_COST_CLASSES - 1;
         if (valid && L.qhit >= 0) cls = F.mat_b[L.qhit].y > 0.f ? 0 : (F.mat_a[L.qhit].w > 0.f ? 1 : 2);
         const uint32_t below = (1u << lane) - 1u;
@@ -488,13 +493,20 @@ size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode) {
 
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_mode);
-    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *);
-    kern_t k = p.stage_mode == 0 ? (p.count ? whitted_kernel<true, 0, 0> : whitted_kernel<false, 0, 0>)
-             : p.stage_mode == 1 ? (p.count ? whitted_kernel<true, 1, 0> : whitted_kernel<false, 1, 0>)
-             : p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, 2, 3> : whitted_kernel<false, 2, 3>)
-             : p.sphere_lights == 2 ? (p.count ? whitted_kernel<true, 2, 2> : whitted_kernel<false, 2, 2>)
-             : p.sphere_lights == 1 ? (p.count ? whitted_kernel<true, 2, 1> : whitted_kernel<false, 2, 1>)
-                                    : (p.count ? whitted_kernel<true, 2, 0> : whitted_kernel<false, 2, 0>);
+    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *, PtBvh);
+    const bool bvh = p.use_bvh && !p.count;
+    kern_t k;
+    if (bvh) {          // large scenes: tables through L1 / L2 or geometry-only staging, the light count still compiled in
+        const int nl = p.sphere_lights >= 1 && p.sphere_lights <= 3 ? p.sphere_lights : 0;
+        k = p.stage_mode == 0 ? (nl == 3 ? whitted_kernel<false, 0, 3, true> : nl == 2 ? whitted_kernel<false, 0, 2, true> : nl == 1 ? whitted_kernel<false, 0, 1, true> : whitted_kernel<false, 0, 0, true>)
+                              : (nl == 3 ? whitted_kernel<false, 1, 3, true> : nl == 2 ? whitted_kernel<false, 1, 2, true> : nl == 1 ? whitted_kernel<false, 1, 1, true> : whitted_kernel<false, 1, 0, true>);
+    } else
+        k = p.stage_mode == 0 ? (p.count ? whitted_kernel<true, 0, 0, false> : whitted_kernel<false, 0, 0, false>)
+          : p.stage_mode == 1 ? (p.count ? whitted_kernel<true, 1, 0, false> : whitted_kernel<false, 1, 0, false>)
+          : p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, 2, 3, false> : whitted_kernel<false, 2, 3, false>)
+          : p.sphere_lights == 2 ? (p.count ? whitted_kernel<true, 2, 2, false> : whitted_kernel<false, 2, 2, false>)
+          : p.sphere_lights == 1 ? (p.count ? whitted_kernel<true, 2, 1, false> : whitted_kernel<false, 2, 1, false>)
+                                 : (p.count ? whitted_kernel<true, 2, 0, false> : whitted_kernel<false, 2, 0, false>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int nb = blocks_per_sm(k, W_THREADS, smem);
@@ -514,11 +526,11 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         long cgrid = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
         if (cgrid > (long)p.sm_count * 16) cgrid = (long)p.sm_count * 16;
-        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame, p.shard, p.n_items, p.order, p.class_counts, p.stage_mode != 0);
+        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame, p.shard, p.n_items, p.order, p.class_counts, p.stage_mode != 0, bvh ? 1 : 0, p.bvh);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         n_work = p.n_valid;
     }
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
-                                                  p.counters);
+                                                  p.counters, p.bvh);
     return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 #include "whitted_lane.cuh"
 #include "r306_lane.cuh"
 #include "pt_bvh.cuh"
+#include "whitted_bvh.cuh"
 
 // Launch shape (overridable with -D for the A/B builds of tools/variants.sh).
 // smallpt: 128-thread CTAs capped at 64 registers (8 CTAs = 32 warps per SM) measured 6 % faster on Cornell than
@@ -35,6 +36,10 @@
 // Scenes with at least this many spheres walk the hierarchy (RT_TUNE_PT_BVH = -1).
 #ifndef PT_BVH_MIN_SPHERES
 #define PT_BVH_MIN_SPHERES 128
+#endif
+// Whitted scenes with at least this many non-light spheres walk the hierarchy (RT_TUNE_WHITTED_BVH = -1).
+#ifndef W_BVH_MIN_SPHERES
+#define W_BVH_MIN_SPHERES 64
 #endif
 #ifndef W_THREADS
 #define W_THREADS 64
@@ -72,6 +77,8 @@ struct WLaunch {
     uint32_t *order;            // NULL: screen order; else scratch of 3 x n_items entries: one work list per cost class
     unsigned *class_counts;     // 3 x u32 scratch: entries in each list
     uint32_t n_valid;           // pixels owned by this rank (n_items minus the padding of the 8x4 blocks)
+    int use_bvh;                // 1: frame.runs lists only what is not in the hierarchy `bvh`; queries continue in the tree (not for counting launches)
+    rtb::PtBvh bvh;
 };
 
 struct R306Launch {

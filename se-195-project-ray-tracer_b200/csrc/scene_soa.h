@@ -7,6 +7,7 @@
 #include "../../include/rt_b200.h"
 #include "pt_lane.cuh"
 #include "whitted_lane.cuh"
+#include "pt_bvh_build.h"
 
 namespace rtb {
 
@@ -41,6 +42,11 @@ struct WSoA {
     std::vector<int> runs_hot;          // the same runs without primitives that can never be hit (timed launches use these)
     std::vector<float> rrad;
     int n_spheres = 0, n_planes = 0;
+    // large scenes (build_w_bvh): the non-light spheres in the exact hierarchy of pt_bvh.cuh, and the run table of
+    // everything else that can be hit (planes, lights, spheres the tree does not take) -- what every query still walks
+    PtBvhHost bvh;
+    std::vector<int> runs_bvh;
+    int n_tree = 0;
 };
 
 inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
@@ -88,6 +94,32 @@ inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
         out.runs_hot.push_back(i); out.runs_hot.push_back(j - i); out.runs_hot.push_back(out.flags[i]);
         i = j;
     }
+}
+
+// The hierarchy over the non-light spheres of a Whitted scene table, after build_w_soa.  Lights stay in the run table
+// (a shadow ray skips them, RNO:234, and there are few); so do planes and whatever the builder itself keeps out of the tree.
+inline void build_w_bvh(const rt_primitive *p, int n, WSoA &out) {
+    std::vector<f4> g((size_t)n), c((size_t)n);
+    std::vector<char> skip((size_t)n, 1);
+    for (int i = 0; i < n; i++) {
+        g[i] = out.geom[i]; c[i] = f4{0, 0, 0, 0};
+        if ((out.flags[i] & W_FLAG_SPHERE) && !(out.flags[i] & W_FLAG_LIGHT)) { c[i].w = p[i].radius; skip[i] = 0; }
+    }
+    build_pt_bvh(g, c, out.bvh, &skip);
+    std::vector<char> in_tree((size_t)n, 0);
+    for (size_t j = (size_t)out.bvh.n_big; j < out.bvh.index.size(); j++) in_tree[out.bvh.index[j]] = 1;
+    out.n_tree = (int)out.bvh.index.size() - out.bvh.n_big;
+    out.bvh.n_big = 0;                                 // the builder's always-tested spheres join the run table below
+    auto dead = [&](int i) { return !(out.flags[i] & W_FLAG_SPHERE) && out.geom[i].x == 0.f && out.geom[i].y == 0.f && out.geom[i].z == 0.f; };
+    out.runs_bvh.clear();
+    for (int i = 0; i < n;) {
+        if (dead(i) || in_tree[i]) { i++; continue; }
+        int j = i;
+        while (j < n && !dead(j) && !in_tree[j] && out.flags[j] == out.flags[i] && j - i < 32) j++;
+        out.runs_bvh.push_back(i); out.runs_bvh.push_back(j - i); out.runs_bvh.push_back(out.flags[i]);
+        i = j;
+    }
+    if (out.runs_bvh.empty()) { out.runs_bvh.push_back(0); out.runs_bvh.push_back(0); out.runs_bvh.push_back(0); }
 }
 
 static_assert(sizeof(rt_r306_primitive) == 96, "rt_r306_primitive must match the reference Primitive (R306/raytracer.h:24-34)");

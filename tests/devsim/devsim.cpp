@@ -13,6 +13,7 @@
 #include "../../se-195-project-ray-tracer_b200/csrc/scene_soa.h"
 #include "../../se-195-project-ray-tracer_b200/csrc/r306_lane.cuh"
 #include "../../se-195-project-ray-tracer_b200/csrc/pt_bvh_build.h"
+#include "../../se-195-project-ray-tracer_b200/csrc/whitted_bvh.cuh"
 
 using namespace rtb;
 
@@ -47,6 +48,8 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     F.flags = soa.flags.data(); F.lights = soa.lights.data(); F.lcenter = soa.lcenter.data(); F.rrad = soa.rrad.data();
     F.runs = soa.runs.data(); F.n_runs = (int)soa.runs.size() / 3;
     if (use_runs == 2) { F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3; }    // what timed launches walk
+    if (use_runs == 3) { build_w_bvh(prims, n, soa); F.runs = soa.runs_bvh.data(); F.n_runs = (int)soa.runs_bvh.size() / 3; }   // + the hierarchy
+    const PtBvh B = soa.bvh.view(soa.bvh.nodes.data(), soa.bvh.geom.data(), soa.bvh.index.data());
     F.n = n; F.n_lights = (int)soa.lights.size(); F.n_spheres = soa.n_spheres; F.n_planes = soa.n_planes;
     F.w = w; F.h = h;
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
@@ -65,9 +68,11 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
         for (;;) {
             // the body of the kernel's loop, for one lane
             w_query_nearest<true>(L, F.geom, F.runs, F.n_runs, true);
+            if (use_runs == 3) w_bvh_nearest(L, B);
             w_after_nearest<true>(L, F);
             while (L.phase == PH_SHADOW) {
                 w_query_shadow<true>(L, F.geom, F.runs, F.n_runs, true);
+                if (use_runs == 3) w_bvh_shadow(L, B);
                 w_after_shadow<true>(L, F);
             }
             if (w_finalize<true>(L, F, queue)) break;

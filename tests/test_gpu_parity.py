@@ -155,11 +155,52 @@ def test_whitted_on_generated_sphere_scenes(gpu, orc, rt, tmp_path):
     for path, (w, h) in [(str(p), (40, 30)), (None, (64, 48)), (str(p5), (32, 24)), (str(p6), (24, 18))]:
         spheres, cam = rt.read_scene(path, w, h) if path else (load_smallpt_golden(rt, "cornell")[k] for k in ("spheres", "camera"))
         prims = rt.whitted_from_spheres(spheres, cam)
-        px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
         px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
         orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 16, None)
-        assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o), prims.size
+        try:
+            for bvh in (0, 1):      # every primitive in the run tables / the non-light spheres in the exact hierarchy
+                gpu.set_tuning(rt.TUNE_WHITTED_BVH, bvh)
+                px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+                assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o), (prims.size, bvh)
+        finally:
+            gpu.set_tuning(rt.TUNE_WHITTED_BVH, -1)
         assert (px[..., :3].sum(-1) > 0).mean() > 0.15 and len(np.unique(hits)) > 4
+
+
+def test_whitted_hierarchy_equals_run_tables_at_size(gpu, orc, rt, whitted_golden, tmp_path):
+    """The hierarchy against the run tables where the oracle would take minutes: 783 / 3 908 / 19 533 spheres at 320x180, plus
+    walls, three lights, glass and mirrors around the 783-sphere cloud; and the reference's own scene 0 forced through
+    the hierarchy (a tree of seven spheres) still equals the oracle."""
+    for depth in (4, 5, 6):
+        p = tmp_path / f"c{depth}.scn"
+        rt.write_complex_scene(str(p), depth)
+        w, h = 320, 180
+        spheres, cam = rt.read_scene(str(p), w, h)
+        tables = [rt.whitted_from_spheres(spheres, cam)]
+        if depth == 4:
+            box = rt.whitted_create_scene(0)
+            v = np.concatenate([box[[0, 8, 9, 10, 11, 12]], tables[0], box[13:16]])
+            v["m_refl"][10:200:4] = 0.6; v["m_refr"][11:200:4] = 0.8; v["m_refr_index"][11:200:4] = 1.3
+            tables.append(v)
+        try:
+            for k, prims in enumerate(tables):
+                outs = []
+                for bvh in (0, 1):
+                    gpu.set_tuning(rt.TUNE_WHITTED_BVH, bvh)
+                    outs.append(gpu.whitted_render(prims, w, h, want_hit_ids=True))
+                assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0]), (depth, k)
+        finally:
+            gpu.set_tuning(rt.TUNE_WHITTED_BVH, -1)
+    prims = rt.whitted_create_scene(0)
+    w, h = 203, 77
+    px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+    orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, None)
+    try:
+        gpu.set_tuning(rt.TUNE_WHITTED_BVH, 1)
+        px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+    finally:
+        gpu.set_tuning(rt.TUNE_WHITTED_BVH, -1)
+    assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
 
 
 def test_whitted_cost_ordered_schedule_changes_nothing(gpu, rt):

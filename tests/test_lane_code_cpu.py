@@ -216,3 +216,24 @@ def test_bvh_traversal_on_random_clouds(devsim, rt):
             b = _devsim_pt(devsim, integ, scene, cam, 32, 24, 4, seeds, 0)
             for x, y in zip(a, b):
                 assert np.array_equal(x, y), (n, integ)
+
+
+def test_whitted_hierarchy_equals_oracle_on_generated_sphere_scenes(devsim, orc, rt, tmp_path):
+    """The Whitted tracer on .scn sphere scenes with the non-light spheres in the exact hierarchy (whitted_bvh.cuh): pixels
+    and hit IDs equal the oracle's, which tests every primitive -- also with planes, several lights, glass and mirrors."""
+    for depth, w, h in [(3, 48, 36), (4, 40, 30)]:
+        sph, cam = _complex_scene(rt, tmp_path, depth, w, h)
+        prims = rt.whitted_from_spheres(sph, cam)
+        variants = [prims]
+        v = prims.copy()
+        box = rt.whitted_create_scene(0)
+        v = np.concatenate([box[[0, 8, 9, 10, 11, 12]], v, box[13:16]])          # the six walls and the three lights of scene 0 around it
+        v["m_refl"][10:60:4] = 0.6; v["m_refr"][11:60:4] = 0.8; v["m_refr_index"][11:60:4] = 1.3
+        variants.append(v)
+        for k, pv in enumerate(variants):
+            px, hits = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+            devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(pv), pv.size, 0, 1, 8, None, None, 3)
+            px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+            orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(pv), pv.size, 4, None)
+            assert np.array_equal(hits, hits_o), (depth, k)
+            assert np.array_equal(px, px_o), (depth, k)

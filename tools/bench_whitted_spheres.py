@@ -13,10 +13,14 @@ with tempfile.TemporaryDirectory() as d:
         prims = rt.whitted_from_spheres(spheres, cam)
         r.whitted_upload(prims, w, h)
         r.set_counting(True); r.whitted_launch(); c = r.counters(); r.set_counting(False)
-        ts = []
-        for _ in range(3):
-            r.timer_begin(); r.whitted_launch(); ts.append(r.timer_end())
         rays = c["nearest_queries"] + c["shadow_queries"]
         flop = 16.0 * c["sphere_tests"] + 12.0 * c["plane_tests"]
-        print(f"Whitted {prims.size} primitives {w}x{h}: {min(ts):.2f} ms  {rays / min(ts) / 1e3:.0f} Mrays/s  {rays / (w * h):.1f} rays/pixel  {flop / min(ts) / 1e9:.2f} TFLOP/s algorithmic", flush=True)
+        for bvh, name in ((0, "run tables"), (1, "exact hierarchy")):
+            r.set_tuning(rt.TUNE_WHITTED_BVH, bvh)
+            r.whitted_launch(); r.sync()
+            ts = []
+            for _ in range(3):
+                r.timer_begin(); r.whitted_launch(); ts.append(r.timer_end())
+            print(f"Whitted {prims.size} primitives {w}x{h} [{name}]: {min(ts):.2f} ms  {rays / min(ts) / 1e3:.0f} Mrays/s  {rays / (w * h):.1f} rays/pixel  {flop / min(ts) / 1e9:.2f} TFLOP/s reference-equivalent", flush=True)
+        r.set_tuning(rt.TUNE_WHITTED_BVH, -1)
 r.close()
