@@ -189,7 +189,7 @@ pt_bvh_kernel(PtFrame F, PtBvh B, Shard S, uint32_t n_items, float *colors, uint
         } else if (nl > ni) {
             if (leaf) pt_bvh_leaf<false>(L, B, T, stack, stack_t);
         } else {
-            if (inner) pt_bvh_inner(L, B, T, stack, stack_t);
+            if (inner) pt_bvh_inner(L, B, T, stack, stack_t);        // (leaf children tested inside this step instead: 8-25 % slower)
         }
     }
 }
