@@ -277,11 +277,18 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
         // round 1: every lane with a ray finds its nearest hit; round 2 (repeated while lights remain): every lane
         // that hit a surface tests up to three shadow rays at once; then the finished rays are folded into their pixels.
         const bool nq = L.phase == PH_NEAREST;
+#ifdef W_ROUND_STATS      /* debug build: lane participation per round, reported through the counting launch's counters */
+        if (COUNT && lane == 0) { atomicAdd(&counters[0], 32ull); atomicAdd(&counters[1], (unsigned long long)__popc(__ballot_sync(FULL_MASK, nq))); }
+        else if (COUNT) __ballot_sync(FULL_MASK, nq);
+#endif
         w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
         if (BVH && nq) w_bvh_nearest(L, B);
         if (nq) w_after_nearest<COUNT, NL>(L, F);
         while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
             const bool sq = L.phase == PH_SHADOW;
+#ifdef W_ROUND_STATS
+            { const unsigned m = __ballot_sync(FULL_MASK, sq); if (COUNT && lane == 0) { atomicAdd(&counters[2], 32ull); atomicAdd(&counters[3], (unsigned long long)__popc(m)); } }
+#endif
             w_query_shadow<COUNT>(L, s_geom, s_runs, F.n_runs, sq);
             if (BVH && sq) w_bvh_shadow(L, B);
             if (sq) w_after_shadow<COUNT, NL>(L, F);
@@ -290,6 +297,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(L.ar, L.ag, L.ab);
     }
 
+#ifndef W_ROUND_STATS
     if (COUNT) {
         const uint64_t a = warp_sum(L.c_nearest), b = warp_sum(L.c_shadow), c = warp_sum(L.c_sphere_tests),
                        d = warp_sum(L.c_plane_tests), e = warp_sum(L.c_samples);
@@ -299,6 +307,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             atomicAdd(&counters[4], (unsigned long long)e);
         }
     }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -448,7 +448,11 @@ RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
             // A material with neither a diffuse nor a specular term (m_diff <= 0 and m_spec <= 0: glass, mirrors) gathers
             // exactly nothing from any light whatever the shadow rays say (RNO:242-276 skips both terms): no shadow rays.
             // Counting launches still trace them, so that the ray and test counters equal the reference's.
+#ifdef W_ROUND_STATS
+            { const f4 mb = F.mat_b[L.hit]; if (!(mb.x > 0.f) & !(mb.w > 0.f)) return; }
+#else
             if (!COUNT) { const f4 mb = F.mat_b[L.hit]; if (!(mb.x > 0.f) & !(mb.w > 0.f)) return; }
+#endif
 #endif
             if (NL > 0) w_shadow_batch_fixed<NL>(L, F);
             else w_next_shadow_batch(L, F);
