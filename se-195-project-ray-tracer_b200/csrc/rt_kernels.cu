@@ -240,6 +240,63 @@ __device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, const f4 *&s_g
 // 64-slot x 80-byte ray queue in private memory; here the primitives are SoA float4 in shared memory
 // and the FIFO is 32 slots x 48 bytes (the most a breadth-first walk of a depth-5 binary tree holds).
 // NL > 0: the scene has exactly NL lights and all of them are spheres (straight-line shadow set-up, one batch).
+// The tree part of a Whitted query round, warp-synchronous: every lane with a query descends through inner nodes until
+// all of them hold a leaf (or are done), then the leaves are tested together (same results as w_bvh_nearest /
+// w_bvh_blocked, which run one lane to the end).
+__device__ __forceinline__ void w_bvh_nearest_round(WLane &L, const PtBvh &B, bool q) {
+    if (B.root == PT_BVH_NONE) return;
+    int stack[PT_BVH_STACK];
+    float stack_t[PT_BVH_STACK];
+    PtTrav T;
+    T.sp = 0; T.node = PT_BVH_DONE;
+    if (q) { T.R = bvh_ray(L.qox, L.qoy, L.qoz, L.qdx, L.qdy, L.qdz, B); T.node = bvh_root(L.qox, L.qoy, L.qoz, L.cumu, B, T.R); }
+    while (__any_sync(FULL_MASK, T.node != PT_BVH_DONE)) {
+        for (;;) {
+            const bool inner = pt_bvh_at_inner(T);
+            if (!__any_sync(FULL_MASK, inner)) break;
+            if (inner) bvh_inner(L.qox, L.qoy, L.qoz, L.cumu, B, T, stack, stack_t);
+        }
+        if (pt_bvh_at_leaf(T)) {
+            const int code = ~T.node, first = code >> 3, count = (code & 7) + 1;
+#pragma unroll 1
+            for (int j = 0; j < count; j++) w_bvh_sphere_nearest(L, B.geom[first + j], B.index[first + j]);
+            bvh_pop(L.cumu, T, stack, stack_t);
+        }
+    }
+}
+__device__ __forceinline__ void w_bvh_shadow_round(WLane &L, const PtBvh &B, bool q) {
+    if (B.root == PT_BVH_NONE) return;
+    int stack[PT_BVH_STACK];
+    float stack_t[PT_BVH_STACK];
+#pragma unroll 1
+    for (int k = 0; k < W_SHADOW_BATCH; k++) {
+        const bool qk = q && k < L.ns && !((L.sblk >> k) & 1);
+        if (!__any_sync(FULL_MASK, qk)) continue;
+        const float ox = k == 0 ? L.sox[0] : (k == 1 ? L.sox[1] : L.sox[2]), oy = k == 0 ? L.soy[0] : (k == 1 ? L.soy[1] : L.soy[2]);
+        const float oz = k == 0 ? L.soz[0] : (k == 1 ? L.soz[1] : L.soz[2]), dx = k == 0 ? L.slx[0] : (k == 1 ? L.slx[1] : L.slx[2]);
+        const float dy = k == 0 ? L.sly[0] : (k == 1 ? L.sly[1] : L.sly[2]), dz = k == 0 ? L.slz[0] : (k == 1 ? L.slz[1] : L.slz[2]);
+        const float reach = k == 0 ? L.sreach[0] : (k == 1 ? L.sreach[1] : L.sreach[2]);
+        PtTrav T;
+        T.sp = 0; T.node = PT_BVH_DONE;
+        if (qk) { T.R = bvh_ray(ox, oy, oz, dx, dy, dz, B); T.node = bvh_root(ox, oy, oz, reach, B, T.R); }
+        while (__any_sync(FULL_MASK, T.node != PT_BVH_DONE)) {
+            for (;;) {
+                const bool inner = pt_bvh_at_inner(T);
+                if (!__any_sync(FULL_MASK, inner)) break;
+                if (inner) bvh_inner(ox, oy, oz, reach, B, T, stack, stack_t);
+            }
+            if (pt_bvh_at_leaf(T)) {
+                const int code = ~T.node, first = code >> 3, count = (code & 7) + 1;
+                bool blocked = false;
+#pragma unroll 1
+                for (int j = 0; j < count; j++) blocked = blocked | w_bvh_sphere_blocks(ox, oy, oz, dx, dy, dz, reach, B.geom[first + j]);
+                if (blocked) { L.sblk |= 1 << k; T.node = PT_BVH_DONE; }
+                else bvh_pop(reach, T, stack, stack_t);
+            }
+        }
+    }
+}
+
 // BVH: the run tables hold only what is not in the hierarchy B (planes, lights, odd spheres); after them every query
 // continues in the tree, lane by lane (whitted_bvh.cuh) -- scenes of hundreds to thousands of spheres.
 template <bool COUNT, int STAGED, int NL, bool BVH>
@@ -282,7 +339,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
         else if (COUNT) __ballot_sync(FULL_MASK, nq);
 #endif
         w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
-        if (BVH && nq) w_bvh_nearest(L, B);
+        if (BVH) w_bvh_nearest_round(L, B, nq);
         if (nq) w_after_nearest<COUNT, NL>(L, F);
         while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
             const bool sq = L.phase == PH_SHADOW;
@@ -290,7 +347,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             { const unsigned m = __ballot_sync(FULL_MASK, sq); if (COUNT && lane == 0) { atomicAdd(&counters[2], 32ull); atomicAdd(&counters[3], (unsigned long long)__popc(m)); } }
 #endif
             w_query_shadow<COUNT>(L, s_geom, s_runs, F.n_runs, sq);
-            if (BVH && sq) w_bvh_shadow(L, B);
+            if (BVH) w_bvh_shadow_round(L, B, sq);
             if (sq) w_after_shadow<COUNT, NL>(L, F);
         }
         if (L.phase == PH_FINAL && w_finalize<COUNT>(L, F, queue))
