@@ -503,6 +503,34 @@ def test_smallpt_exact_hierarchy_tie_rule_and_mixed_scenes(gpu, rt, tmp_path):
         gpu.set_tuning(rt.TUNE_PT_BVH, -1)
 
 
+def test_hierarchy_forced_on_degenerate_scenes(gpu, orc, rt, cornell):
+    """RT_TUNE_*_BVH = 1 on scenes that give the tree nothing or almost nothing: one and two spheres, the Cornell box (nine
+    spheres, six of them walls 1e5 units wide), a Whitted table without any non-light sphere."""
+    spheres, cam = cornell
+    w, h = 96, 72
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=4)
+    try:
+        for sc in (spheres[8:9], spheres[7:9], spheres):
+            outs = []
+            for bvh in (1, 0):
+                gpu.set_tuning(rt.TUNE_PT_BVH, bvh)
+                gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(sc.copy()); gpu.pt_set_camera(cam)
+                outs.append(gpu.pt_render(0, 3))
+            for k in ("seeds", "colors", "pixels"):
+                assert np.array_equal(outs[0][k].reshape(-1).view(np.uint32), outs[1][k].reshape(-1).view(np.uint32)), (sc.size, k)
+        prims = rt.whitted_create_scene(0)
+        flat = prims[(prims["type"] != 1) | (prims["is_light"] != 0)].copy()            # planes, lights and the blank slot only
+        px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(flat), flat.size, 4, None)
+        gpu.set_tuning(rt.TUNE_WHITTED_BVH, 1)
+        px, hits = gpu.whitted_render(flat, w, h, want_hit_ids=True)
+        assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
+    finally:
+        gpu.set_tuning(rt.TUNE_PT_BVH, -1)
+        gpu.set_tuning(rt.TUNE_WHITTED_BVH, -1)
+
+
 def test_smallpt_exact_hierarchy_sharded_progressive_and_resumed(gpu, rt, tmp_path):
     """The hierarchy kernel behind the same API features as the loop kernel: row-tile shards assemble to the unsharded
     frame, and two progressive calls (2 + 3 passes) equal one call of 5."""
