@@ -116,6 +116,8 @@ enum {
     RT_TUNE_PT_ALIGNED = 4,             /* path tracer: 1 = warps run the shading steps in lock-step, 0 = plain query loop, -1 (default) = by scene size.  Same image either way */
     RT_TUNE_WHITTED_BVH = 6,            /* Whitted tracer: the same hierarchy for the non-light spheres of large scenes (rt_whitted_from_spheres tables); planes,
                                            lights and odd spheres are still tested by every query.  1 / 0 / -1 (default: by scene size).  Same image either way */
+    RT_TUNE_R306_SPLIT = 7,             /* rt_r306_*: 1 (default) = each of a pixel's nine sub-samples is a work unit of its own and a second pass adds them in the
+                                           reference's order; 0 = one pixel per work unit.  Same image either way */
     RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
                                            reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };

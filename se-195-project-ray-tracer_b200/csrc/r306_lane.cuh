@@ -78,6 +78,14 @@ RT_HD void r306_begin_pixel(R306Lane &L, const R306Frame &F, int x, int y) {
     L.q.x = x; L.q.y = y; L.q.sub = 0; L.tr = L.tg = L.tb = 0.f;
     r306_start_subsample(L, F);
 }
+// One sub-sample as a work unit of its own (r306_kernel<SPLIT>): Engine_Render folds each sub-sample's tree into one colour
+// and adds the nine colours to the pixel in order (R306:504-506), so the nine trees are independent computations.  The
+// lane delivers 0 + colour (L.tr after one sub-sample: exactly what the reference's total holds after its first addition)
+// and r306_resolve_kernel adds the nine values in the reference's order.
+RT_HD void r306_begin_subsample(R306Lane &L, const R306Frame &F, int x, int y, int sub) {
+    L.q.x = x; L.q.y = y; L.q.sub = sub; L.tr = L.tg = L.tb = 0.f;
+    r306_start_subsample(L, F);
+}
 
 // powf(v, 20) of R306:172 for v > 0 (glibc's algorithm, rt_math.cuh); a subnormal base underflows to 0 like in glibc.
 RT_HD float r306_pow20(float v) { return v < 0x1p-126f ? 0.f : powf_glibc_unit(v, 20.0f); }
@@ -262,7 +270,7 @@ RT_HD void r306_fold(const R306Frame &F, R306Tree &T, unsigned long long traced)
 }
 
 // Moves on to the next node that is traced (R306:398-465), the next sub-sample, or the end of the pixel (returns true).
-RT_HD bool r306_next_node(R306Lane &L, const R306Frame &F, R306Tree &T) {
+RT_HD bool r306_next_node(R306Lane &L, const R306Frame &F, R306Tree &T, bool one_sub = false) {
     WLane &q = L.q;
     for (;;) {
         const int i = ++L.node;
@@ -282,7 +290,7 @@ RT_HD bool r306_next_node(R306Lane &L, const R306Frame &F, R306Tree &T) {
     r306_fold(F, T, L.traced);
     L.tr = f_add(L.tr, T.col[0][0]); L.tg = f_add(L.tg, T.col[0][1]); L.tb = f_add(L.tb, T.col[0][2]);
     q.sub++;
-    if (q.sub < 9) { r306_start_subsample(L, F); return false; }
+    if (!one_sub && q.sub < 9) { r306_start_subsample(L, F); return false; }
     q.phase = PH_IDLE;
     return true;
 }

@@ -35,6 +35,7 @@ struct rt_ctx {
     int pt_aligned = -1;                           // step-aligned path-tracer warps: -1 by scene size, 0 off, 1 on
     int pt_bvh = -1;                               // exact hierarchy for the sphere queries: -1 by scene size, 0 off, 1 on
     int w_bvh = -1;                                // the same for the Whitted tracer's non-light spheres
+    int r306_split = 1;                            // 3.0.06 frame: one sub-sample per work unit (1) or one pixel (0)
     bool w_bvh_ready = false;
     f4 *d_wbnodes = nullptr, *d_wbgeom = nullptr; int *d_wbindex = nullptr, *d_wruns_bvh = nullptr;
     size_t cap_wbnodes = 0, cap_wbgeom = 0, cap_wbindex = 0, cap_wruns_bvh = 0;
@@ -57,6 +58,7 @@ struct rt_ctx {
         f4 *geom = nullptr, *ma = nullptr, *mb = nullptr; int *flags = nullptr, *lights = nullptr, *runs = nullptr; float *rrad = nullptr, *sx = nullptr, *sy = nullptr; f4 *lcenter = nullptr; size_t cap_lcenter = 0;
         size_t cap_geom = 0, cap_ma = 0, cap_mb = 0, cap_flags = 0, cap_lights = 0, cap_runs = 0, cap_rrad = 0, cap_sx = 0, cap_sy = 0;
         uint32_t *dest = nullptr; size_t dest_cap = 0;
+        float *subcol = nullptr; size_t subcol_cap = 0;      // sub-sample colours (r306_kernel<SPLIT>)
         int w = 0, h = 0, n = 0, nl = 0, nr = 0, ns = 0, np = 0;
         float DX = 0.f, DY = 0.f;
         WSoA soa; std::vector<float> h_sx, h_sy;
@@ -158,7 +160,7 @@ void rt_destroy(rt_ctx *ctx) {
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex,
                      ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh };
     for (void *b : bufs) if (b) cudaFree(b);
-    void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter };
+    void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter, ctx->r306.subcol };
     for (void *b : rbufs) if (b) cudaFree(b);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -210,6 +212,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_PT_ALIGNED: if (value < -1 || value > 1) break; ctx->pt_aligned = value; return RT_OK;
         case RT_TUNE_PT_BVH: if (value < -1 || value > 1) break; ctx->pt_bvh = value; return RT_OK;
         case RT_TUNE_WHITTED_BVH: if (value < -1 || value > 1) break; ctx->w_bvh = value; return RT_OK;
+        case RT_TUNE_R306_SPLIT: ctx->r306_split = value ? 1 : 0; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -378,8 +381,30 @@ int rt_r306_launch(rt_ctx *ctx) {
     p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;
     p.shard = make_shard(R.w, R.h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.dest = R.dest; p.work_counter = ctx->d_work; p.sm_count = ctx->sm_count;
+    p.order = nullptr; p.class_counts = nullptr; p.subcol = nullptr;
+    p.n_valid = (uint32_t)p.shard.local_rows * (uint32_t)R.w;
+    if (ctx->r306_split) {
+        const size_t need = (size_t)R.w * R.h * 27;
+        if (need > R.subcol_cap) {
+            if (R.subcol) cudaFree(R.subcol);
+            R.subcol = nullptr; R.subcol_cap = 0;
+            CK(cudaMalloc((void **)&R.subcol, need * sizeof(float)));
+            R.subcol_cap = need;
+        }
+        p.subcol = R.subcol;
+    }
+    if (ctx->whitted_sort && p.n_items) {
+        if (p.n_items > ctx->worder_cap) {
+            if (ctx->d_worder) cudaFree(ctx->d_worder);
+            ctx->d_worder = nullptr; ctx->worder_cap = 0;
+            CK(cudaMalloc((void **)&ctx->d_worder, 3 * (size_t)p.n_items * sizeof(uint32_t)));
+            ctx->worder_cap = p.n_items;
+        }
+        if (!ctx->d_wclass) CK(cudaMalloc((void **)&ctx->d_wclass, 4 * sizeof(unsigned)));
+        p.order = ctx->d_worder; p.class_counts = ctx->d_wclass;
+    }
     CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
-    if (p.n_items) { CK(rtk_launch_r306(p, ctx->stream)); ctx->launches++; }
+    if (p.n_items) { CK(rtk_launch_r306(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.subcol ? 1 : 0); }
     return RT_OK;
 }
 

@@ -371,8 +371,13 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 // raytracer3.0.06 (BASELINE config 1): the frame of Engine_Render (R306/raytracer.cpp:301-530) on the GPU.  Same shape as
 // the Whitted kernel -- persistent warps, one lane per pixel, a nearest round then batched shadow rounds over the
 // shared-memory scene -- around the 63-node implicit ray tree of r306_lane.cuh, which lives in local memory.
+// SPLIT: the work unit is one SUB-SAMPLE of a pixel (unit u = entry u / 9 of the work list, sub-sample u % 9): the nine ray
+// trees of a pixel are independent, and a pixel behind the glass spheres is 9 x 63 rays traced one after the other -- as one
+// unit it kept a single lane busy for most of the frame (ncu: SMs busy 56 % of the time).  The sub-sample colours go to
+// `subcol`; r306_resolve_kernel adds them in the reference's order and packs the pixel.
+template <bool SPLIT>
 __global__ void __launch_bounds__(W_THREADS)
-r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *work_counter) {
+r306_kernel(R306Frame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride, uint32_t *dest, float *subcol, unsigned *work_counter) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     const f4 *s_geom; const int *s_runs;
@@ -390,7 +395,17 @@ r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *wo
         if (need) {
             if (item < n_items) {
                 int x, y;
-                if (item_to_pixel(S, F.W.w, item, x, y) && y >= F.row0 && y < F.row1) r306_begin_pixel(L, F, x, y);
+                uint32_t it = SPLIT ? item / 9u : item;
+                const int sub = SPLIT ? (int)(item % 9u) : 0;
+                const uint32_t item = it;        // position in the work list
+                if (order) {                     // expensive pixels first (whitted_classify_kernel): the frame no longer ends on the glass spheres
+                    const uint32_t n0 = class_counts[0], n1 = class_counts[1];
+                    it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
+                }
+                if (item_to_pixel(S, F.W.w, it, x, y) && y >= F.row0 && y < F.row1) {
+                    if (SPLIT) r306_begin_subsample(L, F, x, y, sub);
+                    else r306_begin_pixel(L, F, x, y);
+                }
             } else exhausted = true;
         }
         const bool active = L.q.phase != PH_IDLE;
@@ -406,8 +421,25 @@ r306_kernel(R306Frame F, Shard S, uint32_t n_items, uint32_t *dest, unsigned *wo
             if (sq) r306_after_shadow(L, F);
         }
         if (L.q.phase == PH_FINAL) { r306_finish_hit(L, F, T); node_done = true; }
-        if (node_done && r306_next_node(L, F, T))
-            dest[(size_t)L.q.y * F.W.w + L.q.x] = r306_pack_pixel(L.tr, L.tg, L.tb);
+        if (node_done && r306_next_node(L, F, T, SPLIT)) {
+            if (SPLIT) {
+                float *c = subcol + (((size_t)L.q.y * F.W.w + L.q.x) * 9 + (size_t)(L.q.sub - 1)) * 3;
+                c[0] = L.tr; c[1] = L.tg; c[2] = L.tb;
+            } else dest[(size_t)L.q.y * F.W.w + L.q.x] = r306_pack_pixel(L.tr, L.tg, L.tb);
+        }
+    }
+}
+
+// total_acc += the nine sub-sample colours, in order (R306:504-506), then the pixel (R306:512-520).  Rows row0 .. row1-1 of this rank.
+__global__ void r306_resolve_kernel(Shard S, int w, int row0, int row1, uint32_t n_items, const float *subcol, uint32_t *dest) {
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+        int x, y;
+        if (!item_to_pixel(S, w, item, x, y) || y < row0 || y >= row1) continue;
+        const float *c = subcol + ((size_t)y * w + x) * 27;
+        float tr = 0.f, tg = 0.f, tb = 0.f;
+#pragma unroll
+        for (int s = 0; s < 9; s++) { tr = f_add(tr, c[3 * s]); tg = f_add(tg, c[3 * s + 1]); tb = f_add(tb, c[3 * s + 2]); }
+        dest[(size_t)y * w + x] = r306_pack_pixel(tr, tg, tb);
     }
 }
 
@@ -539,15 +571,38 @@ cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigne
 
 cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.W.n, p.frame.W.n_lights, p.frame.W.n_runs, 2);
-    cudaError_t e = cudaFuncSetAttribute(r306_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool split = p.subcol != nullptr;
+    auto kernel = split ? r306_kernel<true> : r306_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int nb = blocks_per_sm(r306_kernel, W_THREADS, smem);
+    int nb = blocks_per_sm(kernel, W_THREADS, smem);
     if (nb < 1) return cudaErrorLaunchOutOfResources;
+    uint32_t n_work = p.n_items;
+    if (p.order) {      // the Whitted pre-pass on the same scene tables (its camera rays differ from Engine_Render's running sums by rounding: fine for a schedule)
+        const size_t csmem = (size_t)p.frame.W.n * sizeof(f4) + (size_t)p.frame.W.n_runs * 3 * sizeof(int) + 16;
+        e = cudaFuncSetAttribute(whitted_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(p.class_counts, 0, W_COST_CLASSES * sizeof(unsigned), stream);
+        if (e != cudaSuccess) return e;
+        long cgrid = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
+        if (cgrid > (long)p.sm_count * 16) cgrid = (long)p.sm_count * 16;
+        PtBvh none;
+        memset(&none, 0, sizeof none);
+        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame.W, p.shard, p.n_items, p.order, p.class_counts, 1, 0, none);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        n_work = p.n_valid;
+    }
+    const uint32_t units = split ? n_work * 9u : n_work;
     long grid = (long)nb * p.sm_count;
-    const long need = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
+    const long need = ((long)units + W_THREADS - 1) / W_THREADS;
     if (grid > need) grid = need > 0 ? need : 1;
-    r306_kernel<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, p.dest, p.work_counter);
-    return cudaGetLastError();
+    kernel<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, units, p.order, p.class_counts, p.n_items, p.dest, p.subcol, p.work_counter);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (split) {
+        r306_resolve_kernel<<<p.sm_count * 8, 256, 0, stream>>>(p.shard, p.frame.W.w, p.frame.row0, p.frame.row1, p.n_items, p.subcol, p.dest);
+        e = cudaGetLastError();
+    }
+    return e;
 }
 
 size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode) {

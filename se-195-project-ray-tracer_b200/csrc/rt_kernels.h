@@ -88,6 +88,10 @@ struct R306Launch {
     uint32_t *dest;
     unsigned *work_counter;
     int sm_count;
+    uint32_t *order;            // as in WLaunch: NULL = screen order, else scratch for the cost-class work lists
+    unsigned *class_counts;
+    uint32_t n_valid;
+    float *subcol;              // NULL: one pixel per work unit; else w*h*9*3 floats of scratch: one sub-sample per work unit + a resolve pass
 };
 
 cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream);

@@ -262,10 +262,15 @@ def test_r306_frame_equals_the_reference(gpu, rt):
     from conftest import GOLDEN, graft
     g = json.load(open(os.path.join(GOLDEN, "r306_golden.json")))
     prims = rt.r306_create_scene()
-    for key, want in g["frames"].items():
-        w, h = (int(v) for v in key.split("x"))
-        img = gpu.r306_render(prims, w, h)
-        assert hashlib.sha256(img.tobytes()).hexdigest() == want, key
+    try:
+        for split in (0, 1):        # one pixel per work unit / one sub-sample per work unit + the in-order resolve pass (the default)
+            gpu.set_tuning(rt.TUNE_R306_SPLIT, split)
+            for key, want in g["frames"].items():
+                w, h = (int(v) for v in key.split("x"))
+                img = gpu.r306_render(prims, w, h)
+                assert hashlib.sha256(img.tobytes()).hexdigest() == want, (key, split)
+    finally:
+        gpu.set_tuning(rt.TUNE_R306_SPLIT, 1)
     want = np.frombuffer(zlib.decompress(open(os.path.join(GOLDEN, "r306_160x120.u32.zlib"), "rb").read()), np.uint32).reshape(120, 160)
     dest = np.full((120, 160), 0xdeadbeef, np.uint32)
     gpu.r306_render(prims, 160, 120, dest=dest)
