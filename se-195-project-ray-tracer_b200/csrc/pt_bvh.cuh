@@ -17,25 +17,30 @@
 //   |det - (B*B - OO + rad2)| <= 12u * OO * max(1, |d|^2) + u * rad2,      B*B - OO = eps*OO - (1+eps)*rho^2,
 // rho = distance from c to the line through o' = c - op (|o' - o| <= u*|op| per component) along d.  Hence det >= 0 needs
 //   rho^2 <= rad2 + eta,   eta = (|eps| + 13u)(1 + 2|eps|) * OO + (2|eps| + 2u) * rad2:
-// the line passes through the sphere inflated to R' = sqrt(rad2 + eta) <= rad + eta / (2*rad).  The accepted distance is
-// fl(b -+ sqrt(det)), which lies within (|eps| + 10u) * |op| of the parametric entry / exit of that inflated sphere.
-// (and <= rad + sqrt(eta): far from the scene eta exceeds rad2 -- the reference's own det is noise there -- and the
-// first bound would grow without need).  A node stores the box of its spheres and hinv = 0.5 / (smallest radius below it);
-// the scene stores the largest radius r_max of the tree.  Per ray, D_k = the largest
-// |root box corner - o| per axis bounds |op_k| of every sphere of the tree (every node's box lies inside the root's), so with
+// the line passes through the sphere inflated to R' = sqrt(rad2 + eta), and R' - rad <= min(eta / (2*rad), sqrt(eta)).
+// (The second bound matters far from the scene, where eta exceeds rad2 -- the reference's own det is rounding noise
+// there, which the hierarchy has to reproduce -- and the first one would swallow the whole tree.)  The accepted distance
+// is fl(b -+ sqrt(det)), which lies within (|eps| + 10u) * |op| of the parametric entry / exit of that inflated sphere.
+//
+// A node stores the box of its spheres and hinv = 0.5 / (smallest radius below it); the scene stores the largest radius
+// r_max of the tree.  Per ray, D_k = the largest |root box corner - o| per axis bounds |op_k| of every sphere of the tree
+// (every node's box lies inside the root's), so with
 //   K1 = 2*e + 34u, K2 = 4*e + 24u  (e = |fl(d.d) - 1| >= |eps| - 4u: TWICE the bounds above),
 //   eta = K1 * (Dx^2+Dy^2+Dz^2) + K2 * r_max^2,
 //   m  = min(eta * hinv, 1.001 * sqrt(eta)) + 1e-6 * (1 + Dx+Dy+Dz)     (the last term covers o' - o and the slab roundings)
 // every sphere below a node that could return d != 0 has its inflated sphere inside the node's box grown by m; the slab
 // test on the grown box yields [te, tx], and no accepted distance below the node is smaller than te - kT*(Dx+Dy+Dz) or
-// larger than tx + kT*(Dx+Dy+Dz), kT = 2*e + 40u.  A node is skipped only if the grown box is missed, lies behind the origin or
-// lies beyond the current limit by those margins; every comparison is written so that a NaN (0 * inf on a slab face)
-// means "visit".  The bounds hold for any |eps| (a direction that is not exactly unit length -- the Whitted tracer's
-// reflections off computed sphere normals are off by ~1e-4 -- just sees slightly larger spheres, which is what the
-// reference's unit-length formula does with it); beyond |eps| = 2^-7 the ray gets K1 = kT = inf and visits everything.  Spheres that are much larger than the rest (the 10 000-unit floor) or not
-// finite are not in the tree at all: they form a short list that every query tests first.
-// tests/: the traversal against the plain loop on the lane simulator (CPU), and against the brute-force kernel on the
-// GPU at full size -- colours, RNG state and pixels bit-identical.
+// larger than tx + kT*(Dx+Dy+Dz), kT = 2*e + 40u.  A node is skipped only if the grown box is missed, lies behind the
+// origin or lies beyond the current limit by those margins; every comparison is written so that a NaN (0 * inf on a slab
+// face) means "visit".  The bounds hold for any |eps|: a direction that is not exactly of unit length -- the Whitted
+// tracer's reflections off computed sphere normals are off by ~1e-4 -- just sees slightly larger spheres, which is what
+// the reference's unit-length formula does with it; beyond |eps| = 2^-7 the ray gets K1 = K2 = kT = inf and visits
+// everything.  Spheres that are much larger than the rest (the 10 000-unit floor) or not finite are not in the tree at
+// all: they form a short list that every query tests first.
+//
+// tests/: the traversal against the plain loop on the lane simulator (CPU), against the brute-force kernel on the GPU at
+// full size, and tools/bvh_fuzz.py (thousands of random scenes; a build without the margin is caught) -- colours, RNG
+// state and pixels bit-identical.
 #pragma once
 #include "pt_lane.cuh"
 
