@@ -118,6 +118,8 @@ enum {
                                            lights and odd spheres are still tested by every query.  1 / 0 / -1 (default: by scene size).  Same image either way */
     RT_TUNE_R306_SPLIT = 7,             /* rt_r306_*: 1 (default) = each of a pixel's nine sub-samples is a work unit of its own and a second pass adds them in the
                                            reference's order; 0 = one pixel per work unit.  Same image either way */
+    RT_TUNE_PT_SINCOS_TABLE = 8,        /* path tracer: 1 (default) = sin / cos of the 2^23 angles 2*pi*GetRandom() can take come from a 64 MB table the device
+                                           fills once with the function it replaces; 0 = computed per call.  Same image either way */
     RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
                                            reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };

@@ -37,6 +37,7 @@ struct PtFrame {
     float inv_w, inv_h;
     int pass0, n_passes;
     int direct_only;                // 0: RadiancePathTracing, 1: RadianceDirectLighting
+    const float *sincos_tab;        // NULL, or 2 x 2^23 floats: (sin, cos) of every angle 2*pi*GetRandom() can be (rt_math.cuh)
     int sum_mode;                   // 1: accumulate sums instead of the running mean (sample-sharded mode)
 };
 
@@ -280,14 +281,16 @@ RT_HD void pt_light_step(PtLane &L, const PtFrame &F) {
     const float lrad = F.colr[lid].w;
     // UniformSampleSphere(GetRandom(), GetRandom(), ..): the reference's compiler evaluates the
     // arguments right to left, so the SECOND argument (u2) takes the first draw.
-    const float u2 = get_random(L.s0, L.s1);
+    uint32_t u2_bits;
+    const float u2 = get_random_bits(L.s0, L.s1, u2_bits);
     const float u1 = get_random(L.s0, L.s1);
     const float zz = f_sub(1.f, f_mul(2.f, u1));
     const float inside = f_sub(1.f, f_mul(zz, zz));
     const float r = f_sqrt(0.f > inside ? 0.f : inside);
     const float phi = f_mul(f_mul(2.f, PT_PI), u2);
     float sn, cs;
-    sincos_glibc(phi, &sn, &cs);
+    if (F.sincos_tab) { sn = F.sincos_tab[2 * u2_bits]; cs = F.sincos_tab[2 * u2_bits + 1]; }     // phi == sincos_table_angle(u2_bits)
+    else sincos_glibc(phi, &sn, &cs);
     const float ux = f_mul(r, cs), uy = f_mul(r, sn), uz = zz;
     const float spx = f_add(f_mul(lrad, ux), lg.x), spy = f_add(f_mul(lrad, uy), lg.y), spz = f_add(f_mul(lrad, uz), lg.z);
     float sx = f_sub(spx, L.ox), sy = f_sub(spy, L.oy), sz = f_sub(spz, L.oz);
@@ -306,8 +309,9 @@ RT_HD void pt_light_step(PtLane &L, const PtFrame &F) {
 }
 
 // Cosine-weighted bounce, SPT/geomfunc.h:243-275.
-RT_HD void pt_diffuse_bounce(PtLane &L) {
-    const float r1 = f_mul(f_mul(2.f, PT_PI), get_random(L.s0, L.s1));
+RT_HD void pt_diffuse_bounce(PtLane &L, const PtFrame &F) {
+    uint32_t r1_bits;
+    const float r1 = f_mul(f_mul(2.f, PT_PI), get_random_bits(L.s0, L.s1, r1_bits));
     const float r2 = get_random(L.s0, L.s1);
     const float r2s = f_sqrt(r2);
     const float wx = L.nlx, wy = L.nly, wz = L.nlz;
@@ -320,7 +324,8 @@ RT_HD void pt_diffuse_bounce(PtLane &L) {
     pt_unit(ux, uy, uz);
     const float vx = f_sub(f_mul(wy, uz), f_mul(wz, uy)), vy = f_sub(f_mul(wz, ux), f_mul(wx, uz)), vz = f_sub(f_mul(wx, uy), f_mul(wy, ux));
     float sn, cs;
-    sincos_glibc(r1, &sn, &cs);
+    if (F.sincos_tab) { sn = F.sincos_tab[2 * r1_bits]; cs = F.sincos_tab[2 * r1_bits + 1]; }
+    else sincos_glibc(r1, &sn, &cs);
     const float ku = f_mul(cs, r2s), kv = f_mul(sn, r2s), kw = f_sqrt(f_sub(1.f, r2));
     L.dx = f_add(f_add(f_mul(ku, ux), f_mul(kv, vx)), f_mul(kw, wx));
     L.dy = f_add(f_add(f_mul(ku, uy), f_mul(kv, vy)), f_mul(kw, wy));
@@ -365,7 +370,7 @@ RT_HD bool pt_advance(PtLane &L, const PtFrame &F) {
     else pt_light_done<COUNT>(L, F);
     while (L.phase == PH_LIGHTS) pt_light_step(L, F);
     if (L.phase == PH_SHADOW) return false;
-    if (L.phase == PH_DIFFUSE) pt_diffuse_bounce(L);
+    if (L.phase == PH_DIFFUSE) pt_diffuse_bounce(L, F);
     if (L.phase == PH_BOUNCE) pt_bounce(L);
     if (L.phase == PH_NEAREST) return false;
     return pt_end_sample<COUNT>(L, F);

@@ -36,6 +36,8 @@ struct rt_ctx {
     int pt_bvh = -1;                               // exact hierarchy for the sphere queries: -1 by scene size, 0 off, 1 on
     int w_bvh = -1;                                // the same for the Whitted tracer's non-light spheres
     int r306_split = 1;                            // 3.0.06 frame: one sub-sample per work unit (1) or one pixel (0)
+    int pt_sincos_table = 1;                       // path tracer: sin / cos of 2*pi*GetRandom() from a 64 MB table (1) or computed (0)
+    float *d_sincos = nullptr;
     bool w_bvh_ready = false;
     f4 *d_wbnodes = nullptr, *d_wbgeom = nullptr; int *d_wbindex = nullptr, *d_wruns_bvh = nullptr;
     size_t cap_wbnodes = 0, cap_wbgeom = 0, cap_wbindex = 0, cap_wruns_bvh = 0;
@@ -158,7 +160,7 @@ void rt_destroy(rt_ctx *ctx) {
     void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex,
-                     ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh };
+                     ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh, ctx->d_sincos };
     for (void *b : bufs) if (b) cudaFree(b);
     void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter, ctx->r306.subcol };
     for (void *b : rbufs) if (b) cudaFree(b);
@@ -213,6 +215,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_PT_BVH: if (value < -1 || value > 1) break; ctx->pt_bvh = value; return RT_OK;
         case RT_TUNE_WHITTED_BVH: if (value < -1 || value > 1) break; ctx->w_bvh = value; return RT_OK;
         case RT_TUNE_R306_SPLIT: ctx->r306_split = value ? 1 : 0; return RT_OK;
+        case RT_TUNE_PT_SINCOS_TABLE: ctx->pt_sincos_table = value ? 1 : 0; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -517,6 +520,15 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
     F.inv_w = 1.f / ctx->p_w; F.inv_h = 1.f / ctx->p_h;          // SPT/smallptCPU.cpp:80-81
     F.pass0 = ctx->current_sample; F.n_passes = n_passes;
     F.direct_only = integrator; F.sum_mode = ctx->sum_mode;
+    F.sincos_tab = nullptr;
+    if (ctx->pt_sincos_table) {
+        if (!ctx->d_sincos) {              // once per context: 2^23 (sin, cos) pairs, 64 MB
+            CK(cudaMalloc((void **)&ctx->d_sincos, (size_t)2 * (1u << 23) * sizeof(float)));
+            CK(rtk_fill_sincos_table(ctx->d_sincos, ctx->sm_count, ctx->stream));
+            ctx->launches++;
+        }
+        F.sincos_tab = ctx->d_sincos;
+    }
     p.shard = make_shard(ctx->p_w, ctx->p_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.colors = ctx->d_colors; p.seeds = ctx->d_seeds; p.pixels = ctx->peer_ppixels ? ctx->peer_ppixels : ctx->d_ppixels;
     p.work_counter = ctx->d_work; p.counters = ctx->d_counters;

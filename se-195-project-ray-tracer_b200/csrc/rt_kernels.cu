@@ -95,7 +95,7 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
                     if (sq) pt_light_done<COUNT>(L, F);
                 }
             }
-            if (L.phase == PH_DIFFUSE) pt_diffuse_bounce(L);
+            if (L.phase == PH_DIFFUSE) pt_diffuse_bounce(L, F);
             if (L.phase == PH_BOUNCE) pt_bounce(L);
             if (L.phase == PH_END && pt_end_sample<COUNT>(L, F)) {
                 const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
@@ -169,7 +169,7 @@ pt_bvh_kernel(PtFrame F, PtBvh B, Shard S, uint32_t n_items, float *colors, uint
             else if (fin && L.phase == PH_SHADOW) pt_light_done<false>(L, F);
             while (__any_sync(FULL_MASK, fin && L.phase == PH_LIGHTS))
                 if (fin && L.phase == PH_LIGHTS) pt_light_step(L, F);             // -> PH_SHADOW (a query), the next light, or past the last one
-            if (fin && L.phase == PH_DIFFUSE) pt_diffuse_bounce(L);
+            if (fin && L.phase == PH_DIFFUSE) pt_diffuse_bounce(L, F);
             if (fin && L.phase == PH_BOUNCE) pt_bounce(L);
             if (fin && L.phase == PH_END && pt_end_sample<false>(L, F)) {
                 const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
@@ -191,6 +191,15 @@ pt_bvh_kernel(PtFrame F, PtBvh B, Shard S, uint32_t n_items, float *colors, uint
         } else {
             if (inner) pt_bvh_inner(L, B, T, stack, stack_t);        // (leaf children tested inside this step instead: 8-25 % slower)
         }
+    }
+}
+
+// The sin / cos table of rt_math.cuh: 2^23 entries made by the function they stand in for.
+__global__ void sincos_table_kernel(float *tab) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (1u << 23); i += gridDim.x * blockDim.x) {
+        float sn, cs;
+        sincos_glibc(sincos_table_angle(i), &sn, &cs);
+        tab[2 * i] = sn; tab[2 * i + 1] = cs;
     }
 }
 
@@ -519,6 +528,11 @@ static int blocks_per_sm(K kernel, int threads, size_t smem) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess) return 0;
     return nb;
+}
+
+cudaError_t rtk_fill_sincos_table(float *tab, int sm_count, cudaStream_t stream) {
+    sincos_table_kernel<<<sm_count * 8, 256, 0, stream>>>(tab);
+    return cudaGetLastError();
 }
 
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {

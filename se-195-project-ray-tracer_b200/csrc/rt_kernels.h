@@ -96,6 +96,7 @@ struct R306Launch {
 
 cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream);
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream);
+cudaError_t rtk_fill_sincos_table(float *tab /* 2 x 2^23 floats */, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);
 size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode);

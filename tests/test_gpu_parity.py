@@ -357,6 +357,25 @@ def test_smallpt_step_aligned_and_plain_schedules_give_the_same_bits(gpu, orc, r
         gpu.set_tuning(rt.TUNE_PT_ALIGNED, 5)
 
 
+def test_smallpt_sincos_table_equals_the_computed_functions(gpu, orc, rt, cornell):
+    """sin / cos of 2*pi*GetRandom() read from the 2^23-entry table (default) or computed per call: same bits, both equal to
+    the oracle; and every table entry equals the device function it replaces."""
+    spheres, cam = cornell
+    w, h = 160, 120
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=12)
+    col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, spheres, cam, w, h, seeds, 6)
+    try:
+        for tab in (0, 1):
+            gpu.set_tuning(rt.TUNE_PT_SINCOS_TABLE, tab)
+            gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+            out = gpu.pt_render(0, 6)
+            assert np.array_equal(out["seeds"], sd_o) and np.array_equal(out["pixels"].reshape(-1), pix_o), tab
+            assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32)), tab
+    finally:
+        gpu.set_tuning(rt.TUNE_PT_SINCOS_TABLE, 1)
+
+
 def test_smallpt_progressive_calls_continue_the_sample_counter(gpu, orc, rt, cornell):
     """UpdateRenderingGPU semantics: repeated calls accumulate; scene/camera/resize reset currentSample."""
     spheres, cam = cornell
