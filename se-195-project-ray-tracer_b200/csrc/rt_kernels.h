@@ -35,7 +35,7 @@
 #endif
 // Scenes with at least this many spheres walk the hierarchy (RT_TUNE_PT_BVH = -1).
 #ifndef PT_BVH_MIN_SPHERES
-#define PT_BVH_MIN_SPHERES 128
+#define PT_BVH_MIN_SPHERES 48          /* measured crossover (tools/ab_threshold.py): 33 spheres 1.28 / 1.24 ms, 48: 1.48 / 1.53, 64: 1.53 / 1.86, 128: 2.04 / 2.72 */
 #endif
 // Whitted scenes with at least this many non-light spheres walk the hierarchy (RT_TUNE_WHITTED_BVH = -1).
 #ifndef W_BVH_MIN_SPHERES
