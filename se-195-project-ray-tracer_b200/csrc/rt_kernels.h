@@ -39,7 +39,7 @@
 #endif
 // Whitted scenes with at least this many non-light spheres walk the hierarchy (RT_TUNE_WHITTED_BVH = -1).
 #ifndef W_BVH_MIN_SPHERES
-#define W_BVH_MIN_SPHERES 64
+#define W_BVH_MIN_SPHERES 24           /* tools/ab_threshold_whitted.py: the reference's scene 1 (59 such spheres) 3.4 / 6.3 ms, its scene 0 (7) 5.0 / 2.9 ms */
 #endif
 #ifndef W_THREADS
 #define W_THREADS 64
