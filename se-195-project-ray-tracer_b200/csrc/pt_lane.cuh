@@ -15,6 +15,7 @@
 namespace rtb {
 
 struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(8) f2 { float x, y; };
 
 enum { PH_IDLE = 0, PH_NEAREST = 1, PH_SHADOW = 2 };
 
@@ -37,7 +38,7 @@ struct PtFrame {
     float inv_w, inv_h;
     int pass0, n_passes;
     int direct_only;                // 0: RadiancePathTracing, 1: RadianceDirectLighting
-    const float *sincos_tab;        // NULL, or 2 x 2^23 floats: (sin, cos) of every angle 2*pi*GetRandom() can be (rt_math.cuh)
+    const f2 *sincos_tab;           // NULL, or 2^23 (sin, cos) pairs: every angle 2*pi*GetRandom() can be (rt_math.cuh)
     int sum_mode;                   // 1: accumulate sums instead of the running mean (sample-sharded mode)
 };
 
@@ -289,7 +290,7 @@ RT_HD void pt_light_step(PtLane &L, const PtFrame &F) {
     const float r = f_sqrt(0.f > inside ? 0.f : inside);
     const float phi = f_mul(f_mul(2.f, PT_PI), u2);
     float sn, cs;
-    if (F.sincos_tab) { sn = F.sincos_tab[2 * u2_bits]; cs = F.sincos_tab[2 * u2_bits + 1]; }     // phi == sincos_table_angle(u2_bits)
+    if (F.sincos_tab) { const f2 t = F.sincos_tab[u2_bits]; sn = t.x; cs = t.y; }     // phi == sincos_table_angle(u2_bits)
     else sincos_glibc(phi, &sn, &cs);
     const float ux = f_mul(r, cs), uy = f_mul(r, sn), uz = zz;
     const float spx = f_add(f_mul(lrad, ux), lg.x), spy = f_add(f_mul(lrad, uy), lg.y), spz = f_add(f_mul(lrad, uz), lg.z);
@@ -324,7 +325,7 @@ RT_HD void pt_diffuse_bounce(PtLane &L, const PtFrame &F) {
     pt_unit(ux, uy, uz);
     const float vx = f_sub(f_mul(wy, uz), f_mul(wz, uy)), vy = f_sub(f_mul(wz, ux), f_mul(wx, uz)), vz = f_sub(f_mul(wx, uy), f_mul(wy, ux));
     float sn, cs;
-    if (F.sincos_tab) { sn = F.sincos_tab[2 * r1_bits]; cs = F.sincos_tab[2 * r1_bits + 1]; }
+    if (F.sincos_tab) { const f2 t = F.sincos_tab[r1_bits]; sn = t.x; cs = t.y; }
     else sincos_glibc(r1, &sn, &cs);
     const float ku = f_mul(cs, r2s), kv = f_mul(sn, r2s), kw = f_sqrt(f_sub(1.f, r2));
     L.dx = f_add(f_add(f_mul(ku, ux), f_mul(kv, vx)), f_mul(kw, wx));

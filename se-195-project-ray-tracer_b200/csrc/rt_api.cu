@@ -527,7 +527,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
             CK(rtk_fill_sincos_table(ctx->d_sincos, ctx->sm_count, ctx->stream));
             ctx->launches++;
         }
-        F.sincos_tab = ctx->d_sincos;
+        F.sincos_tab = (const f2 *)ctx->d_sincos;
     }
     p.shard = make_shard(ctx->p_w, ctx->p_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.colors = ctx->d_colors; p.seeds = ctx->d_seeds; p.pixels = ctx->peer_ppixels ? ctx->peer_ppixels : ctx->d_ppixels;
