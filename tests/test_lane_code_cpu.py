@@ -237,3 +237,28 @@ def test_whitted_hierarchy_equals_oracle_on_generated_sphere_scenes(devsim, orc,
             orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(pv), pv.size, 4, None)
             assert np.array_equal(hits, hits_o), (depth, k)
             assert np.array_equal(px, px_o), (depth, k)
+
+
+def test_hierarchy_builder_on_degenerate_inputs(devsim, rt):
+    """build_pt_bvh: every sphere ends up exactly once in the tree or in the always-tested list, and the depth stays below
+    the traversal stack (64) -- one sphere, a thousand identical ones, NaN / inf / huge entries, a line of 5 000, 200 000
+    random ones."""
+    sph, _ = rt.cornell_scene(32, 24)
+    rs = np.random.RandomState(3)
+
+    def stats(s):
+        st = np.zeros(5, np.int32)
+        devsim.devsim_bvh_stats(vp(s), s.size, vp(st))
+        return st
+
+    one = np.zeros(1, sph.dtype); one["rad"] = 1
+    st = stats(one); assert st[1] == 1 and st[3] < 64
+    same = np.zeros(1000, sph.dtype); same["rad"] = 1; same["p"] = (1, 2, 3)
+    st = stats(same); assert st[1] == 1000 and st[3] < 64 and st[2] == 0
+    odd = np.zeros(100, sph.dtype); odd["rad"] = rs.rand(100) + 0.1; odd["p"] = rs.rand(100, 3) * 10
+    odd["p"][3, 0] = np.nan; odd["rad"][5] = np.inf; odd["p"][7, 1] = 1e30
+    st = stats(odd); assert st[1] == 100 and st[2] >= 3          # the three odd ones are tested by every query
+    line = np.zeros(5000, sph.dtype); line["rad"] = 0.1; line["p"][:, 0] = np.arange(5000)
+    st = stats(line); assert st[1] == 5000 and st[3] < 64
+    big = np.zeros(200000, sph.dtype); big["rad"] = rs.rand(200000) * 0.5 + 0.01; big["p"] = rs.rand(200000, 3) * 1000
+    st = stats(big); assert st[1] == 200000 and st[3] < 64 and st[4] >= 200000 // 8
