@@ -70,6 +70,7 @@ struct rt_ctx {
     bool own_stream = true;
     // path tracer
     int p_w = 0, p_h = 0, p_n = 0, p_nl = 0;
+    size_t p_px_cap = 0;                           // pixels the colour / seed / pixel buffers can hold
     float *d_colors = nullptr;
     uint32_t *d_seeds = nullptr, *d_ppixels = nullptr;
     f4 *d_pgeom = nullptr, *d_pemis = nullptr, *d_pcolr = nullptr;
@@ -440,13 +441,17 @@ int rt_pt_resize(rt_ctx *ctx, int w, int h, const uint32_t *seeds) {
     if (w < 1 || h < 1 || !seeds) return fail(ctx, RT_ERR_ARG, "rt_pt_resize: need w >= 1, h >= 1 and a seed array of 2*w*h values");
     CK(cudaSetDevice(ctx->device));
     const size_t px = (size_t)w * h;
-    if (ctx->d_colors) cudaFree(ctx->d_colors);
-    if (ctx->d_seeds) cudaFree(ctx->d_seeds);
-    if (ctx->d_ppixels) cudaFree(ctx->d_ppixels);
-    ctx->d_colors = nullptr; ctx->d_seeds = nullptr; ctx->d_ppixels = nullptr; ctx->have_size = false;
-    CK(cudaMalloc((void **)&ctx->d_colors, px * 3 * sizeof(float)));
-    CK(cudaMalloc((void **)&ctx->d_seeds, px * 2 * sizeof(uint32_t)));
-    CK(cudaMalloc((void **)&ctx->d_ppixels, px * sizeof(uint32_t)));
+    ctx->have_size = false;
+    if (px > ctx->p_px_cap) {              // the buffers are kept across calls of the same (or a smaller) size
+        if (ctx->d_colors) cudaFree(ctx->d_colors);
+        if (ctx->d_seeds) cudaFree(ctx->d_seeds);
+        if (ctx->d_ppixels) cudaFree(ctx->d_ppixels);
+        ctx->d_colors = nullptr; ctx->d_seeds = nullptr; ctx->d_ppixels = nullptr; ctx->p_px_cap = 0;
+        CK(cudaMalloc((void **)&ctx->d_colors, px * 3 * sizeof(float)));
+        CK(cudaMalloc((void **)&ctx->d_seeds, px * 2 * sizeof(uint32_t)));
+        CK(cudaMalloc((void **)&ctx->d_ppixels, px * sizeof(uint32_t)));
+        ctx->p_px_cap = px;
+    }
     CK(cudaMemsetAsync(ctx->d_colors, 0, px * 3 * sizeof(float), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_ppixels, 0, px * sizeof(uint32_t), ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_seeds, seeds, px * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
