@@ -210,20 +210,25 @@ int rt_sync(rt_ctx *ctx);
 /* CUDA events on the context's stream: begin/end bracket any number of *_launch calls. */
 int rt_timer_begin(rt_ctx *ctx);
 int rt_timer_end(rt_ctx *ctx, float *elapsed_ms);   /* synchronises on the end event */
-/* Kernels launched by this context so far. */
+/* Render-path kernels launched by this context so far (one-time set-up kernels such as table fills are not counted). */
 uint64_t rt_launch_count(const rt_ctx *ctx);
 /* Device addresses of the context's buffers, for collectives issued by the caller (NCCL through
  * torch.distributed in bench.py) -- returns NULL if not allocated.  which: */
 enum { RT_BUF_WHITTED_PIXELS = 0, RT_BUF_WHITTED_HITS = 1, RT_BUF_PT_PIXELS = 2, RT_BUF_PT_COLORS = 3, RT_BUF_PT_SEEDS = 4 };
 void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes);
 /* Fused frame assembly over NVLink (second option): rank 0 exports its pixel buffer as a
- * 64-byte CUDA IPC handle (rt_ipc_export, after rt_whitted_upload / rt_pt_resize); every other rank's process
+ * RT_IPC_HANDLE_BYTES-byte handle (rt_ipc_export, after rt_whitted_upload / rt_pt_resize); every other rank's process
  * imports it (rt_ipc_import) and from then on its render kernel stores the pixels of the rows it owns straight
  * into rank 0's frame through the peer mapping -- the transfer rides inside the kernel, tile by tile, and no
  * gather step exists.  The caller only has to order "all ranks' kernels done" before rank 0 reads the frame
  * (any barrier collective on the render stream).  which: RT_BUF_WHITTED_PIXELS or RT_BUF_PT_PIXELS. */
-int rt_ipc_export(rt_ctx *ctx, int which, unsigned char *handle64);
-int rt_ipc_import(rt_ctx *ctx, int which, const unsigned char *handle64);
+#define RT_IPC_HANDLE_BYTES 80   /* CUDA IPC handle (64) + the exporter's capacity in pixels (8) + a magic word (8) */
+/* Lifetime rules (errors are RT_ERR_STATE): an exported framebuffer is never reallocated -- an upload / resize that would
+ * have to grow it fails until rt_ipc_close has been called (on every rank; it is the caller's collective); an importer
+ * refuses a frame larger than the exporter's capacity, at import and at every later upload / resize; while a mapping is
+ * open, rt_*_download of the PIXELS on the importing rank fails (they live in rank 0's frame). */
+int rt_ipc_export(rt_ctx *ctx, int which, unsigned char *handle /* RT_IPC_HANDLE_BYTES */);
+int rt_ipc_import(rt_ctx *ctx, int which, const unsigned char *handle /* RT_IPC_HANDLE_BYTES */);
 int rt_ipc_close(rt_ctx *ctx);
 /* The context's cudaStream_t as an opaque pointer (for callers that order their own work after it). */
 void *rt_stream(rt_ctx *ctx);

@@ -48,6 +48,7 @@ RT_DIFF_, RT_SPEC_, RT_REFR_ = 0, 1, 2
 RT_OK, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_ARG, RT_ERR_STATE, RT_ERR_CAPACITY, RT_ERR_IO = 0, -1, -2, -3, -4, -5, -6
 TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER, TUNE_PT_ALIGNED, TUNE_PT_BVH, TUNE_WHITTED_BVH, TUNE_R306_SPLIT, TUNE_PT_SINCOS_TABLE = 0, 1, 2, 3, 4, 5, 6, 7, 8
 BUF_WHITTED_PIXELS, BUF_WHITTED_HITS, BUF_PT_PIXELS, BUF_PT_COLORS, BUF_PT_SEEDS = 0, 1, 2, 3, 4
+IPC_HANDLE_BYTES = 80
 
 # Every symbol include/rt_b200.h declares: name -> (restype, argtypes).
 _VP, _I, _U32, _U64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64
@@ -334,7 +335,7 @@ def share_rank0_framebuffer(renderer, which, rank, world):
     if world == 1:
         return False
     dev = torch.device("cuda", torch.cuda.current_device())
-    handle = torch.zeros(64, dtype=torch.uint8, device=dev)
+    handle = torch.zeros(IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
     ok = torch.ones(1, dtype=torch.int32, device=dev)
     if rank == 0:
         try:
@@ -442,13 +443,13 @@ class Renderer:
         return out
 
     def ipc_export(self, which):
-        h = np.zeros(64, np.uint8)
+        h = np.zeros(IPC_HANDLE_BYTES, np.uint8)
         self._ck(self._lib.rt_ipc_export(self._ctx, which, _ptr(h)))
         return h
 
     def ipc_import(self, which, handle):
         h = np.ascontiguousarray(handle, dtype=np.uint8)
-        assert h.size == 64
+        assert h.size == IPC_HANDLE_BYTES
         self._ck(self._lib.rt_ipc_import(self._ctx, which, _ptr(h)))
 
     def ipc_close(self):

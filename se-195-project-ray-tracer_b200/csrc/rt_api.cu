@@ -37,12 +37,15 @@ struct rt_ctx {
     int w_bvh = -1;                                // the same for the Whitted tracer's non-light spheres
     int r306_split = 1;                            // 3.0.06 frame: one sub-sample per work unit (1) or one pixel (0)
     int pt_sincos_table = 1;                       // path tracer: sin / cos of 2*pi*GetRandom() from a 64 MB table (1) or computed (0)
-    float *d_sincos = nullptr;
+    float *d_sincos = nullptr; bool sincos_failed = false;
+    uint64_t setup_launches = 0;                   // one-time set-up kernels (tables); not part of rt_launch_count
     bool w_bvh_ready = false;
     f4 *d_wbnodes = nullptr, *d_wbgeom = nullptr; int *d_wbindex = nullptr, *d_wruns_bvh = nullptr;
     size_t cap_wbnodes = 0, cap_wbgeom = 0, cap_wbindex = 0, cap_wruns_bvh = 0;
     std::vector<rt_primitive> w_prims;             // the last uploaded table (the hierarchy is built from it on first use)
     uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
+    size_t peer_wcap = 0, peer_pcap = 0;           // ... and how many pixels rank 0 said they hold
+    bool exported_w = false, exported_p = false;   // this context's framebuffers are mapped by other processes: never reallocate them
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
     unsigned *d_wclass = nullptr;
     // Whitted
@@ -115,6 +118,22 @@ static cudaError_t upload_vec(T **dptr, size_t *cap, const std::vector<T> &v, cu
     return cudaSuccess;
 }
 
+// The sin / cos table of the path tracer (rt_math.cuh): 2^23 (sin, cos) pairs = 64 MB, filled once per context by the very
+// function it stands in for.  Failing to get the memory is not an error: the kernels then compute the same bits.
+static void ensure_sincos_table(rt_ctx *ctx) {
+    if (!ctx->pt_sincos_table || ctx->d_sincos || ctx->sincos_failed) return;
+    if (cudaMalloc((void **)&ctx->d_sincos, (size_t)2 * (1u << 23) * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();                // clear the sticky-less allocation error
+        ctx->d_sincos = nullptr; ctx->sincos_failed = true;
+        return;
+    }
+    if (rtk_fill_sincos_table(ctx->d_sincos, ctx->sm_count, ctx->stream) != cudaSuccess) {
+        cudaFree(ctx->d_sincos); ctx->d_sincos = nullptr; ctx->sincos_failed = true;
+        return;
+    }
+    ctx->setup_launches++;
+}
+
 extern "C" {
 
 int rt_init(rt_ctx **out, int device) {
@@ -132,7 +151,7 @@ int rt_init(rt_ctx **out, int device) {
     memset(&ctx->cam, 0, sizeof ctx->cam);
     auto bail = [&](cudaError_t err, const char *what) {
         fail(nullptr, RT_ERR_CUDA, "rt_init: %s failed: %s", what, cudaGetErrorString(err));
-        delete ctx;
+        rt_destroy(ctx);               // frees whatever the partial initialisation already holds
         return (int)RT_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
@@ -155,7 +174,7 @@ int rt_init(rt_ctx **out, int device) {
 void rt_destroy(rt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->peer_wpixels) cudaIpcCloseMemHandle(ctx->peer_wpixels);
     if (ctx->peer_ppixels) cudaIpcCloseMemHandle(ctx->peer_ppixels);
     void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
@@ -242,17 +261,24 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(upload_vec(&ctx->d_wruns, &ctx->cap_wruns, soa.runs, ctx->stream));
     CK(upload_vec(&ctx->d_wruns_hot, &ctx->cap_wruns_hot, soa.runs_hot, ctx->stream));
     const size_t px = (size_t)w * h;
+    if (ctx->peer_wpixels && px > ctx->peer_wcap)
+        return fail(ctx, RT_ERR_STATE, "rt_whitted_upload: %dx%d exceeds the %zu pixels of the imported rank-0 framebuffer (rt_ipc_close, then share again)", w, h, ctx->peer_wcap);
     if (px > ctx->w_pixels_cap) {
+        if (ctx->exported_w)
+            return fail(ctx, RT_ERR_STATE, "rt_whitted_upload: the framebuffer (%zu pixels) is mapped by other ranks and cannot grow to %dx%d; rt_ipc_close on every rank first", ctx->w_pixels_cap, w, h);
         if (ctx->d_wpixels) cudaFree(ctx->d_wpixels);
         ctx->d_wpixels = nullptr; ctx->w_pixels_cap = 0;
         CK(cudaMalloc((void **)&ctx->d_wpixels, px * sizeof(uint32_t)));
         ctx->w_pixels_cap = px;
+        // rows another rank owns (rt_set_shard) are never written here: they read back as 0, not as stale device memory
+        CK(cudaMemsetAsync(ctx->d_wpixels, 0, px * sizeof(uint32_t), ctx->stream));
     }
     if (want_hit_ids && px * 9 > ctx->w_hits_cap) {
         if (ctx->d_whits) cudaFree(ctx->d_whits);
         ctx->d_whits = nullptr; ctx->w_hits_cap = 0;
         CK(cudaMalloc((void **)&ctx->d_whits, px * 9 * sizeof(int32_t)));
         ctx->w_hits_cap = px * 9;
+        CK(cudaMemsetAsync(ctx->d_whits, 0xff, px * 9 * sizeof(int32_t), ctx->stream));      // -1 = "no hit" for rows of other ranks
     }
     ctx->w_w = w; ctx->w_h = h; ctx->w_n = n; ctx->w_nl = (int)soa.lights.size();
     ctx->w_ns = soa.n_spheres; ctx->w_np = soa.n_planes; ctx->w_nr = (int)soa.runs.size() / 3; ctx->w_nr_hot = (int)soa.runs_hot.size() / 3; ctx->w_want_hits = want_hit_ids ? 1 : 0;
@@ -278,8 +304,12 @@ int rt_whitted_launch(rt_ctx *ctx) {
     p.pixels = ctx->peer_wpixels ? ctx->peer_wpixels : ctx->d_wpixels;     // fused gather: store straight into rank 0's frame
     p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
     p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
-    p.stage_mode = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 2) <= RTK_WHITTED_STAGE_LIMIT ? 2
-                 : rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, ctx->w_nr, 1) <= RTK_WHITTED_STAGE_LIMIT ? 1 : 0;
+    // sized with the LARGEST run table a launch of this scene may stage (all primitives / without the dead ones / without
+    // what the hierarchy holds: splitting runs can add runs), so that the choice never overshoots the per-CTA budget
+    int nr_max = ctx->w_nr > ctx->w_nr_hot ? ctx->w_nr : ctx->w_nr_hot;
+    if ((int)ctx->w_soa.runs_bvh.size() / 3 > nr_max) nr_max = (int)ctx->w_soa.runs_bvh.size() / 3;
+    p.stage_mode = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, nr_max, 2) <= RTK_WHITTED_STAGE_LIMIT ? 2
+                 : rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, nr_max, 1) <= RTK_WHITTED_STAGE_LIMIT ? 1 : 0;
     p.sphere_lights = ctx->w_nl;
     for (int l : ctx->w_soa.lights) if (!(ctx->w_soa.flags[l] & W_FLAG_SPHERE)) p.sphere_lights = 0;
     p.order = nullptr; p.class_counts = nullptr;
@@ -322,6 +352,8 @@ int rt_whitted_download(rt_ctx *ctx, rt_uchar4 *pixels_out, int32_t *hit_id_out)
     if (!ctx) return RT_ERR_ARG;
     if (!ctx->d_wpixels) return fail(ctx, RT_ERR_STATE, "rt_whitted_download: nothing rendered yet");
     if (hit_id_out && !ctx->w_want_hits) return fail(ctx, RT_ERR_STATE, "rt_whitted_download: hit IDs were not requested at upload");
+    if (pixels_out && ctx->peer_wpixels)
+        return fail(ctx, RT_ERR_STATE, "rt_whitted_download: this rank renders into rank 0's framebuffer (rt_ipc_import); read the frame there, or rt_ipc_close first");
     CK(cudaSetDevice(ctx->device));
     const size_t px = (size_t)ctx->w_w * ctx->w_h;
     if (pixels_out) CK(cudaMemcpyAsync(pixels_out, ctx->d_wpixels, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -348,7 +380,7 @@ int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, in
     auto &R = ctx->r306;
     build_r306_soa(prims, n, R.soa);
     build_r306_screen(w, h, R.h_sx, R.h_sy, &R.DX, &R.DY);
-    if (rtk_whitted_smem_bytes(n, (int)R.soa.lights.size(), (int)R.soa.runs.size() / 3, 2) > (size_t)ctx->max_smem_optin)
+    if (rtk_whitted_smem_bytes(n, (int)R.soa.lights.size(), (int)R.soa.runs_hot.size() / 3, 2) > (size_t)ctx->max_smem_optin)   // the table the launch stages
         return fail(ctx, RT_ERR_CAPACITY, "rt_r306_upload: %d primitives exceed the %d-byte shared-memory staging of this build", n, ctx->max_smem_optin);
     CK(upload_vec(&R.geom, &R.cap_geom, R.soa.geom, ctx->stream));
     CK(upload_vec(&R.ma, &R.cap_ma, R.soa.mat_a, ctx->stream));
@@ -366,6 +398,7 @@ int rt_r306_upload(rt_ctx *ctx, const rt_r306_primitive *prims, int n, int w, in
         R.dest = nullptr; R.dest_cap = 0;
         CK(cudaMalloc((void **)&R.dest, px * sizeof(uint32_t)));
         R.dest_cap = px;
+        CK(cudaMemsetAsync(R.dest, 0, px * sizeof(uint32_t), ctx->stream));      // rows of other ranks read back as 0
     }
     R.w = w; R.h = h; R.n = n; R.nl = (int)R.soa.lights.size(); R.nr = (int)R.soa.runs_hot.size() / 3;
     R.ns = R.soa.n_spheres; R.np = R.soa.n_planes;
@@ -441,6 +474,10 @@ int rt_pt_resize(rt_ctx *ctx, int w, int h, const uint32_t *seeds) {
     if (w < 1 || h < 1 || !seeds) return fail(ctx, RT_ERR_ARG, "rt_pt_resize: need w >= 1, h >= 1 and a seed array of 2*w*h values");
     CK(cudaSetDevice(ctx->device));
     const size_t px = (size_t)w * h;
+    if (ctx->peer_ppixels && px > ctx->peer_pcap)
+        return fail(ctx, RT_ERR_STATE, "rt_pt_resize: %dx%d exceeds the %zu pixels of the imported rank-0 framebuffer (rt_ipc_close, then share again)", w, h, ctx->peer_pcap);
+    if (px > ctx->p_px_cap && ctx->exported_p)
+        return fail(ctx, RT_ERR_STATE, "rt_pt_resize: the framebuffer (%zu pixels) is mapped by other ranks and cannot grow to %dx%d; rt_ipc_close on every rank first", ctx->p_px_cap, w, h);
     ctx->have_size = false;
     if (px > ctx->p_px_cap) {              // the buffers are kept across calls of the same (or a smaller) size
         if (ctx->d_colors) cudaFree(ctx->d_colors);
@@ -457,6 +494,7 @@ int rt_pt_resize(rt_ctx *ctx, int w, int h, const uint32_t *seeds) {
     CK(cudaMemcpyAsync(ctx->d_seeds, seeds, px * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->p_w = w; ctx->p_h = h; ctx->have_size = true; ctx->current_sample = 0;
+    ensure_sincos_table(ctx);              // one-time set-up belongs here, not inside the first timed launch
     return RT_OK;
 }
 
@@ -527,12 +565,8 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
     F.direct_only = integrator; F.sum_mode = ctx->sum_mode;
     F.sincos_tab = nullptr;
     if (ctx->pt_sincos_table) {
-        if (!ctx->d_sincos) {              // once per context: 2^23 (sin, cos) pairs, 64 MB
-            CK(cudaMalloc((void **)&ctx->d_sincos, (size_t)2 * (1u << 23) * sizeof(float)));
-            CK(rtk_fill_sincos_table(ctx->d_sincos, ctx->sm_count, ctx->stream));
-            ctx->launches++;
-        }
-        F.sincos_tab = (const f2 *)ctx->d_sincos;
+        ensure_sincos_table(ctx);          // normally already there (rt_pt_resize)
+        F.sincos_tab = (const f2 *)ctx->d_sincos;      // NULL if the 64 MB could not be had: the kernel then computes the same bits
     }
     p.shard = make_shard(ctx->p_w, ctx->p_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.colors = ctx->d_colors; p.seeds = ctx->d_seeds; p.pixels = ctx->peer_ppixels ? ctx->peer_ppixels : ctx->d_ppixels;
@@ -564,6 +598,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
 int rt_pt_resolve_sums(rt_ctx *ctx, int total_samples) {
     if (!ctx) return RT_ERR_ARG;
     if (!ctx->have_size || total_samples < 1) return fail(ctx, RT_ERR_STATE, "rt_pt_resolve_sums: nothing to resolve");
+    if (ctx->peer_ppixels) return fail(ctx, RT_ERR_STATE, "rt_pt_resolve_sums: the sample-sharded mode keeps a full frame per rank; rt_ipc_close first");
     CK(cudaSetDevice(ctx->device));
     CK(rtk_launch_pt_resolve(ctx->d_colors, ctx->d_ppixels, ctx->p_w, ctx->p_h, 1.f / (float)total_samples, ctx->sm_count, ctx->stream));
     ctx->launches++;
@@ -573,6 +608,8 @@ int rt_pt_resolve_sums(rt_ctx *ctx, int total_samples) {
 int rt_pt_download(rt_ctx *ctx, uint32_t *pixels_out, float *colors_out, uint32_t *seeds_out) {
     if (!ctx) return RT_ERR_ARG;
     if (!ctx->have_size) return fail(ctx, RT_ERR_STATE, "rt_pt_download: rt_pt_resize has not been called");
+    if (pixels_out && ctx->peer_ppixels)
+        return fail(ctx, RT_ERR_STATE, "rt_pt_download: this rank renders its 8-bit pixels into rank 0's framebuffer (rt_ipc_import); read them there, or rt_ipc_close first");
     CK(cudaSetDevice(ctx->device));
     const size_t px = (size_t)ctx->p_w * ctx->p_h;
     if (pixels_out) CK(cudaMemcpyAsync(pixels_out, ctx->d_ppixels, px * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -633,29 +670,43 @@ void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes) {
     return p;
 }
 
-int rt_ipc_export(rt_ctx *ctx, int which, unsigned char *handle64) {
-    if (!ctx || !handle64) return RT_ERR_ARG;
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+// Handle blob: the 64-byte CUDA IPC handle, then the exporter's capacity in pixels (u64) and a magic word (u64), so that an
+// importer can refuse a frame that does not fit instead of storing past the end of rank 0's allocation.
+static const uint64_t RT_IPC_MAGIC = 0x3030326274725f49ull;
+int rt_ipc_export(rt_ctx *ctx, int which, unsigned char *handle) {
+    if (!ctx || !handle) return RT_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64 && RT_IPC_HANDLE_BYTES == 80, "CUDA IPC handle (64 bytes) + capacity + magic");
     void *p = which == RT_BUF_WHITTED_PIXELS ? (void *)ctx->d_wpixels : which == RT_BUF_PT_PIXELS ? (void *)ctx->d_ppixels : nullptr;
     if (!p) return fail(ctx, RT_ERR_STATE, "rt_ipc_export: buffer %d is not allocated (upload / resize first) or cannot be shared", which);
     CK(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, p));
-    memcpy(handle64, &h, 64);
+    const uint64_t cap = which == RT_BUF_WHITTED_PIXELS ? ctx->w_pixels_cap : ctx->p_px_cap;
+    memcpy(handle, &h, 64);
+    memcpy(handle + 64, &cap, 8);
+    memcpy(handle + 72, &RT_IPC_MAGIC, 8);
+    (which == RT_BUF_WHITTED_PIXELS ? ctx->exported_w : ctx->exported_p) = true;    // from now on this allocation must not move
     return RT_OK;
 }
 
-int rt_ipc_import(rt_ctx *ctx, int which, const unsigned char *handle64) {
-    if (!ctx || !handle64) return RT_ERR_ARG;
+int rt_ipc_import(rt_ctx *ctx, int which, const unsigned char *handle) {
+    if (!ctx || !handle) return RT_ERR_ARG;
     if (which != RT_BUF_WHITTED_PIXELS && which != RT_BUF_PT_PIXELS) return fail(ctx, RT_ERR_ARG, "rt_ipc_import: only the pixel buffers can be redirected");
+    uint64_t cap = 0, magic = 0;
+    memcpy(&cap, handle + 64, 8);
+    memcpy(&magic, handle + 72, 8);
+    if (magic != RT_IPC_MAGIC) return fail(ctx, RT_ERR_ARG, "rt_ipc_import: not a handle made by rt_ipc_export (RT_IPC_HANDLE_BYTES = %d bytes)", RT_IPC_HANDLE_BYTES);
+    const size_t mine = which == RT_BUF_WHITTED_PIXELS ? (size_t)ctx->w_w * ctx->w_h : (size_t)ctx->p_w * ctx->p_h;
+    if (mine > cap) return fail(ctx, RT_ERR_STATE, "rt_ipc_import: this rank's frame (%zu pixels) does not fit rank 0's buffer (%llu pixels)", mine, (unsigned long long)cap);
     CK(cudaSetDevice(ctx->device));
     cudaIpcMemHandle_t h;
-    memcpy(&h, handle64, 64);
+    memcpy(&h, handle, 64);
     void *p = nullptr;
     CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
     uint32_t **slot = which == RT_BUF_WHITTED_PIXELS ? &ctx->peer_wpixels : &ctx->peer_ppixels;
     if (*slot) cudaIpcCloseMemHandle(*slot);
     *slot = (uint32_t *)p;
+    (which == RT_BUF_WHITTED_PIXELS ? ctx->peer_wcap : ctx->peer_pcap) = (size_t)cap;
     return RT_OK;
 }
 
@@ -663,8 +714,9 @@ int rt_ipc_close(rt_ctx *ctx) {
     if (!ctx) return RT_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->peer_wpixels) { cudaIpcCloseMemHandle(ctx->peer_wpixels); ctx->peer_wpixels = nullptr; }
-    if (ctx->peer_ppixels) { cudaIpcCloseMemHandle(ctx->peer_ppixels); ctx->peer_ppixels = nullptr; }
+    if (ctx->peer_wpixels) { cudaIpcCloseMemHandle(ctx->peer_wpixels); ctx->peer_wpixels = nullptr; ctx->peer_wcap = 0; }
+    if (ctx->peer_ppixels) { cudaIpcCloseMemHandle(ctx->peer_ppixels); ctx->peer_ppixels = nullptr; ctx->peer_pcap = 0; }
+    ctx->exported_w = ctx->exported_p = false;     // the caller closes on every rank (a collective): nobody maps this context's frame any more
     return RT_OK;
 }
 

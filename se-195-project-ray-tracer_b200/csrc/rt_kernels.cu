@@ -523,11 +523,36 @@ __global__ void selftest_math_kernel(int op, const float *in, void *out, unsigne
 // ------------------------------------------------------------------------------------------------ launchers
 using namespace rtb;
 
+// Launch configuration of one kernel at one dynamic shared-memory size on one device: the opt-in attribute is set and the
+// occupancy queried ONCE, then remembered -- a 3 ms frame should not pay two driver calls per launch for the same answer.
+#include <mutex>
+#include <vector>
+namespace {
+struct KernelCfg { const void *kernel; size_t smem; int threads, device, blocks; };
+std::mutex g_cfg_mutex;
+std::vector<KernelCfg> g_cfg;
+}
 template <typename K>
-static int blocks_per_sm(K kernel, int threads, size_t smem) {
+static cudaError_t configure_kernel(K kernel, int threads, size_t smem, int *blocks) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    for (const KernelCfg &c : g_cfg)
+        if (c.kernel == (const void *)kernel && c.smem == smem && c.threads == threads && c.device == dev) { *blocks = c.blocks; return cudaSuccess; }
+    // the attribute is a per-function MAXIMUM: only ever raised, so that an earlier, larger configuration keeps launching
+    size_t have = 0;
+    bool seen = false;
+    for (const KernelCfg &c : g_cfg)
+        if (c.kernel == (const void *)kernel && c.device == dev) { seen = true; if (c.smem > have) have = c.smem; }
+    if (!seen || smem > have)
+        if ((e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess) return 0;
-    return nb;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem)) != cudaSuccess) return e;
+    if (nb < 1) return cudaErrorLaunchOutOfResources;
+    g_cfg.push_back(KernelCfg{ (const void *)kernel, smem, threads, dev, nb });
+    *blocks = nb;
+    return cudaSuccess;
 }
 
 cudaError_t rtk_fill_sincos_table(float *tab, int sm_count, cudaStream_t stream) {
@@ -537,8 +562,9 @@ cudaError_t rtk_fill_sincos_table(float *tab, int sm_count, cudaStream_t stream)
 
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
     if (p.use_bvh && !p.count) {
-        int nb = blocks_per_sm(pt_bvh_kernel, PT_THREADS, 0);
-        if (nb < 1) return cudaErrorLaunchOutOfResources;
+        int nb = 0;
+        cudaError_t e = configure_kernel(pt_bvh_kernel, PT_THREADS, 0, &nb);
+        if (e != cudaSuccess) return e;
         if (p.max_blocks_per_sm > 0 && nb > p.max_blocks_per_sm) nb = p.max_blocks_per_sm;
         long grid = (long)nb * p.sm_count;
         const long need = ((long)p.n_items + PT_THREADS - 1) / PT_THREADS;
@@ -560,10 +586,9 @@ cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
     kern_t k = chunked ? (p.count ? pt_kernel<true, true, false> : pt_kernel<false, true, false>)
              : aligned ? (p.count ? pt_kernel<true, false, true> : pt_kernel<false, false, true>)
                        : (p.count ? pt_kernel<true, false, false> : pt_kernel<false, false, false>);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0;
+    cudaError_t e = configure_kernel(k, PT_THREADS, smem, &nb);
     if (e != cudaSuccess) return e;
-    int nb = blocks_per_sm(k, PT_THREADS, smem);
-    if (nb < 1) return cudaErrorLaunchOutOfResources;
     if (p.max_blocks_per_sm > 0 && nb > p.max_blocks_per_sm) nb = p.max_blocks_per_sm;
     long grid = (long)nb * p.sm_count;
     const long need = ((long)p.n_items + PT_THREADS - 1) / PT_THREADS;
@@ -587,15 +612,13 @@ cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.W.n, p.frame.W.n_lights, p.frame.W.n_runs, 2);
     const bool split = p.subcol != nullptr;
     auto kernel = split ? r306_kernel<true> : r306_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0, cnb = 0;
+    cudaError_t e = configure_kernel(kernel, W_THREADS, smem, &nb);
     if (e != cudaSuccess) return e;
-    int nb = blocks_per_sm(kernel, W_THREADS, smem);
-    if (nb < 1) return cudaErrorLaunchOutOfResources;
     uint32_t n_work = p.n_items;
     if (p.order) {      // the Whitted pre-pass on the same scene tables (its camera rays differ from Engine_Render's running sums by rounding: fine for a schedule)
         const size_t csmem = (size_t)p.frame.W.n * sizeof(f4) + (size_t)p.frame.W.n_runs * 3 * sizeof(int) + 16;
-        e = cudaFuncSetAttribute(whitted_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
-        if (e != cudaSuccess) return e;
+        if ((e = configure_kernel(whitted_classify_kernel, W_THREADS, csmem, &cnb)) != cudaSuccess) return e;
         e = cudaMemsetAsync(p.class_counts, 0, W_COST_CLASSES * sizeof(unsigned), stream);
         if (e != cudaSuccess) return e;
         long cgrid = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
@@ -642,10 +665,9 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
           : p.sphere_lights == 2 ? (p.count ? whitted_kernel<true, 2, 2, false> : whitted_kernel<false, 2, 2, false>)
           : p.sphere_lights == 1 ? (p.count ? whitted_kernel<true, 2, 1, false> : whitted_kernel<false, 2, 1, false>)
                                  : (p.count ? whitted_kernel<true, 2, 0, false> : whitted_kernel<false, 2, 0, false>);
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int nb = 0, cnb = 0;
+    cudaError_t e = configure_kernel(k, W_THREADS, smem, &nb);
     if (e != cudaSuccess) return e;
-    int nb = blocks_per_sm(k, W_THREADS, smem);
-    if (nb < 1) return cudaErrorLaunchOutOfResources;
     if (p.max_blocks_per_sm > 0 && nb > p.max_blocks_per_sm) nb = p.max_blocks_per_sm;
     long grid = (long)nb * p.sm_count;
     const long need = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
@@ -655,8 +677,7 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         // scheduling pre-pass: order[] = expensive pixels first; the number of valid entries is known on the host
         size_t csmem = p.stage_mode ? (size_t)p.frame.n * sizeof(f4) + (size_t)p.frame.n_runs * 3 * sizeof(int) : 16;
         if (csmem < 16) csmem = 16;
-        e = cudaFuncSetAttribute(whitted_classify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
-        if (e != cudaSuccess) return e;
+        if ((e = configure_kernel(whitted_classify_kernel, W_THREADS, csmem, &cnb)) != cudaSuccess) return e;
         e = cudaMemsetAsync(p.class_counts, 0, W_COST_CLASSES * sizeof(unsigned), stream);
         if (e != cudaSuccess) return e;
         long cgrid = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
