@@ -120,6 +120,9 @@ enum {
                                            reference's order; 0 = one pixel per work unit.  Same image either way */
     RT_TUNE_PT_SINCOS_TABLE = 8,        /* path tracer: 1 (default) = sin / cos of the 2^23 angles 2*pi*GetRandom() can take come from a 64 MB table the device
                                            fills once with the function it replaces; 0 = computed per call.  Same image either way */
+    RT_TUNE_WHITTED_BLOCKS = 9,         /* Whitted tracer, with COST_ORDER on: 1 (default) = pixels whose centre ray meets neither a reflecting nor a refracting
+                                           surface (same cost each) are handed out as whole 8x4 screen blocks per warp, the others pixel by pixel; 0 = all
+                                           pixel by pixel.  Same image either way */
     RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
                                            reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };

@@ -24,7 +24,7 @@ struct rt_ctx {
     char err[512] = {0};
     int shard_rank = 0, shard_world = 1, tile_rows = 8;
     int counting = 0;
-    unsigned *d_work = nullptr;                    // one work counter per launch slot (zeroed before each launch)
+    unsigned *d_work = nullptr;                    // two work counters (items, screen blocks), zeroed before each launch
     unsigned long long *d_counters = nullptr;      // 5 x u64
     uint64_t launches = 0;
     // tuning
@@ -43,10 +43,15 @@ struct rt_ctx {
     f4 *d_wbnodes = nullptr, *d_wbgeom = nullptr; int *d_wbindex = nullptr, *d_wruns_bvh = nullptr;
     size_t cap_wbnodes = 0, cap_wbgeom = 0, cap_wbindex = 0, cap_wruns_bvh = 0;
     std::vector<rt_primitive> w_prims;             // the last uploaded table (the hierarchy is built from it on first use)
+    WCull w_cull, w_cull_bvh;                      // shadow-round cull tables for runs_hot / runs_bvh (scene_soa.h)
+    f2 *d_wpcull = nullptr, *d_wpcull_bvh = nullptr; f4 *d_wrbox = nullptr, *d_wrbox_bvh = nullptr;
+    size_t cap_wpcull = 0, cap_wpcull_bvh = 0, cap_wrbox = 0, cap_wrbox_bvh = 0;
     uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
     size_t peer_wcap = 0, peer_pcap = 0;           // ... and how many pixels rank 0 said they hold
     bool exported_w = false, exported_p = false;   // this context's framebuffers are mapped by other processes: never reallocate them
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
+    uint8_t *d_wcls = nullptr; size_t wcls_cap = 0;
+    int whitted_blocks = 1;                        // class-2 pixels as whole screen blocks per warp (needs whitted_sort)
     unsigned *d_wclass = nullptr;
     // Whitted
     int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_nr = 0, w_want_hits = 0;
@@ -164,7 +169,7 @@ int rt_init(rt_ctx **out, int device) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if ((e = cudaMalloc((void **)&ctx->d_work, sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_work, 2 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_counters, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
     *out = ctx;
@@ -180,7 +185,8 @@ void rt_destroy(rt_ctx *ctx) {
     void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex,
-                     ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh, ctx->d_sincos };
+                     ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh, ctx->d_sincos,
+                     ctx->d_wpcull, ctx->d_wpcull_bvh, ctx->d_wrbox, ctx->d_wrbox_bvh, ctx->d_wcls };
     for (void *b : bufs) if (b) cudaFree(b);
     void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter, ctx->r306.subcol };
     for (void *b : rbufs) if (b) cudaFree(b);
@@ -236,6 +242,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_WHITTED_BVH: if (value < -1 || value > 1) break; ctx->w_bvh = value; return RT_OK;
         case RT_TUNE_R306_SPLIT: ctx->r306_split = value ? 1 : 0; return RT_OK;
         case RT_TUNE_PT_SINCOS_TABLE: ctx->pt_sincos_table = value ? 1 : 0; return RT_OK;
+        case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -260,6 +267,9 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     CK(upload_vec(&ctx->d_wrrad, &ctx->cap_wrrad, soa.rrad, ctx->stream));
     CK(upload_vec(&ctx->d_wruns, &ctx->cap_wruns, soa.runs, ctx->stream));
     CK(upload_vec(&ctx->d_wruns_hot, &ctx->cap_wruns_hot, soa.runs_hot, ctx->stream));
+    build_w_cull(soa, soa.runs_hot, ctx->w_cull);
+    CK(upload_vec(&ctx->d_wpcull, &ctx->cap_wpcull, ctx->w_cull.pcull, ctx->stream));
+    CK(upload_vec(&ctx->d_wrbox, &ctx->cap_wrbox, ctx->w_cull.rbox, ctx->stream));
     const size_t px = (size_t)w * h;
     if (ctx->peer_wpixels && px > ctx->peer_wcap)
         return fail(ctx, RT_ERR_STATE, "rt_whitted_upload: %dx%d exceeds the %zu pixels of the imported rank-0 framebuffer (rt_ipc_close, then share again)", w, h, ctx->peer_wcap);
@@ -300,6 +310,8 @@ int rt_whitted_launch(rt_ctx *ctx) {
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
     F.DX = (WX2 - WX1) / ctx->w_w; F.DY = (WY2 - WY1) / ctx->w_h;
     F.hit_ids = ctx->w_want_hits ? ctx->d_whits : nullptr;
+    if (ctx->counting) { F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; }         // counting launches execute every test
+    else { F.pcull = ctx->d_wpcull; F.rbox = ctx->d_wrbox; F.cull_rp2 = ctx->w_cull.rp2; }   // the tables of runs_hot
     p.shard = make_shard(ctx->w_w, ctx->w_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.pixels = ctx->peer_wpixels ? ctx->peer_wpixels : ctx->d_wpixels;     // fused gather: store straight into rank 0's frame
     p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
@@ -310,9 +322,10 @@ int rt_whitted_launch(rt_ctx *ctx) {
     if ((int)ctx->w_soa.runs_bvh.size() / 3 > nr_max) nr_max = (int)ctx->w_soa.runs_bvh.size() / 3;
     p.stage_mode = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, nr_max, 2) <= RTK_WHITTED_STAGE_LIMIT ? 2
                  : rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, nr_max, 1) <= RTK_WHITTED_STAGE_LIMIT ? 1 : 0;
+    if (p.stage_mode == 2 && ctx->w_n <= W_TAB_CAP && nr_max <= W_TAB_RUNS) p.stage_mode = 3;
     p.sphere_lights = ctx->w_nl;
     for (int l : ctx->w_soa.lights) if (!(ctx->w_soa.flags[l] & W_FLAG_SPHERE)) p.sphere_lights = 0;
-    p.order = nullptr; p.class_counts = nullptr;
+    p.order = nullptr; p.class_counts = nullptr; p.cls = nullptr;
     p.n_valid = (uint32_t)p.shard.local_rows * (uint32_t)ctx->w_w;
     int tree_candidates = 0;
     for (int i = 0; i < ctx->w_n; i++) tree_candidates += (ctx->w_soa.flags[i] & (W_FLAG_SPHERE | W_FLAG_LIGHT)) == W_FLAG_SPHERE;
@@ -325,12 +338,16 @@ int rt_whitted_launch(rt_ctx *ctx) {
             CK(upload_vec(&ctx->d_wbgeom, &ctx->cap_wbgeom, soa.bvh.geom, ctx->stream));
             CK(upload_vec(&ctx->d_wbindex, &ctx->cap_wbindex, soa.bvh.index, ctx->stream));
             CK(upload_vec(&ctx->d_wruns_bvh, &ctx->cap_wruns_bvh, soa.runs_bvh, ctx->stream));
+            build_w_cull(soa, soa.runs_bvh, ctx->w_cull_bvh);
+            CK(upload_vec(&ctx->d_wpcull_bvh, &ctx->cap_wpcull_bvh, ctx->w_cull_bvh.pcull, ctx->stream));
+            CK(upload_vec(&ctx->d_wrbox_bvh, &ctx->cap_wrbox_bvh, ctx->w_cull_bvh.rbox, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             ctx->w_bvh_ready = true;
         }
         p.bvh = soa.bvh.view(ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex);
         F.runs = ctx->d_wruns_bvh; F.n_runs = (int)soa.runs_bvh.size() / 3;
-        if (p.stage_mode == 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
+        F.pcull = ctx->d_wpcull_bvh; F.rbox = ctx->d_wrbox_bvh; F.cull_rp2 = ctx->w_cull_bvh.rp2;
+        if (p.stage_mode >= 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
     } else memset(&p.bvh, 0, sizeof p.bvh);
     if (ctx->whitted_sort && p.n_items) {
         if (p.n_items > ctx->worder_cap) {
@@ -341,8 +358,17 @@ int rt_whitted_launch(rt_ctx *ctx) {
         }
         if (!ctx->d_wclass) CK(cudaMalloc((void **)&ctx->d_wclass, 4 * sizeof(unsigned)));
         p.order = ctx->d_worder; p.class_counts = ctx->d_wclass;
+        if (ctx->whitted_blocks) {
+            if (p.n_items > ctx->wcls_cap) {
+                if (ctx->d_wcls) cudaFree(ctx->d_wcls);
+                ctx->d_wcls = nullptr; ctx->wcls_cap = 0;
+                CK(cudaMalloc((void **)&ctx->d_wcls, p.n_items));
+                ctx->wcls_cap = p.n_items;
+            }
+            p.cls = ctx->d_wcls;
+        }
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += p.order ? 2 : 1; }
     return RT_OK;
@@ -415,6 +441,7 @@ int rt_r306_launch(rt_ctx *ctx) {
     F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.lcenter = R.lcenter; F.runs = R.runs; F.n_runs = R.nr;
     F.rrad = R.rrad; F.n = R.n; F.n_lights = R.nl; F.n_spheres = R.ns; F.n_planes = R.np;
     F.w = R.w; F.h = R.h; F.DX = R.DX; F.DY = R.DY; F.hit_ids = nullptr;
+    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f;
     p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;
     p.shard = make_shard(R.w, R.h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.dest = R.dest; p.work_counter = ctx->d_work; p.sm_count = ctx->sm_count;
@@ -440,7 +467,7 @@ int rt_r306_launch(rt_ctx *ctx) {
         if (!ctx->d_wclass) CK(cudaMalloc((void **)&ctx->d_wclass, 4 * sizeof(unsigned)));
         p.order = ctx->d_worder; p.class_counts = ctx->d_wclass;
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
     if (p.n_items) { CK(rtk_launch_r306(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.subcol ? 1 : 0); }
     return RT_OK;
 }
@@ -588,7 +615,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
         }
         p.bvh = ctx->p_bvh.view(ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex);
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches++; }
     ctx->current_sample += n_passes;

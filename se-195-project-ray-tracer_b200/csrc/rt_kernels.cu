@@ -214,32 +214,62 @@ __global__ void pt_resolve_kernel(const float *colors, uint32_t *pixels, int w, 
 }
 
 // Stages the scene tables of a WFrame into shared memory and redirects the frame's pointers to the copies.
-// layout: geom[n] | mat_a[n] | mat_b[n] (MODE 2) | flags[n] | runs[3*n_runs] | rrad[n] (MODE 2) | lights[n_lights] (MODE 2)
+// layout: geom[n] | mat_a[n] | mat_b[n] | rbox[2*n_runs] (MODE 2) | pcull[n] (MODE 2) | flags[n] | runs[3*n_runs] | rrad[n] (MODE 2) | lights[n_lights] (MODE 2)
 // MODE 2: everything on chip (small scenes; the compiler then knows the material pointers are shared-memory pointers:
 // LDS instead of generic loads).  MODE 1: geometry, flags and runs only.  MODE 0: nothing is staged -- a scene larger
 // than the per-CTA share of shared memory is read through L1 / L2 (every lane of a warp reads the same record).
+// MODE 3: like 2, for scenes of at most W_TAB_CAP primitives in at most W_TAB_RUNS runs (the reference's scenes): the tables sit in a
+// STATIC shared-memory struct, so every table address is a compile-time constant -- with the dynamic layout of mode 2 the
+// offsets depend on n, and under the register cap the compiler re-derived them at every use (7 % of the executed
+// instructions of the 1080p frame were that address arithmetic, plus an S2R / LEA per loop iteration).
+struct WTables {
+    f4 geom[W_TAB_CAP], ma[W_TAB_CAP], mb[W_TAB_CAP], rbox[2 * W_TAB_RUNS];
+    f2 pcull[W_TAB_CAP];
+    float rrad[W_TAB_CAP];
+    int flags[W_TAB_CAP], lights[W_TAB_CAP], runs[3 * W_TAB_RUNS];
+};
 template <int MODE>
 __device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, const f4 *&s_geom_out, const int *&s_runs_out) {
     if (MODE == 0) { s_geom_out = F.geom; s_runs_out = F.runs; return; }
+    if (MODE == 3) {
+        __shared__ WTables T;
+        const bool cull = F.pcull != nullptr;
+        for (int i = threadIdx.x; i < F.n; i += blockDim.x) {
+            T.geom[i] = F.geom[i]; T.ma[i] = F.mat_a[i]; T.mb[i] = F.mat_b[i]; T.rrad[i] = F.rrad[i]; T.flags[i] = F.flags[i];
+            if (cull) T.pcull[i] = F.pcull[i];
+        }
+        for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) T.runs[i] = F.runs[i];
+        for (int i = threadIdx.x; i < F.n_lights; i += blockDim.x) T.lights[i] = F.lights[i];
+        if (cull) for (int i = threadIdx.x; i < 2 * F.n_runs; i += blockDim.x) T.rbox[i] = F.rbox[i];
+        __syncthreads();
+        F.geom = T.geom; F.mat_a = T.ma; F.mat_b = T.mb; F.rrad = T.rrad; F.flags = T.flags; F.lights = T.lights;
+        if (cull) { F.pcull = T.pcull; F.rbox = T.rbox; }
+        s_geom_out = T.geom; s_runs_out = T.runs;
+        return;
+    }
     const int n = F.n;
     f4 *s_geom = s_raw;
-    f4 *s_ma = s_geom + n, *s_mb = s_ma + n;
-    int *ibase = MODE == 2 ? (int *)(s_mb + n) : (int *)(s_geom + n);
+    f4 *s_ma = s_geom + n, *s_mb = s_ma + n, *s_box = s_mb + n;
+    f2 *s_pc = (f2 *)(s_box + 2 * F.n_runs);
+    int *ibase = MODE == 2 ? (int *)(s_pc + n) : (int *)(s_geom + n);
     int *s_flags = ibase;
     int *s_runs = ibase + n;
     float *s_rr = (float *)(s_runs + 3 * F.n_runs);
     int *s_li = (int *)(s_rr + n);
+    const bool cull = MODE == 2 && F.pcull != nullptr;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         s_geom[i] = F.geom[i];
         s_flags[i] = F.flags[i];
-        if (MODE == 2) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; }
+        if (MODE == 2) { s_ma[i] = F.mat_a[i]; s_mb[i] = F.mat_b[i]; s_rr[i] = F.rrad[i]; if (cull) s_pc[i] = F.pcull[i]; }
     }
     for (int i = threadIdx.x; i < 3 * F.n_runs; i += blockDim.x) s_runs[i] = F.runs[i];
-    if (MODE == 2)
+    if (MODE == 2) {
         for (int i = threadIdx.x; i < F.n_lights; i += blockDim.x) s_li[i] = F.lights[i];
+        if (cull) for (int i = threadIdx.x; i < 2 * F.n_runs; i += blockDim.x) s_box[i] = F.rbox[i];
+    }
     __syncthreads();
     F.geom = s_geom; F.flags = s_flags;
-    if (MODE == 2) { F.mat_a = s_ma; F.mat_b = s_mb; F.rrad = s_rr; F.lights = s_li; }
+    if (MODE == 2) { F.mat_a = s_ma; F.mat_b = s_mb; F.rrad = s_rr; F.lights = s_li; if (cull) { F.pcull = s_pc; F.rbox = s_box; } }
     s_geom_out = s_geom; s_runs_out = s_runs;
 }
 
@@ -311,7 +341,7 @@ __device__ __forceinline__ void w_bvh_shadow_round(WLane &L, const PtBvh &B, boo
 template <bool COUNT, int STAGED, int NL, bool BVH>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
-               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B) {
+               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B, const uint8_t *cls) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     const f4 *s_geom; const int *s_runs;
@@ -322,12 +352,21 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
     L.phase = PH_IDLE;
     L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_sphere_tests = L.c_plane_tests = 0;
     bool exhausted = false;
+    // Two ways of handing out pixels (see whitted_classify_kernel).  Pixels of classes 0 and 1 (a refracting / reflecting
+    // surface behind the centre ray: ray trees of very different sizes) go to single lanes, each lane taking the next one
+    // when it is done.  Pixels of class 2 (everything else, most of the frame: 9 primary rays + their shadow rays, the same
+    // cost for every pixel) are handed out as whole 8x4 SCREEN BLOCKS to whole warps once the lists are empty: a warp whose
+    // 32 rays run side by side hits the same few primitives, so the votes in front of the square roots / divisions and
+    // the shadow-round culls decide for the warp what they decide for a lane (with single-lane refill a warp soon holds 32
+    // unrelated pixels).  `cls` == NULL: lists only.
+    const uint32_t n_lane_items = (order && cls) ? class_counts[0] + class_counts[1] : n_items;
+    const uint32_t n_blocks = cls ? n_stride >> 5 : 0u;
 
     for (;;) {
         const bool need = (L.phase == PH_IDLE) && !exhausted;
         const uint32_t item = fetch_items(work_counter, need, lane);
         if (need) {
-            if (item < n_items) {
+            if (item < n_lane_items) {
                 int x, y;
                 uint32_t it = item;
                 if (order) {                     // walk the cost classes in turn (see whitted_classify_kernel)
@@ -337,8 +376,18 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
                 if (item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
             } else exhausted = true;
         }
-        const bool active = L.phase != PH_IDLE;
-        if (!__any_sync(FULL_MASK, active || !exhausted)) break;
+        if (!__any_sync(FULL_MASK, L.phase != PH_IDLE || !exhausted)) {
+            // every lane is idle and the lists are empty: the next block of class-2 pixels, for the whole warp
+            if (!cls) break;
+            uint32_t blk = 0;
+            if (lane == 0) blk = atomicAdd(work_counter + 1, 1u);
+            blk = __shfl_sync(FULL_MASK, blk, 0);
+            if (blk >= n_blocks) break;
+            const uint32_t it = blk * 32u + lane;
+            int x, y;
+            if (cls[it] == 2 && item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
+            if (!__any_sync(FULL_MASK, L.phase != PH_IDLE)) continue;       // a block without such pixels
+        }
 
         // round 1: every lane with a ray finds its nearest hit; round 2 (repeated while lights remain): every lane
         // that hit a surface tests up to three shadow rays at once; then the finished rays are folded into their pixels.
@@ -355,7 +404,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 #ifdef W_ROUND_STATS
             { const unsigned m = __ballot_sync(FULL_MASK, sq); if (COUNT && lane == 0) { atomicAdd(&counters[2], 32ull); atomicAdd(&counters[3], (unsigned long long)__popc(m)); } }
 #endif
-            w_query_shadow<COUNT>(L, s_geom, s_runs, F.n_runs, sq);
+            w_query_shadow<COUNT, (NL > 0 && !COUNT)>(L, s_geom, s_runs, F.n_runs, sq, F.pcull, F.rbox);     // NL > 0: the host made the cull tables
             if (BVH) w_bvh_shadow_round(L, B, sq);
             if (sq) w_after_shadow<COUNT, NL>(L, F);
         }
@@ -384,13 +433,13 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 // trees of a pixel are independent, and a pixel behind the glass spheres is 9 x 63 rays traced one after the other -- as one
 // unit it kept a single lane busy for most of the frame (ncu: SMs busy 56 % of the time).  The sub-sample colours go to
 // `subcol`; r306_resolve_kernel adds them in the reference's order and packs the pixel.
-template <bool SPLIT>
+template <bool SPLIT, int STAGED = 3>
 __global__ void __launch_bounds__(W_THREADS)
 r306_kernel(R306Frame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride, uint32_t *dest, float *subcol, unsigned *work_counter) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     const f4 *s_geom; const int *s_runs;
-    stage_scene<2>(F.W, s_raw, s_geom, s_runs);
+    stage_scene<STAGED>(F.W, s_raw, s_geom, s_runs);
 
     R306Tree T;
     R306Lane L;
@@ -463,7 +512,8 @@ __global__ void r306_resolve_kernel(Shard S, int w, int row0, int row1, uint32_t
 // It changes WHEN a pixel is rendered, never what is computed for it.
 #define W_COST_CLASSES 3
 __global__ void __launch_bounds__(W_THREADS)
-whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* W_COST_CLASSES x n_items */, unsigned *class_counts, int staged, int use_bvh, PtBvh B) {
+whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* W_COST_CLASSES x n_items */, unsigned *class_counts, int staged, int use_bvh, PtBvh B,
+                        uint8_t *cls_out /* NULL, or n_items bytes: the class of every item (255: padding); class 2 then gets no list */) {
     extern __shared__ f4 s_raw[];
     const f4 *s_geom = F.geom;
     const int *s_runs = F.runs;
@@ -490,8 +540,10 @@ whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* 
         int cls = W_COST_CLASSES - 1;
         if (valid && L.qhit >= 0) cls = F.mat_b[L.qhit].y > 0.f ? 0 : (F.mat_a[L.qhit].w > 0.f ? 1 : 2);
         const uint32_t below = (1u << lane) - 1u;
+        if (cls_out && item < n_items) cls_out[item] = valid ? (uint8_t)cls : (uint8_t)255;
 #pragma unroll
         for (int c = 0; c < W_COST_CLASSES; c++) {
+            if (cls_out && c == W_COST_CLASSES - 1) break;          // handed out by blocks, not from a list
             const uint32_t m = __ballot_sync(FULL_MASK, valid && cls == c);
             uint32_t b0 = 0;
             if (lane == 0 && m) b0 = atomicAdd(&class_counts[c], (unsigned)__popc(m));
@@ -609,9 +661,10 @@ cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigne
 }
 
 cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
-    const size_t smem = rtk_whitted_smem_bytes(p.frame.W.n, p.frame.W.n_lights, p.frame.W.n_runs, 2);
+    const bool fixed = p.frame.W.n <= W_TAB_CAP && p.frame.W.n_runs <= W_TAB_RUNS;
+    const size_t smem = rtk_whitted_smem_bytes(p.frame.W.n, p.frame.W.n_lights, p.frame.W.n_runs, fixed ? 3 : 2);
     const bool split = p.subcol != nullptr;
-    auto kernel = split ? r306_kernel<true> : r306_kernel<false>;
+    auto kernel = fixed ? (split ? r306_kernel<true, 3> : r306_kernel<false, 3>) : (split ? r306_kernel<true, 2> : r306_kernel<false, 2>);
     int nb = 0, cnb = 0;
     cudaError_t e = configure_kernel(kernel, W_THREADS, smem, &nb);
     if (e != cudaSuccess) return e;
@@ -625,7 +678,7 @@ cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
         if (cgrid > (long)p.sm_count * 16) cgrid = (long)p.sm_count * 16;
         PtBvh none;
         memset(&none, 0, sizeof none);
-        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame.W, p.shard, p.n_items, p.order, p.class_counts, 1, 0, none);
+        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame.W, p.shard, p.n_items, p.order, p.class_counts, 1, 0, none, nullptr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         n_work = p.n_valid;
     }
@@ -643,15 +696,15 @@ cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream) {
 }
 
 size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode) {
-    if (stage_mode == 0) return 16;
+    if (stage_mode == 0 || stage_mode == 3) return 16;          // 3: static shared memory, nothing dynamic
     size_t b = (size_t)n * (sizeof(f4) + sizeof(int)) + (size_t)n_runs * 3 * sizeof(int);
-    if (stage_mode == 2) b += (size_t)n * (2 * sizeof(f4) + sizeof(float)) + (size_t)n_lights * sizeof(int);
+    if (stage_mode == 2) b += (size_t)n * (2 * sizeof(f4) + sizeof(f2) + sizeof(float)) + (size_t)n_runs * 2 * sizeof(f4) + (size_t)n_lights * sizeof(int);
     return b < 16 ? 16 : b;
 }
 
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_mode);
-    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *, PtBvh);
+    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *, PtBvh, const uint8_t *);
     const bool bvh = p.use_bvh && !p.count;
     kern_t k;
     if (bvh) {          // large scenes: tables through L1 / L2 or geometry-only staging, the light count still compiled in
@@ -661,6 +714,10 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     } else
         k = p.stage_mode == 0 ? (p.count ? whitted_kernel<true, 0, 0, false> : whitted_kernel<false, 0, 0, false>)
           : p.stage_mode == 1 ? (p.count ? whitted_kernel<true, 1, 0, false> : whitted_kernel<false, 1, 0, false>)
+          : p.stage_mode == 3 ? (p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, 3, 3, false> : whitted_kernel<false, 3, 3, false>)
+                               : p.sphere_lights == 2 ? (p.count ? whitted_kernel<true, 3, 2, false> : whitted_kernel<false, 3, 2, false>)
+                               : p.sphere_lights == 1 ? (p.count ? whitted_kernel<true, 3, 1, false> : whitted_kernel<false, 3, 1, false>)
+                                                      : (p.count ? whitted_kernel<true, 3, 0, false> : whitted_kernel<false, 3, 0, false>))
           : p.sphere_lights == 3 ? (p.count ? whitted_kernel<true, 2, 3, false> : whitted_kernel<false, 2, 3, false>)
           : p.sphere_lights == 2 ? (p.count ? whitted_kernel<true, 2, 2, false> : whitted_kernel<false, 2, 2, false>)
           : p.sphere_lights == 1 ? (p.count ? whitted_kernel<true, 2, 1, false> : whitted_kernel<false, 2, 1, false>)
@@ -682,11 +739,11 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         long cgrid = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
         if (cgrid > (long)p.sm_count * 16) cgrid = (long)p.sm_count * 16;
-        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame, p.shard, p.n_items, p.order, p.class_counts, p.stage_mode != 0, bvh ? 1 : 0, p.bvh);
+        whitted_classify_kernel<<<(unsigned)cgrid, W_THREADS, csmem, stream>>>(p.frame, p.shard, p.n_items, p.order, p.class_counts, p.stage_mode != 0, bvh ? 1 : 0, p.bvh, p.cls);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         n_work = p.n_valid;
     }
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
-                                                  p.counters, p.bvh);
+                                                  p.counters, p.bvh, p.order ? p.cls : nullptr);
     return cudaGetLastError();
 }

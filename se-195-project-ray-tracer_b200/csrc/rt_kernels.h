@@ -72,10 +72,11 @@ struct WLaunch {
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
     int count, sm_count, max_blocks_per_sm;
-    int stage_mode;             // 2: scene tables + materials in shared memory, 1: geometry / flags / runs only, 0: read through L1 / L2
+    int stage_mode;             // 3: all tables in static shared memory (small scenes), 2: all tables in dynamic shared memory, 1: geometry / flags / runs only, 0: read through L1 / L2
     int sphere_lights;          // number of lights when all of them are spheres, else 0
     uint32_t *order;            // NULL: screen order; else scratch of 3 x n_items entries: one work list per cost class
     unsigned *class_counts;     // 3 x u32 scratch: entries in each list
+    uint8_t *cls;               // NULL, or n_items bytes of scratch: the class of every item; class-2 pixels are then handed out as 8x4 blocks to whole warps
     uint32_t n_valid;           // pixels owned by this rank (n_items minus the padding of the 8x4 blocks)
     int use_bvh;                // 1: frame.runs lists only what is not in the hierarchy `bvh`; queries continue in the tree (not for counting launches)
     rtb::PtBvh bvh;
@@ -100,5 +101,7 @@ cudaError_t rtk_fill_sincos_table(float *tab /* 2 x 2^23 floats */, int sm_count
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);
 size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode);
+#define W_TAB_CAP 64                              /* stage mode 3: static shared-memory tables for scenes of at most this many primitives ... */
+#define W_TAB_RUNS 24                             /* ... in at most this many runs */
 #define RTK_WHITTED_STAGE_LIMIT (18 * 1024)      /* per-CTA share of shared memory with 12 resident CTAs per SM */
 cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigned long long n, int sm_count, cudaStream_t stream);

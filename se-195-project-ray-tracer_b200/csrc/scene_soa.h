@@ -4,6 +4,7 @@
 #include <vector>
 #include <stdint.h>
 #include <string.h>
+#include <cmath>
 #include "../../include/rt_b200.h"
 #include "pt_lane.cuh"
 #include "whitted_lane.cuh"
@@ -120,6 +121,133 @@ inline void build_w_bvh(const rt_primitive *p, int n, WSoA &out) {
         i = j;
     }
     if (out.runs_bvh.empty()) { out.runs_bvh.push_back(0); out.runs_bvh.push_back(0); out.runs_bvh.push_back(0); }
+}
+
+// Tables of the shadow-round culls of whitted_lane.cuh ("Exact culls of the shadow round"), for one run table of one scene.
+// Everything here is evaluated in double and rounded AWAY from "cull", so the float comparisons of the kernel are safe.
+//
+// Setting: every light is a sphere (else `enabled` stays false).  Rs = largest |coordinate| + radius over all spheres, RL =
+// sqrt(3) Rs bounds |c_light|; the culls only apply to hit points with |P| < RP = 2 Rs + 16, so a shadow ray (o = fl(P +
+// fl(L EPS)), L = fl(fl(1 / len) (c_l - P)), RNO:214-231) has |o - P| <= 1.01 EPS + 1.8u RP, length len < RR = RP + RL + 0.002,
+// |op| < V = RR for every sphere, | |L|^2 - 1 | <= 12u, and the real point o + (len - EPS) L lies within 6u (RP + RL) of the
+// light's centre.  u = 2^-24, EPS = 0.001 (RNO:26); scenes with RR > 8 000 get no culls.
+//
+// Plane (N, depth), nn = |N|, g(t) = N.(o + t L) + depth, D = N.L (reals).  The reference computes d = fl(N.L) and, iff d != 0,
+// s = fl(fl(N.o) + depth) and dist = fl(-s / d); the plane blocks iff 0 < dist < len (RNO:97-108, 232-240).  Bounds:
+// |s - g(0)| <= e2 = 4u (nn |o| + |depth|), |d - D| <= 3.1u nn; the kernel's fused N.P + depth is within 4u (nn RP + |depth|)
+// of the real value.  T = nn (3 EPS + 40u (RP + RR)) + 40u |depth|.  The kernel culls when sgn (N.P + depth) > T (float, T
+// rounded up); the table holds an entry only if sgn (N.c_l + depth) >= 2T for EVERY light (double, here).  Then
+//   sgn g(0) >= 1.99 nn EPS + 34u nn (RP + RR) and sgn s >= 1.99 nn EPS: s is non-zero and has the sign sgn;
+//   sgn g(len - EPS) >= 2T - 6u nn (RP + RL) >= 1.8 T: g has no zero on [0, len - EPS].
+//   d == 0: no test (RNO:98).   sign d == sgn: dist <= 0.
+//   sign d == -sgn but sign D != -sgn (rounding flipped it): |d| <= 3.1u nn, dist >= 1.99 nn EPS / (3.1u nn) > 10 000 > RR > len.
+//   sign d == sign D == -sgn: |g(0)| = |g(len - EPS)| + (len - EPS)|D|, so |s| / |d| >= (1.7 T + (len - EPS)|D|) / (|D| + 3.1u nn),
+//     which is >= len (1 + 2u) because 1.7 T >= nn (5.1 EPS + 68u (RP + RR)) > (EPS + 2u RR)|D| + 3.2u nn RR: dist >= len.
+//   In no case a blocker, for any ray of the batch (T does not depend on the light).
+// Sphere run with box [lo, hi] (centres -+ radii), r_min / r_max its radii.  pt_bvh.cuh (the Whitted test has the same
+// roundings): det >= 0 implies the line through o' (|o' - o| <= 1.8u V) along L passes within R' of the centre, R' - rad <=
+// min(eta_S / (2 rad), sqrt(eta_S)), eta_S = (|e| + 13u)(1 + 2|e|) OO + (2|e| + 2u) rad^2 <= eta = 28u V^2 + 28u r_max^2 for
+// |e| <= 12u, and every accepted distance is the parameter of a point of that inflated sphere up to (|e| + 10u)|op| <= 22u V.
+// grow = min(eta / (2 r_min), 1.001 sqrt(eta)) + 3 EPS + 96u (V + RP).  If P (kernel, float, box rounded outwards) and every
+// light centre (double, here) lie beyond one face of the box grown by `grow`, then every point o' + t L with -22u V <= t <=
+// len + 22u V lies beyond that face grown by R' - rad (the coordinate is linear in t; the ends are within 1.01 EPS + 1.8u RP
+// + 1.8u V, resp. 6u (RP + RL) + 1.8u V + EPS, of P and of the light), where no point of an inflated sphere of the run is:
+// no sphere of the run returns an accepted distance in [0, len).
+struct WCull {
+    std::vector<f2> pcull;      // per primitive
+    std::vector<f4> rbox;       // two per run
+    float rp2 = 0.f;
+    bool enabled = false;
+    int planes_cullable = 0, runs_cullable = 0;     // for the record (tests, bench)
+};
+
+inline float w_cull_up(double v) { float f = (float)v; if ((double)f < v) f = nextafterf(f, INFINITY); return f; }
+inline float w_cull_down(double v) { float f = (float)v; if ((double)f > v) f = nextafterf(f, -INFINITY); return f; }
+
+inline void build_w_cull(const WSoA &soa, const std::vector<int> &runs, WCull &out) {
+    const int n = (int)soa.geom.size(), n_runs = (int)runs.size() / 3;
+    const f2 never = { 0.f, INFINITY };
+    const f4 open_lo = { -INFINITY, -INFINITY, -INFINITY, 0.f }, open_hi = { INFINITY, INFINITY, INFINITY, 0.f };
+    out.pcull.assign((size_t)(n > 0 ? n : 1), never);
+    out.rbox.assign((size_t)(n_runs > 0 ? 2 * n_runs : 2), open_lo);
+    for (int r = 0; r < n_runs; r++) out.rbox[2 * r + 1] = open_hi;
+    out.rp2 = 0.f; out.enabled = false; out.planes_cullable = out.runs_cullable = 0;
+    if (soa.lights.empty()) return;
+    const double u = 1.0 / 16777216.0, EPS = 0.001;
+    double Rs = 0.0;
+    for (int i = 0; i < n; i++) {
+        if (!(soa.flags[i] & W_FLAG_SPHERE)) continue;
+        const f4 g = soa.geom[i];
+        if (!(std::isfinite(g.x) && std::isfinite(g.y) && std::isfinite(g.z) && std::isfinite(g.w)) || g.w < 0.f) return;
+        const double ext = std::fmax(std::fabs((double)g.x), std::fmax(std::fabs((double)g.y), std::fabs((double)g.z))) + std::sqrt((double)g.w);
+        if (ext > Rs) Rs = ext;
+    }
+    for (int l : soa.lights) if (!(soa.flags[l] & W_FLAG_SPHERE)) return;       // a light that is not a sphere: the general path, no culls
+    const double RL = std::sqrt(3.0) * Rs, RP = 2.0 * Rs + 16.0, RR = RP + RL + 0.002, V = RR;
+    if (!(RR <= 8000.0)) return;
+    // planes
+    for (int i = 0; i < n; i++) {
+        if (soa.flags[i] & (W_FLAG_SPHERE | W_FLAG_LIGHT)) continue;
+        const f4 g = soa.geom[i];
+        if (!(std::isfinite(g.x) && std::isfinite(g.y) && std::isfinite(g.z) && std::isfinite(g.w))) continue;
+        const double nn = std::sqrt((double)g.x * g.x + (double)g.y * g.y + (double)g.z * g.z);
+        if (!(nn > 0.0)) continue;
+#ifdef W_CULL_TEST_NO_MARGIN      /* tools/cull_fuzz.py --self-check: tables WITHOUT the margins must be caught by the fuzz */
+        const double T = 0.0;
+#else
+        const double T = nn * (3.0 * EPS + 40.0 * u * (RP + RR)) + 40.0 * u * std::fabs((double)g.w);
+#endif
+        int side = 0;
+        bool ok = true;
+        for (int l : soa.lights) {
+            const f4 c = soa.geom[l];
+            const double sl = (double)g.x * c.x + (double)g.y * c.y + (double)g.z * c.z + (double)g.w;
+            const int sg = sl > 0.0 ? 1 : -1;
+            if (!(std::fabs(sl) >= 2.0 * T) || (side != 0 && sg != side)) { ok = false; break; }
+            side = sg;
+        }
+        if (!ok || side == 0) continue;
+        out.pcull[i] = f2{ (float)side, w_cull_up(T) };
+        out.planes_cullable++;
+    }
+    // runs of non-light spheres
+    for (int r = 0; r < n_runs; r++) {
+        const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
+        if (!(fl & W_FLAG_SPHERE) || (fl & W_FLAG_LIGHT) || count < 1) continue;
+        double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY }, rmin = INFINITY, rmax = 0.0;
+        for (int i = start; i < start + count; i++) {
+            const f4 g = soa.geom[i];
+            const double rad = std::sqrt((double)g.w), c[3] = { g.x, g.y, g.z };
+            for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], c[a] - rad); hi[a] = std::fmax(hi[a], c[a] + rad); }
+            rmin = std::fmin(rmin, rad); rmax = std::fmax(rmax, rad);
+        }
+        const double eta = 28.0 * u * V * V + 28.0 * u * rmax * rmax;
+#ifdef W_CULL_TEST_NO_MARGIN
+        const double grow = -0.02 * rmax;
+#else
+        const double grow = (rmin > 0.0 ? std::fmin(eta / (2.0 * rmin), 1.001 * std::sqrt(eta)) : 1.001 * std::sqrt(eta)) + 3.0 * EPS + 96.0 * u * (V + RP);
+#endif
+        float flo[3], fhi[3];
+        bool any = false;
+        for (int a = 0; a < 3; a++) {
+            bool above = true, below = true;             // every light centre beyond the grown face
+            for (int l : soa.lights) {
+                const f4 cg = soa.geom[l];
+                const double c = a == 0 ? cg.x : (a == 1 ? cg.y : cg.z);
+                if (!(c > hi[a] + grow)) above = false;
+                if (!(c < lo[a] - grow)) below = false;
+            }
+            fhi[a] = above ? w_cull_up(hi[a] + grow) : INFINITY;
+            flo[a] = below ? w_cull_down(lo[a] - grow) : -INFINITY;
+            any = any || above || below;
+        }
+        out.rbox[2 * r] = f4{ flo[0], flo[1], flo[2], 0.f };
+        out.rbox[2 * r + 1] = f4{ fhi[0], fhi[1], fhi[2], 0.f };
+        if (any) out.runs_cullable++;
+    }
+    out.rp2 = w_cull_down(RP * RP * (1.0 - 8.0 * u));
+    out.enabled = out.planes_cullable > 0 || out.runs_cullable > 0;
+    if (!out.enabled) out.rp2 = 0.f;
 }
 
 static_assert(sizeof(rt_r306_primitive) == 96, "rt_r306_primitive must match the reference Primitive (R306/raytracer.h:24-34)");

@@ -48,6 +48,11 @@ struct WFrame {
     int w, h;
     float DX, DY;               // (WX2-WX1)/w, (WY2-WY1)/h computed on the host exactly as RNO:295-296
     int32_t *hit_ids;           // NULL or int[w*h*9]
+    // Shadow-round culls (see "Exact culls of the shadow round" below); NULL = none.  Built on the host by build_w_cull.
+    const f2 *pcull;            // per primitive, planes only: (sgn, T) -- no light-bound ray from a point P with sgn*(N.P + depth) > T can hit the plane
+    const f4 *rbox;             // per run of `runs`: (lo.xyz, -) and (hi.xyz, -) of the run's spheres, grown by the proven margin; a face
+                                //  that does not separate the run from every light is at -+inf
+    float cull_rp2;             // the culls' margins hold for hit points with |P|^2 < cull_rp2
 };
 
 struct WLane {
@@ -67,6 +72,7 @@ struct WLane {
     float slx[W_SHADOW_BATCH], sly[W_SHADOW_BATCH], slz[W_SHADOW_BATCH];   //  unit directions to lights li .. li+ns-1
     float sreach[W_SHADOW_BATCH];                   //  and distances to them
     int ns, sblk;                                   // rays in the batch; bit k set = ray k is blocked
+    bool pnear;                                     // |P|^2 < F.cull_rp2: the shadow culls' margins cover this hit point
     int li, phase;
     uint32_t c_nearest, c_shadow, c_samples;
     uint64_t c_sphere_tests, c_plane_tests;
@@ -268,17 +274,57 @@ RT_HD void w_shadow_plane(WLane &L, const f4 g, int alive_in, bool has) {
         }
     }
 }
-template <bool COUNT>
-RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs, bool has) {
+// Exact culls of the shadow round (timed launches of scenes whose lights are all spheres; tables from build_w_cull,
+// scene_soa.h, which also states the margins).  A shadow ray runs from o = fl(P + L*EPS) along L = fl((1/len) * (c_light - P))
+// and is blocked by a primitive iff the reference's float test returns a distance in (0, len) (RNO:232-240).  Both culls use
+// one fact: a linear function of the ray parameter that has the same sign at both ends of the segment has no zero on it.
+//   plane    g(t) = N.(o + t L) + depth.  g at the light's centre is a constant of the scene (sign sgn, magnitude >= 2T);
+//            if sgn * (N.P + depth) > T -- evaluated ONCE per hit point for the whole batch, fused, any rounding is inside
+//            T -- then the plane's zero lies before o or beyond the light by more than the reference's rounding can move it,
+//            so its test returns a distance <= 0, >= len, or inf / NaN for every ray of the batch: not a blocker.  The plane a
+//            point lies on (|N.P + depth| ~ 0) and planes that pass between the lights always take the full test.
+//   spheres  a run of spheres lies inside its box; if P and every light's centre lie beyond the same face of the box grown by
+//            m (the inflated-sphere bound of pt_bvh.cuh: det >= 0 means the ray's line passes within R' of the centre, and
+//            the accepted distance is the parameter of a point of that inflated sphere up to 18u|op|), every point of the
+//            segment does, and no sphere of the run can return an accepted distance: the whole run is skipped for the lane.
+// A lane that is culled keeps its rays out of the run (alive = 0); the tests themselves are unchanged.
+RT_HD float w_fused_plane_side(const f4 g, float px, float py, float pz) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(g.x, px, __fmaf_rn(g.y, py, __fmaf_rn(g.z, pz, g.w)));
+#else
+    return fmaf(g.x, px, fmaf(g.y, py, fmaf(g.z, pz, g.w)));
+#endif
+}
+template <bool COUNT, bool CULL = false>
+RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs, bool has, const f2 *pcull = nullptr, const f4 *rbox = nullptr) {
     for (int r = 0; r < n_runs; ++r) {
         const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
         if (fl & W_FLAG_LIGHT) continue;                                   // RNO:234: lights cast no shadow
-        const int alive = w_alive_mask(L, has);                            // rays of this lane that are still unblocked
+        int alive = w_alive_mask(L, has);                                  // rays of this lane that are still unblocked
         if (!warp_any(alive != 0)) return;                                 // the `break` of RNO:237, for the whole warp
         const int end = start + count;
         // (loading the next primitive's record before testing the current one changed nothing: 2.97 against 2.98 ms)
-        if (fl & W_FLAG_SPHERE) for (int i = start; i < end; ++i) w_shadow_sphere<COUNT>(L, geom[i], alive, has);
-        else                    for (int i = start; i < end; ++i) w_shadow_plane<COUNT>(L, geom[i], alive, has);
+        if (fl & W_FLAG_SPHERE) {
+#ifndef W_NO_RUN_CULL
+            if (CULL) {
+                const f4 lo = rbox[2 * r], hi = rbox[2 * r + 1];
+                const bool outside = L.pnear & ((L.px > hi.x) | (L.px < lo.x) | (L.py > hi.y) | (L.py < lo.y) | (L.pz > hi.z) | (L.pz < lo.z));
+                if (outside) alive = 0;
+                if (!warp_any(alive != 0)) continue;
+            }
+#endif
+            for (int i = start; i < end; ++i) w_shadow_sphere<COUNT>(L, geom[i], alive, has);
+#ifndef W_NO_PLANE_CULL
+        } else if (CULL) {
+            for (int i = start; i < end; ++i) {
+                const f4 g = geom[i];
+                const f2 cu = pcull[i];
+                const bool clear = L.pnear & (f_mul(cu.x, w_fused_plane_side(g, L.px, L.py, L.pz)) > cu.y);
+                const int a = clear ? 0 : alive;
+                if (warp_any(a != 0)) w_shadow_plane<COUNT>(L, g, a, has);
+            }
+#endif
+        } else for (int i = start; i < end; ++i) w_shadow_plane<COUNT>(L, geom[i], alive, has);
     }
 }
 
@@ -444,6 +490,7 @@ RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
             L.py = f_add(L.qoy, f_mul(L.qdy, L.dist));
             L.pz = f_add(L.qoz, f_mul(L.qdz, L.dist));
             L.li = 0;
+            L.pnear = dot3(L.px, L.py, L.pz, L.px, L.py, L.pz) < F.cull_rp2;      // false for NaN / inf and when there are no cull tables (rp2 = 0)
 #ifndef W_NO_UNLIT_SKIP
             // A material with neither a diffuse nor a specular term (m_diff <= 0 and m_spec <= 0: glass, mirrors) gathers
             // exactly nothing from any light whatever the shadow rays say (RNO:242-276 skips both terms): no shadow rays.

@@ -55,6 +55,15 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
     F.DX = (WX2 - WX1) / w; F.DY = (WY2 - WY1) / h;
     F.hit_ids = hit_ids;
+    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f;
+    WCull cull;
+    if (use_runs == 4 || use_runs == 5) {      // what a timed launch does: the runs without dead primitives (5: + the hierarchy), the shadow-round culls, no counting
+        if (use_runs == 5) { build_w_bvh(prims, n, soa); F.runs = soa.runs_bvh.data(); F.n_runs = (int)soa.runs_bvh.size() / 3; }
+        else { F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3; }
+        build_w_cull(soa, use_runs == 5 ? soa.runs_bvh : soa.runs_hot, cull);
+        F.pcull = cull.pcull.data(); F.rbox = cull.rbox.data(); F.cull_rp2 = cull.rp2;
+    }
+    const PtBvh B5 = soa.bvh.view(soa.bvh.nodes.data(), soa.bvh.geom.data(), soa.bvh.index.data());
     uint32_t n_items;
     Shard S = make_shard(w, h, rank, world, tile_rows, &n_items);
     f4 queue[3 * W_QUEUE_SLOTS];
@@ -67,6 +76,18 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
         w_begin_pixel(L, F, x, y);
         for (;;) {
             // the body of the kernel's loop, for one lane
+            if (use_runs >= 4) {
+                w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);
+                if (use_runs == 5) w_bvh_nearest(L, B5);
+                w_after_nearest<false>(L, F);
+                while (L.phase == PH_SHADOW) {
+                    w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox);
+                    if (use_runs == 5) w_bvh_shadow(L, B5);
+                    w_after_shadow<false>(L, F);
+                }
+                if (w_finalize<false>(L, F, queue)) break;
+                continue;
+            }
             w_query_nearest<true>(L, F.geom, F.runs, F.n_runs, true);
             if (use_runs == 3) w_bvh_nearest(L, B);
             w_after_nearest<true>(L, F);
@@ -85,6 +106,15 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     if (counters5) for (int k = 0; k < 5; k++) counters5[k] += c[k];
 }
 
+// What build_w_cull makes of a scene table: out4 = (enabled, cullable planes, cullable sphere runs, runs in the hot table).
+void devsim_whitted_cull_stats(const rt_primitive *prims, int n, int32_t *out4) {
+    WSoA soa;
+    build_w_soa(prims, n, soa);
+    WCull cull;
+    build_w_cull(soa, soa.runs_hot, cull);
+    out4[0] = cull.enabled; out4[1] = cull.planes_cullable; out4[2] = cull.runs_cullable; out4[3] = (int)soa.runs_hot.size() / 3;
+}
+
 // raytracer3.0.06 frame through the lane state machine (rows 20 .. h-71, like Engine_Render).
 void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, int n) {
     WSoA soa;
@@ -97,6 +127,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
     F.W.runs = soa.runs_hot.data(); F.W.n_runs = (int)soa.runs_hot.size() / 3;
     F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
     F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;
+    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f;
     F.sx = sx.data(); F.sy = sy.data(); F.row0 = 20; F.row1 = h - 70;
     R306Tree T;
     for (int y = F.row0; y < F.row1; y++)
