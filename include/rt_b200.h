@@ -106,6 +106,10 @@ int rt_set_shard(rt_ctx *ctx, int rank, int world, int tile_rows);
 /* Enable (1) / disable (0) the work counters; counted launches are slower, never time them. */
 int rt_set_counting(rt_ctx *ctx, int enabled);
 int rt_get_counters(rt_ctx *ctx, rt_counters *out);
+/* The raw counter block of the last counting launch: [0..4] = the fields of rt_counters, [5] = Whitted: the shadow rays a TIMED
+ * launch traces (a timed launch traces none for hits on a material with neither a diffuse nor a specular term, RNO:242-276 adds
+ * nothing for them; counting launches trace them all so that [1] equals the reference's count), [6..7] reserved. */
+int rt_get_counters_ex(rt_ctx *ctx, uint64_t *out8);
 /* Launch tuning (no reference counterpart; the reference's only knob is the OpenCL work-group size
  * argument of its command line, SPT/RUN_SCENE_*.bat).  Keys: */
 enum {
@@ -123,6 +127,8 @@ enum {
     RT_TUNE_WHITTED_BLOCKS = 9,         /* Whitted tracer, with COST_ORDER on: 1 (default) = pixels whose centre ray meets neither a reflecting nor a refracting
                                            surface (same cost each) are handed out as whole 8x4 screen blocks per warp, the others pixel by pixel; 0 = all
                                            pixel by pixel.  Same image either way */
+    RT_TUNE_WHITTED_FILLER_PCT = 10,    /* ... with BLOCKS on: the first <value> % of the frame's blocks (default 25) are still handed out pixel by pixel, after
+                                           the expensive pixels, so that lanes whose expensive pixel is done do not idle.  Same image for any value */
     RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
                                            reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };
@@ -225,6 +231,15 @@ void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes);
  * into rank 0's frame through the peer mapping -- the transfer rides inside the kernel, tile by tile, and no
  * gather step exists.  The caller only has to order "all ranks' kernels done" before rank 0 reads the frame
  * (any barrier collective on the render stream).  which: RT_BUF_WHITTED_PIXELS or RT_BUF_PT_PIXELS. */
+/* Multi-GPU read-back without the hop through rank 0 (the end-to-end path of bench.py at N > 1): `frame` is ONE full w x h host
+ * frame shared by all ranks' processes (POSIX shared memory, optionally page-locked in each process with rt_host_register); every
+ * rank copies just the rows it owns under rt_set_shard into their place, over its own PCIe link.  After all ranks have returned
+ * (a host barrier is the caller's), the frame is complete -- the same bytes rt_whitted_download / rt_pt_download give on one GPU.
+ * Blocking, like the reference's clEnqueueReadBuffer(CL_TRUE) (SPT/smallptGPU.cpp:757-770, R323/raytracer.c:600-640). */
+int rt_whitted_download_rows(rt_ctx *ctx, rt_uchar4 *frame);
+int rt_pt_download_rows(rt_ctx *ctx, uint32_t *frame /* pixels, w*h */);
+int rt_host_register(rt_ctx *ctx, void *ptr, uint64_t bytes);      /* cudaHostRegister: makes copies to `ptr` true DMA */
+int rt_host_unregister(rt_ctx *ctx, void *ptr);
 #define RT_IPC_HANDLE_BYTES 80   /* CUDA IPC handle (64) + the exporter's capacity in pixels (8) + a magic word (8) */
 /* Lifetime rules (errors are RT_ERR_STATE): an exported framebuffer is never reallocated -- an upload / resize that would
  * have to grow it fails until rt_ipc_close has been called (on every rank; it is the caller's collective); an importer

@@ -57,6 +57,9 @@ void oracle_whitted_rows(uint8_t *pixels, int32_t *hit_ids, int w, int h, int y0
 void oracle_whitted_render(uint8_t *pixels, int32_t *hit_ids, int w, int h,
                            const ow_prim *prims, int n, int threads, ow_counters *ctr);
 
+/* create_scene() of R323/scene.c with CHOOSE_SCENE 0 as 17 flat records (the last one all zero); returns 17, or -1 if cap < 17. */
+int oracle_whitted_scene0(ow_prim *out, int cap);
+
 /* ---- smallpt path tracer (smallptgpu-v1.6: smallptCPU.cpp, geomfunc.h, simplernd.h) ---- */
 
 typedef struct { float x, y, z; } op_vec;

@@ -274,3 +274,45 @@ void oracle_whitted_render(uint8_t *pixels, int32_t *hit_ids, int w, int h,
         }
     free(t); free(jobs);
 }
+
+/* The scene table of create_scene() with CHOOSE_SCENE 0 (R323/scene.c:48-96) as flat Primitive_2 records (the copy of
+ * R323/raytracer.c:721-746): n_primitives is 17 although only 16 slots are filled (scene.c:55-57 memsets the list), so slot 16
+ * is an all-zero plane.  Used by bench.py's --impl reference arm when oracle/_ref (the reference's own scene.c) was not shipped,
+ * so that the arm never touches the product library.  Row: type, r, g, b, refl, refr, refr_index, diff, spec, is_light, x, y, z, depth|radius. */
+int oracle_whitted_scene0(ow_prim *out, int cap) {
+    static const float rows[16][14] = {
+        { 0, 0.6f, 0.6f, 0.6f, 0.0f, 0.0f, 0.0f, 0.4f, 1.8f, 0, 0.0f, 0.75f, 0.0f, 4.4f },
+        { 1, 0.08f, 0.08f, 0.08f, 0.2f, 1.0f, 1.4f, 0.0f, 0.0f, 0, 3.4f, -3.4f, 23.0f, 2.5f },
+        { 1, 0.07f, 0.17f, 0.07f, 0.1f, 1.0f, 1.2f, 0.0f, 0.0f, 0, -0.7f, -4.90f, 27.0f, 1.0f },
+        { 1, 1.0f, 1.0f, 1.0f, 0.8f, 0.0f, 0.0f, 0.0f, 0.0f, 0, -3.4f, -3.4f, 29.0f, 2.5f },
+        { 1, 1.5f, 0.7f, 0.7f, 0.1f, 0.0f, 0.0f, 0.2f, 0.2f, 0, 0.5f, -4.1f, 29.0f, 1.5f },
+        { 1, 0.7f, 0.7f, 1.7f, 0.2f, 0.0f, 0.0f, 0.2f, 0.2f, 0, -6.0f, -4.1f, 32.0f, 1.5f },
+        { 1, 0.07f, 0.17f, 0.07f, 0.3f, 1.0f, 1.2f, 0.2f, 0.8f, 0, -6.7f, -4.90f, 29.0f, 1.0f },
+        { 1, 0.08f, 0.08f, 0.08f, 0.7f, 1.0f, 1.3f, 0.8f, 0.0f, 0, 6.4f, -4.9f, 18.0f, 1.0f },
+        { 0, 1.0f, 0.6f, 0.6f, 0.0f, 0.0f, 0.0f, 0.8f, 1.5f, 0, 0.7f, 0.0f, 0.0f, 5.4f },
+        { 0, 0.7f, 0.6f, 1.0f, 0.0f, 0.0f, 0.0f, 0.8f, 0.8f, 0, -0.7f, 0.0f, 0.0f, 5.4f },
+        { 0, 1.0f, 1.0f, 1.0f, 0.0f, 0.0f, 0.0f, 1.2f, 0.8f, 0, 0.0f, -0.8f, 0.0f, 5.4f },
+        { 0, 1.5f, 1.5f, 1.5f, 0.0f, 0.0f, 0.0f, 1.2f, 0.8f, 0, 0.0f, 0.0f, -0.14f, 5.4f },
+        { 0, 0.1f, 0.1f, 0.1f, 0.0f, 0.0f, 0.0f, 1.0f, 1.0f, 0, 0.0f, 0.0f, 0.72f, 5.4f },
+        { 1, 0.85f, 0.85f, 0.85f, 0.0f, 0.0f, 0.0f, 0.0f, 1.8f, 1, 0.0f, 6.5f, 22.0f, 0.35f },
+        { 1, 0.85f, 0.85f, 0.85f, 0.0f, 0.0f, 0.0f, 0.0f, 1.8f, 1, -3.0f, 6.5f, 22.0f, 0.35f },
+        { 1, 0.85f, 0.85f, 0.85f, 0.0f, 0.0f, 0.0f, 0.0f, 1.8f, 1, 3.0f, 6.5f, 22.0f, 0.35f },
+    };
+    if (!out || cap < 17) return -1;
+    memset(out, 0, sizeof(ow_prim) * 17);
+    for (int i = 0; i < 16; i++) {
+        const float *r = rows[i];
+        ow_prim *p = &out[i];
+        p->type = (int32_t)r[0];
+        p->color.x = r[1]; p->color.y = r[2]; p->color.z = r[3];
+        p->refl = r[4]; p->refr = r[5]; p->refr_index = r[6]; p->diff = r[7]; p->spec = r[8];
+        p->is_light = (uint8_t)r[9];
+        if (p->type == 1) {        /* create_sphere, scene.c:34-46 */
+            p->center.x = r[10]; p->center.y = r[11]; p->center.z = r[12];
+            p->radius = r[13]; p->sq_radius = r[13] * r[13]; p->r_radius = 1.0f / r[13];
+        } else {                   /* create_plane, scene.c:20-32 */
+            p->normal.x = r[10]; p->normal.y = r[11]; p->normal.z = r[12]; p->depth = r[13];
+        }
+    }
+    return 17;
+}

@@ -46,7 +46,7 @@ class Counters(C.Structure):
 
 RT_DIFF_, RT_SPEC_, RT_REFR_ = 0, 1, 2
 RT_OK, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_ARG, RT_ERR_STATE, RT_ERR_CAPACITY, RT_ERR_IO = 0, -1, -2, -3, -4, -5, -6
-TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER, TUNE_PT_ALIGNED, TUNE_PT_BVH, TUNE_WHITTED_BVH, TUNE_R306_SPLIT, TUNE_PT_SINCOS_TABLE, TUNE_WHITTED_BLOCKS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER, TUNE_PT_ALIGNED, TUNE_PT_BVH, TUNE_WHITTED_BVH, TUNE_R306_SPLIT, TUNE_PT_SINCOS_TABLE, TUNE_WHITTED_BLOCKS, TUNE_WHITTED_FILLER_PCT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 BUF_WHITTED_PIXELS, BUF_WHITTED_HITS, BUF_PT_PIXELS, BUF_PT_COLORS, BUF_PT_SEEDS = 0, 1, 2, 3, 4
 IPC_HANDLE_BYTES = 80
 
@@ -60,6 +60,7 @@ SYMBOLS = {
     "rt_set_shard": (_I, [_VP, _I, _I, _I]),
     "rt_set_counting": (_I, [_VP, _I]),
     "rt_get_counters": (_I, [_VP, C.POINTER(Counters)]),
+    "rt_get_counters_ex": (_I, [_VP, _VP]),
     "rt_set_tuning": (_I, [_VP, _I, _I]),
     "rt_whitted_render": (_I, [_VP, _VP, _I, _I, _I, _VP, _VP]),
     "rt_whitted_upload": (_I, [_VP, _VP, _I, _I, _I, _I]),
@@ -89,6 +90,10 @@ SYMBOLS = {
     "rt_ipc_export": (_I, [_VP, _I, _VP]),
     "rt_ipc_import": (_I, [_VP, _I, _VP]),
     "rt_ipc_close": (_I, [_VP]),
+    "rt_whitted_download_rows": (_I, [_VP, _VP]),
+    "rt_pt_download_rows": (_I, [_VP, _VP]),
+    "rt_host_register": (_I, [_VP, _VP, _U64]),
+    "rt_host_unregister": (_I, [_VP, _VP]),
     "rt_stream": (_VP, [_VP]),
     "rt_set_stream": (_I, [_VP, _VP]),
     "rt_update_camera": (None, [_VP, _I, _I]),
@@ -413,6 +418,12 @@ class Renderer:
         self._ck(self._lib.rt_get_counters(self._ctx, C.byref(c)))
         return c.as_dict()
 
+    def counters_ex(self):
+        """Raw counter block (8 x u64) of the last counting launch; [5] = shadow rays a timed Whitted launch traces."""
+        out = np.zeros(8, np.uint64)
+        self._ck(self._lib.rt_get_counters_ex(self._ctx, _ptr(out)))
+        return out
+
     def set_tuning(self, key, value):
         self._ck(self._lib.rt_set_tuning(self._ctx, key, value))
 
@@ -503,6 +514,22 @@ class Renderer:
         hits = np.zeros((h, w, 9), np.int32) if want_hit_ids else None
         self._ck(self._lib.rt_whitted_download(self._ctx, _ptr(pixels), _ptr(hits)))
         return (pixels, hits) if want_hit_ids else pixels
+
+    # -- multi-GPU read-back into one host frame shared by all ranks
+    def whitted_download_rows(self, frame):
+        """Copies the rows this rank owns into `frame` (a contiguous (h, w, 4) uint8 array, e.g. over shared memory)."""
+        assert frame.flags["C_CONTIGUOUS"] and frame.nbytes == self.whitted_size[0] * self.whitted_size[1] * 4
+        self._ck(self._lib.rt_whitted_download_rows(self._ctx, _ptr(frame)))
+
+    def pt_download_rows(self, frame):
+        assert frame.flags["C_CONTIGUOUS"] and frame.nbytes == self.pt_size[0] * self.pt_size[1] * 4
+        self._ck(self._lib.rt_pt_download_rows(self._ctx, _ptr(frame)))
+
+    def host_register(self, array):
+        self._ck(self._lib.rt_host_register(self._ctx, _ptr(array), array.nbytes))
+
+    def host_unregister(self, array):
+        self._ck(self._lib.rt_host_unregister(self._ctx, _ptr(array)))
 
     # -- smallpt (AllocateBuffers / ReInitSceneGPU / ReInitGPU / UpdateRenderingGPU)
     def pt_resize(self, w, h, seeds):

@@ -25,7 +25,7 @@ struct rt_ctx {
     int shard_rank = 0, shard_world = 1, tile_rows = 8;
     int counting = 0;
     unsigned *d_work = nullptr;                    // two work counters (items, screen blocks), zeroed before each launch
-    unsigned long long *d_counters = nullptr;      // 5 x u64
+    unsigned long long *d_counters = nullptr;      // 8 x u64
     uint64_t launches = 0;
     // tuning
     int pt_max_resident_bytes = 96 * 1024;
@@ -52,6 +52,7 @@ struct rt_ctx {
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
     uint8_t *d_wcls = nullptr; size_t wcls_cap = 0;
     int whitted_blocks = 1;                        // class-2 pixels as whole screen blocks per warp (needs whitted_sort)
+    int whitted_filler_pct = 25;                   // ... except this share of the frame, which fills idle lanes pixel by pixel
     unsigned *d_wclass = nullptr;
     // Whitted
     int w_w = 0, w_h = 0, w_n = 0, w_nl = 0, w_ns = 0, w_np = 0, w_nr = 0, w_want_hits = 0;
@@ -170,8 +171,8 @@ int rt_init(rt_ctx **out, int device) {
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaMalloc((void **)&ctx->d_work, 2 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMalloc((void **)&ctx->d_counters, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
-    if ((e = cudaMemset(ctx->d_counters, 0, 5 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
+    if ((e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
     *out = ctx;
     return RT_OK;
 }
@@ -230,6 +231,14 @@ int rt_get_counters(rt_ctx *ctx, rt_counters *out) {
     return RT_OK;
 }
 
+int rt_get_counters_ex(rt_ctx *ctx, uint64_t *out8) {
+    if (!ctx || !out8) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out8, ctx->d_counters, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
 int rt_set_tuning(rt_ctx *ctx, int key, int value) {
     if (!ctx) return RT_ERR_ARG;
     switch (key) {
@@ -243,6 +252,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_R306_SPLIT: ctx->r306_split = value ? 1 : 0; return RT_OK;
         case RT_TUNE_PT_SINCOS_TABLE: ctx->pt_sincos_table = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
+        case RT_TUNE_WHITTED_FILLER_PCT: if (value < 0 || value > 100) break; ctx->whitted_filler_pct = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -325,7 +335,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
     if (p.stage_mode == 2 && ctx->w_n <= W_TAB_CAP && nr_max <= W_TAB_RUNS) p.stage_mode = 3;
     p.sphere_lights = ctx->w_nl;
     for (int l : ctx->w_soa.lights) if (!(ctx->w_soa.flags[l] & W_FLAG_SPHERE)) p.sphere_lights = 0;
-    p.order = nullptr; p.class_counts = nullptr; p.cls = nullptr;
+    p.order = nullptr; p.class_counts = nullptr; p.cls = nullptr; p.filler_items = 0;
     p.n_valid = (uint32_t)p.shard.local_rows * (uint32_t)ctx->w_w;
     int tree_candidates = 0;
     for (int i = 0; i < ctx->w_n; i++) tree_candidates += (ctx->w_soa.flags[i] & (W_FLAG_SPHERE | W_FLAG_LIGHT)) == W_FLAG_SPHERE;
@@ -366,10 +376,11 @@ int rt_whitted_launch(rt_ctx *ctx) {
                 ctx->wcls_cap = p.n_items;
             }
             p.cls = ctx->d_wcls;
+            p.filler_items = (uint32_t)((uint64_t)p.n_items * (uint32_t)ctx->whitted_filler_pct / 100u) & ~31u;
         }
     }
     CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
-    if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += p.order ? 2 : 1; }
     return RT_OK;
 }
@@ -385,6 +396,48 @@ int rt_whitted_download(rt_ctx *ctx, rt_uchar4 *pixels_out, int32_t *hit_id_out)
     if (pixels_out) CK(cudaMemcpyAsync(pixels_out, ctx->d_wpixels, px * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (hit_id_out) CK(cudaMemcpyAsync(hit_id_out, ctx->d_whits, px * 9 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// Copies the rows this rank owns under rt_set_shard from `dev` (a full w x h frame of 4-byte pixels on the device) into the same
+// rows of the host frame `host`: the interleaved tiles are one strided 2-D copy, the ragged last tile (if it is ours) a second one.
+static cudaError_t copy_owned_rows(const rt_ctx *ctx, uint32_t *host, const uint32_t *dev, int w, int h, cudaStream_t stream) {
+    const size_t tile_bytes = (size_t)ctx->tile_rows * w * 4, pitch = tile_bytes * ctx->shard_world;
+    const int n_tiles = h / ctx->tile_rows, ragged = h % ctx->tile_rows;          // full tiles, rows of the last partial tile
+    const int mine = n_tiles > ctx->shard_rank ? (n_tiles - ctx->shard_rank + ctx->shard_world - 1) / ctx->shard_world : 0;
+    const size_t off = (size_t)ctx->shard_rank * ctx->tile_rows * w;
+    cudaError_t e = cudaSuccess;
+    if (mine > 0) e = cudaMemcpy2DAsync(host + off, pitch, dev + off, pitch, tile_bytes, (size_t)mine, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && ragged && n_tiles % ctx->shard_world == ctx->shard_rank) {
+        const size_t o2 = (size_t)n_tiles * ctx->tile_rows * w;
+        e = cudaMemcpyAsync(host + o2, dev + o2, (size_t)ragged * w * 4, cudaMemcpyDeviceToHost, stream);
+    }
+    return e;
+}
+
+int rt_whitted_download_rows(rt_ctx *ctx, rt_uchar4 *frame) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!frame) return fail(ctx, RT_ERR_ARG, "rt_whitted_download_rows: frame is NULL");
+    if (!ctx->d_wpixels) return fail(ctx, RT_ERR_STATE, "rt_whitted_download_rows: nothing rendered yet");
+    if (ctx->peer_wpixels) return fail(ctx, RT_ERR_STATE, "rt_whitted_download_rows: this rank renders into rank 0's framebuffer (rt_ipc_import); rt_ipc_close first");
+    CK(cudaSetDevice(ctx->device));
+    CK(copy_owned_rows(ctx, (uint32_t *)frame, ctx->d_wpixels, ctx->w_w, ctx->w_h, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_host_register(rt_ctx *ctx, void *ptr, uint64_t bytes) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!ptr || !bytes) return fail(ctx, RT_ERR_ARG, "rt_host_register: need a buffer");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return RT_OK;
+}
+
+int rt_host_unregister(rt_ctx *ctx, void *ptr) {
+    if (!ctx) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostUnregister(ptr));
     return RT_OK;
 }
 
@@ -616,7 +669,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
         p.bvh = ctx->p_bvh.view(ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex);
     }
     CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
-    if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 5 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches++; }
     ctx->current_sample += n_passes;
     return RT_OK;
@@ -642,6 +695,17 @@ int rt_pt_download(rt_ctx *ctx, uint32_t *pixels_out, float *colors_out, uint32_
     if (pixels_out) CK(cudaMemcpyAsync(pixels_out, ctx->d_ppixels, px * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (colors_out) CK(cudaMemcpyAsync(colors_out, ctx->d_colors, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (seeds_out) CK(cudaMemcpyAsync(seeds_out, ctx->d_seeds, px * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_pt_download_rows(rt_ctx *ctx, uint32_t *frame) {
+    if (!ctx) return RT_ERR_ARG;
+    if (!frame) return fail(ctx, RT_ERR_ARG, "rt_pt_download_rows: frame is NULL");
+    if (!ctx->have_size) return fail(ctx, RT_ERR_STATE, "rt_pt_download_rows: rt_pt_resize has not been called");
+    if (ctx->peer_ppixels) return fail(ctx, RT_ERR_STATE, "rt_pt_download_rows: this rank renders into rank 0's framebuffer (rt_ipc_import); rt_ipc_close first");
+    CK(cudaSetDevice(ctx->device));
+    CK(copy_owned_rows(ctx, frame, ctx->d_ppixels, ctx->p_w, ctx->p_h, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return RT_OK;
 }

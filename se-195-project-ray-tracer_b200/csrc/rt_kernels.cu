@@ -341,7 +341,7 @@ __device__ __forceinline__ void w_bvh_shadow_round(WLane &L, const PtBvh &B, boo
 template <bool COUNT, int STAGED, int NL, bool BVH>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
-               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B, const uint8_t *cls) {
+               uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B, const uint8_t *cls, uint32_t filler_items) {
     extern __shared__ f4 s_raw[];
     const uint32_t lane = threadIdx.x & 31u;
     const f4 *s_geom; const int *s_runs;
@@ -350,7 +350,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
     f4 queue[3 * W_QUEUE_SLOTS];
     WLane L;
     L.phase = PH_IDLE;
-    L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_sphere_tests = L.c_plane_tests = 0;
+    L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_sphere_tests = L.c_plane_tests = 0; L.c_shadow_lit = 0;
     bool exhausted = false;
     // Two ways of handing out pixels (see whitted_classify_kernel).  Pixels of classes 0 and 1 (a refracting / reflecting
     // surface behind the centre ray: ray trees of very different sizes) go to single lanes, each lane taking the next one
@@ -359,7 +359,12 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
     // 32 rays run side by side hits the same few primitives, so the votes in front of the square roots / divisions and
     // the shadow-round culls decide for the warp what they decide for a lane (with single-lane refill a warp soon holds 32
     // unrelated pixels).  `cls` == NULL: lists only.
-    const uint32_t n_lane_items = (order && cls) ? class_counts[0] + class_counts[1] : n_items;
+    // The first `n_items` / 32 blocks ("filler", a launch parameter) are handed out pixel by pixel as well, after the lists: a
+    // lane gets fewer than two class-0/1 pixels at 1080p, so without cheap pixels to fill in with, a warp waits for its slowest
+    // lane with most lanes idle (25 of 32 lanes per instruction in that phase).
+    const uint32_t n_listed = (order && cls) ? class_counts[0] + class_counts[1] : 0u;
+    const uint32_t n_filler = (order && cls) ? filler_items : 0u;            // items [0, n_filler) of class 2: by single lanes (a multiple of 32)
+    const uint32_t n_lane_items = (order && cls) ? n_listed + n_filler : n_items;
     const uint32_t n_blocks = cls ? n_stride >> 5 : 0u;
 
     for (;;) {
@@ -369,11 +374,13 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             if (item < n_lane_items) {
                 int x, y;
                 uint32_t it = item;
+                bool take = true;
                 if (order) {                     // walk the cost classes in turn (see whitted_classify_kernel)
                     const uint32_t n0 = class_counts[0], n1 = class_counts[1];
-                    it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
+                    if (cls && item >= n_listed) { it = item - n_listed; take = cls[it] == 2; }     // filler: a class-2 pixel of the first blocks
+                    else it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
                 }
-                if (item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
+                if (take && item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
             } else exhausted = true;
         }
         if (!__any_sync(FULL_MASK, L.phase != PH_IDLE || !exhausted)) {
@@ -381,7 +388,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             if (!cls) break;
             uint32_t blk = 0;
             if (lane == 0) blk = atomicAdd(work_counter + 1, 1u);
-            blk = __shfl_sync(FULL_MASK, blk, 0);
+            blk = __shfl_sync(FULL_MASK, blk, 0) + (n_filler >> 5);
             if (blk >= n_blocks) break;
             const uint32_t it = blk * 32u + lane;
             int x, y;
@@ -421,6 +428,8 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             atomicAdd(&counters[2], (unsigned long long)c); atomicAdd(&counters[3], (unsigned long long)d);
             atomicAdd(&counters[4], (unsigned long long)e);
         }
+        const uint64_t f = warp_sum(L.c_shadow_lit);
+        if (lane == 0) atomicAdd(&counters[5], (unsigned long long)f);
     }
 #endif
 }
@@ -704,7 +713,7 @@ size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode) {
 
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     const size_t smem = rtk_whitted_smem_bytes(p.frame.n, p.frame.n_lights, p.frame.n_runs, p.stage_mode);
-    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *, PtBvh, const uint8_t *);
+    typedef void (*kern_t)(WFrame, Shard, uint32_t, const uint32_t *, const unsigned *, uint32_t, uint32_t *, unsigned *, unsigned long long *, PtBvh, const uint8_t *, uint32_t);
     const bool bvh = p.use_bvh && !p.count;
     kern_t k;
     if (bvh) {          // large scenes: tables through L1 / L2 or geometry-only staging, the light count still compiled in
@@ -744,6 +753,6 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         n_work = p.n_valid;
     }
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
-                                                  p.counters, p.bvh, p.order ? p.cls : nullptr);
+                                                  p.counters, p.bvh, p.order ? p.cls : nullptr, p.filler_items);
     return cudaGetLastError();
 }

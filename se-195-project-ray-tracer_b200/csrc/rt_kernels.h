@@ -77,6 +77,7 @@ struct WLaunch {
     uint32_t *order;            // NULL: screen order; else scratch of 3 x n_items entries: one work list per cost class
     unsigned *class_counts;     // 3 x u32 scratch: entries in each list
     uint8_t *cls;               // NULL, or n_items bytes of scratch: the class of every item; class-2 pixels are then handed out as 8x4 blocks to whole warps
+    uint32_t filler_items;      // with cls: the class-2 pixels among items [0, filler_items) are handed out pixel by pixel after the lists (a multiple of 32)
     uint32_t n_valid;           // pixels owned by this rank (n_items minus the padding of the 8x4 blocks)
     int use_bvh;                // 1: frame.runs lists only what is not in the hierarchy `bvh`; queries continue in the tree (not for counting launches)
     rtb::PtBvh bvh;

@@ -75,6 +75,7 @@ struct WLane {
     bool pnear;                                     // |P|^2 < F.cull_rp2: the shadow culls' margins cover this hit point
     int li, phase;
     uint32_t c_nearest, c_shadow, c_samples;
+    uint32_t c_shadow_lit;                          // shadow rays a TIMED launch traces: those of hits on a material with a diffuse or specular term
     uint64_t c_sphere_tests, c_plane_tests;
 };
 
@@ -511,7 +512,11 @@ RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
 // skipped), then set up the next batch or complete the ray.
 template <bool COUNT, int NL = 0>
 RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
-    if (COUNT) L.c_shadow += (uint32_t)L.ns;
+    if (COUNT) {
+        L.c_shadow += (uint32_t)L.ns;
+        const f4 mbc = F.mat_b[L.hit];
+        if ((mbc.x > 0.f) | (mbc.w > 0.f)) L.c_shadow_lit += (uint32_t)L.ns;
+    }
     if (NL > 0) {
         const f4 ma = F.mat_a[L.hit], mb = F.mat_b[L.hit];                // once per hit, not per light
         float nx, ny, nz;

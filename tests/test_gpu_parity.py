@@ -221,6 +221,45 @@ def test_whitted_cost_ordered_schedule_changes_nothing(gpu, rt):
         gpu.set_tuning(rt.TUNE_WHITTED_COST_ORDER, 1)
 
 
+def test_whitted_block_and_filler_schedules_change_nothing(gpu, orc, rt):
+    """Class-2 pixels handed out as screen blocks per warp (RT_TUNE_WHITTED_BLOCKS) with any share of filler pixels
+    (RT_TUNE_WHITTED_FILLER_PCT), or everything pixel by pixel from the lists: the same bytes, equal to the oracle's, on a size
+    with padding items, under sharding, and on a table without reflecting / refracting spheres (empty lists)."""
+    box = rt.whitted_create_scene(0)
+    dull = box.copy(); dull["m_refl"] = 0; dull["m_refr"] = 0
+    try:
+        for prims, (w, h, rank, world, tile) in [(box, (333, 250, 0, 1, 8)), (box, (61, 37, 1, 3, 4)), (dull, (200, 150, 0, 1, 8))]:
+            gpu.set_shard(rank, world, tile)
+            px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
+            rows = np.array([(y // tile) % world == rank for y in range(h)])
+            for blocks, filler in [(1, 25), (1, 0), (1, 100), (1, 7), (0, 25)]:
+                gpu.set_tuning(rt.TUNE_WHITTED_BLOCKS, blocks); gpu.set_tuning(rt.TUNE_WHITTED_FILLER_PCT, filler)
+                a, ha = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+                assert np.array_equal(a[rows], px_o[rows]) and np.array_equal(ha[rows], hits_o[rows]), (w, h, blocks, filler)
+    finally:
+        gpu.set_shard(0, 1, 8)
+        gpu.set_tuning(rt.TUNE_WHITTED_BLOCKS, 1); gpu.set_tuning(rt.TUNE_WHITTED_FILLER_PCT, 25)
+
+
+def test_whitted_shadow_culls_against_oracle_on_moved_lights_and_random_rooms(gpu, orc, rt):
+    """The shadow-round culls (planes by the side of the hit point, sphere runs by a separating box face) on the GPU: lights
+    moved to within a hair of a wall, below the floor, into the sphere cluster; random rooms of tools/cull_fuzz.py."""
+    import importlib.util, os
+    box = rt.whitted_create_scene(0)
+    near = box.copy(); near["center"][13, 1] = np.float32(6.7495)
+    below = box.copy(); below["center"][14, 1] = np.float32(-9.0)
+    inside = box.copy(); inside["center"][15, :3] = (0.4, -3.0, 27.0)
+    spec = importlib.util.spec_from_file_location("cull_fuzz", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "cull_fuzz.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    rs = np.random.RandomState(11)
+    cases = [(near, 320, 240), (below, 320, 240), (inside, 320, 240)] + [(fz.random_scene(rt, rs, box), 96, 72) for _ in range(60)]
+    for k, (prims, w, h) in enumerate(cases):
+        px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+        px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
+        assert np.array_equal(hits, hits_o), k
+        assert np.array_equal(px, px_o), k
+
+
 def test_whitted_counters_equal_oracle(gpu, orc, rt):
     prims = rt.whitted_create_scene(0)
     gpu.set_counting(True)
@@ -790,7 +829,47 @@ def _ipc_worker(rank, world, port, out_dir):
     dist.barrier()                                                     # every rank's kernel has finished
     if rank == 0:
         np.save(os.path.join(out_dir, "assembled.npy"), r.whitted_download())
+    # lifetime rules of the shared frame (include/rt_b200.h): the exporter may not grow it, an importer may not outgrow it or read
+    # "its" pixels locally -- all RT_ERR_STATE, nothing written out of bounds
+    notes = []
+    try:
+        r.whitted_upload(prims, 2 * w, 2 * h)
+        notes.append("grow accepted")
+    except rt.RtError as e:
+        notes.append("grow refused" if e.code == rt.RT_ERR_STATE else f"grow: code {e.code}")
+    if rank != 0:
+        try:
+            r.whitted_download()
+            notes.append("download accepted")
+        except rt.RtError as e:
+            notes.append("download refused" if e.code == rt.RT_ERR_STATE else f"download: code {e.code}")
+        try:
+            r.ipc_import(rt.BUF_WHITTED_PIXELS, np.zeros(rt.IPC_HANDLE_BYTES, np.uint8))
+            notes.append("garbage handle accepted")
+        except rt.RtError as e:
+            notes.append("garbage handle refused" if e.code == rt.RT_ERR_ARG else f"garbage: code {e.code}")
     dist.barrier()
+    r.ipc_close()
+    dist.barrier()
+    r.whitted_upload(prims, 2 * w, 2 * h)                              # after the collective close both may resize again
+    r.whitted_launch(); r.sync()
+    with open(os.path.join(out_dir, f"notes{rank}.txt"), "w") as f:
+        f.write(";".join(notes))
+    # ---- the same assembly for the path tracer's 8-bit frame
+    sph, cam = rt.cornell_scene(64, 48)
+    seeds = rt.reference_seeds(64, 48, seed=3)
+    r.pt_resize(64, 48, seeds); r.pt_set_scene(sph); r.pt_set_camera(cam)
+    box = [r.ipc_export(rt.BUF_PT_PIXELS).tobytes() if rank == 0 else None]
+    dist.broadcast_object_list(box, 0)
+    if rank != 0:
+        r.ipc_import(rt.BUF_PT_PIXELS, np.frombuffer(box[0], np.uint8))
+    dist.barrier()
+    r.pt_launch(0, 3); r.sync()
+    dist.barrier()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "assembled_pt.npy"), r.pt_download(want=("pixels",))["pixels"])
+    dist.barrier()
+    r.ipc_close()
     r.close()
     dist.destroy_process_group()
 
@@ -806,3 +885,100 @@ def test_fused_frame_assembly_through_ipc_peer_memory(rt, orc, tmp_path):
     prims = rt.whitted_create_scene(0)
     px_o, _, _ = oracle_whitted(orc, prims, 160, 120)
     assert np.array_equal(np.load(tmp_path / "assembled.npy"), px_o)
+    assert (tmp_path / "notes0.txt").read_text() == "grow refused"
+    assert (tmp_path / "notes1.txt").read_text() == "grow refused;download refused;garbage handle refused"
+    sph, cam = rt.cornell_scene(64, 48)
+    _, _, pix_o, _ = oracle_pt(orc, 0, sph, cam, 64, 48, rt.reference_seeds(64, 48, seed=3), 3)
+    assert np.array_equal(np.load(tmp_path / "assembled_pt.npy").reshape(-1), pix_o)
+
+
+# ------------------------------------------------------------------------------------------ two ranks: sample-sharded mode, shared host frame
+def _two_rank_worker(rank, world, port, out_dir, shm_name):
+    import os
+    from multiprocessing import shared_memory
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    two_gpus = torch.cuda.device_count() >= world
+    dev = rank if two_gpus else 0
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl" if two_gpus else "gloo", rank=rank, world_size=world)
+    import __graft_entry__ as graft
+    rt = graft.load()
+    r = rt.Renderer(dev)
+    # (1) sample-sharded progressive mode: every rank renders the whole frame with its own seeds, sums are all-reduced, then resolved
+    w, h, passes = 64, 48, 6
+    sph, cam = rt.cornell_scene(w, h)
+    r.pt_set_accumulate_sums(True)
+    r.pt_resize(w, h, rt.reference_seeds(w, h, seed=40 + rank)); r.pt_set_scene(sph); r.pt_set_camera(cam)
+    r.pt_launch(0, passes); r.sync()
+    ptr, nbytes = r.device_buffer(rt.BUF_PT_COLORS)
+    colors = torch.as_tensor(rt.DeviceArray(ptr, (h * w * 3,), "<f4"), device=f"cuda:{dev}")
+    rt.allreduce_sums(colors)                                          # the product's collective (ncclAllReduce; gloo when both ranks share one GPU)
+    torch.cuda.synchronize()
+    r.pt_resolve_sums(passes * world)
+    out = r.pt_download(want=("pixels", "colors"))
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sums.npy"), out["colors"]); np.save(os.path.join(out_dir, "resolved.npy"), out["pixels"])
+    r.pt_set_accumulate_sums(False)
+    # (2) image-sharded Whitted frame read back by every rank into ONE host frame (shared memory), no hop through rank 0
+    ww, wh, tile = 203, 77, 4                                          # ragged last tile
+    shm = shared_memory.SharedMemory(name=shm_name)
+    frame = np.ndarray((wh, ww, 4), np.uint8, buffer=shm.buf)
+    r.host_register(frame)
+    r.set_shard(rank, world, tile)
+    r.whitted_upload(rt.whitted_create_scene(0), ww, wh)
+    r.whitted_launch()
+    r.whitted_download_rows(frame)
+    r.pt_resize(ww, wh, rt.reference_seeds(ww, wh, seed=5)); r.pt_set_scene(sph); c2 = cam.copy(); rt.update_camera(c2, ww, wh); r.pt_set_camera(c2)
+    r.pt_launch(1, 2)
+    pt_frame = np.ndarray((wh, ww), np.uint32, buffer=shm.buf, offset=frame.nbytes)
+    r.pt_download_rows(pt_frame)
+    dist.barrier()
+    r.host_unregister(frame)
+    del frame, pt_frame
+    shm.close()
+    r.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_sample_sharded_sums_and_shared_host_frame(rt, orc, tmp_path):
+    """Two processes = two ranks (on two GPUs over NCCL when the box has them, else both on cuda:0 with gloo as the transport).
+    (1) Sample-sharded mode: per-rank sums -> all-reduce -> rt_pt_resolve_sums equals the mean of the two ranks' oracle images up to
+    float rounding (the mode is judged by RMSE, SURVEY 8e: bound 1e-5 relative here because the sample sets are the same), pixels
+    within 1 LSB.  (2) rt_*_download_rows: both ranks copy their own row tiles into one shared host frame = the unsharded oracle."""
+    import socket
+    from multiprocessing import shared_memory
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ww, wh = 203, 77
+    shm = shared_memory.SharedMemory(create=True, size=2 * ww * wh * 4)
+    try:
+        shm.buf[:] = bytes(len(shm.buf))
+        mp.spawn(_two_rank_worker, args=(2, port, str(tmp_path), shm.name), nprocs=2, join=True)
+        w, h, passes = 64, 48, 6
+        sph, cam = rt.cornell_scene(w, h)
+        means = [oracle_pt(orc, 0, sph, cam, w, h, rt.reference_seeds(w, h, seed=40 + q), passes)[0] for q in range(2)]
+        want = (means[0].astype(np.float64) + means[1]) / 2
+        sums = np.load(tmp_path / "sums.npy").reshape(-1).astype(np.float64)
+        np.testing.assert_allclose(sums / (2 * passes), want, rtol=1e-5, atol=1e-6)
+        rmse = float(np.sqrt(np.mean((sums / (2 * passes) - want) ** 2)))
+        assert rmse < 1e-5
+        pix = np.load(tmp_path / "resolved.npy").reshape(-1)
+        col = want.astype(np.float32)
+        g = np.zeros(col.size, np.int32)                                # expected 8-bit values through the oracle's own toInt
+        orc.oracle_libm_to_int_gamma(vp(col), vp(g), ctypes.c_long(col.size))
+        g = g.reshape(h, w, 3)[::-1].reshape(-1, 3)                     # colors are stored bottom row first (SPT/smallptCPU.cpp:86)
+        exp = (g[:, 0] | (g[:, 1] << 8) | (g[:, 2] << 16)).astype(np.uint32)
+        d = np.abs(pix.view(np.uint8).astype(int) - exp.view(np.uint8).astype(int))
+        assert d.max() <= 1
+        frame = np.ndarray((wh, ww, 4), np.uint8, buffer=shm.buf).copy()
+        pt_frame = np.ndarray((wh, ww), np.uint32, buffer=shm.buf, offset=frame.nbytes).copy()
+        px_o, _, _ = oracle_whitted(orc, rt.whitted_create_scene(0), ww, wh)
+        assert np.array_equal(frame, px_o)
+        c2 = cam.copy(); rt.update_camera(c2, ww, wh)
+        _, _, pix_o, _ = oracle_pt(orc, 1, sph, c2, ww, wh, rt.reference_seeds(ww, wh, seed=5), 2)
+        assert np.array_equal(pt_frame.reshape(-1), pix_o)
+    finally:
+        shm.close(); shm.unlink()

@@ -239,6 +239,40 @@ def test_whitted_hierarchy_equals_oracle_on_generated_sphere_scenes(devsim, orc,
             assert np.array_equal(px, px_o), (depth, k)
 
 
+def test_whitted_shadow_culls_change_nothing(devsim, orc, rt, tmp_path):
+    """The timed path of the Whitted tracer (hot runs, no counting, the shadow-round culls of whitted_lane.cuh with the tables
+    of build_w_cull) against the oracle, which tests every primitive: the reference's two scenes, scene 0 with a light moved to
+    within a hair of a wall (that wall loses its cull entry), with a light below the floor (both sides lit: no entry either), a
+    sphere scene walked through the hierarchy with walls around it, and a handful of random rooms (tools/cull_fuzz.py runs
+    thousands, plus a self-check that tables without the margins are caught)."""
+    import importlib.util, os
+    box = rt.whitted_create_scene(0)
+    near = box.copy(); near["center"][13, 1] = np.float32(6.7495)            # 0.0004 below the ceiling plane y = 6.75
+    below = box.copy(); below["center"][14, 1] = np.float32(-9.0)
+    st = np.zeros(4, np.int32)
+    devsim.devsim_whitted_cull_stats(vp(box), box.size, vp(st))
+    assert list(st[:3]) == [1, 6, 1]                                          # all six walls and the sphere run are cullable
+    devsim.devsim_whitted_cull_stats(vp(near), near.size, vp(st))
+    assert st[1] == 5
+    devsim.devsim_whitted_cull_stats(vp(below), below.size, vp(st))
+    assert st[1] == 5 and st[2] == 0                                          # the floor separates the lights; no box face has them all beyond it
+    cases = [(box, 96, 72, 4), (rt.whitted_create_scene(1), 48, 36, 4), (near, 64, 48, 4), (below, 64, 48, 4)]
+    sph, cam = _complex_scene(rt, tmp_path, 3, 40, 30)
+    v = np.concatenate([box[[0, 8, 9, 10, 11, 12]], rt.whitted_from_spheres(sph, cam), box[13:16]])
+    cases.append((v, 40, 30, 5))
+    spec = importlib.util.spec_from_file_location("cull_fuzz", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "cull_fuzz.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    rs = np.random.RandomState(5)
+    cases += [(fz.random_scene(rt, rs, box), 40, 30, 4) for _ in range(40)]
+    for k, (prims, w, h, mode) in enumerate(cases):
+        px, hits = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, None, None, mode)
+        px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, None)
+        assert np.array_equal(hits, hits_o), k
+        assert np.array_equal(px, px_o), k
+
+
 def test_hierarchy_builder_on_degenerate_inputs(devsim, rt):
     """build_pt_bvh: every sphere ends up exactly once in the tree or in the always-tested list, and the depth stays below
     the traversal stack (64) -- one sphere, a thousand identical ones, NaN / inf / huge entries, a line of 5 000, 200 000

@@ -8,7 +8,9 @@ prims = rt.whitted_create_scene(0)
 size = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
 r.whitted_upload(prims, *size)
 out = []
-for name, knobs in [("blocks", {rt.TUNE_WHITTED_COST_ORDER: 1, rt.TUNE_WHITTED_BLOCKS: 1}), ("lists", {rt.TUNE_WHITTED_COST_ORDER: 1, rt.TUNE_WHITTED_BLOCKS: 0}),
+for name, knobs in [("blocks+filler10", {rt.TUNE_WHITTED_COST_ORDER: 1, rt.TUNE_WHITTED_BLOCKS: 1, rt.TUNE_WHITTED_FILLER_PCT: 10}),
+                    ("filler25", {rt.TUNE_WHITTED_FILLER_PCT: 25}), ("filler40", {rt.TUNE_WHITTED_FILLER_PCT: 40}), ("filler60", {rt.TUNE_WHITTED_FILLER_PCT: 60}),
+                    ("filler0", {rt.TUNE_WHITTED_FILLER_PCT: 0}), ("lists", {rt.TUNE_WHITTED_COST_ORDER: 1, rt.TUNE_WHITTED_BLOCKS: 0}),
                     ("screen-order", {rt.TUNE_WHITTED_COST_ORDER: 0, rt.TUNE_WHITTED_BLOCKS: 0})]:
     for k, v in knobs.items():
         try:
