@@ -324,6 +324,11 @@ def shared_host_frame(dist, rank, world, nbytes):
         dist.broadcast_object_list(box, 0)
     if rank != 0:
         shm = shared_memory.SharedMemory(name=box[0])
+        try:        # attaching registers the segment with this process's resource tracker too (CPython < 3.13); rank 0 owns and unlinks it
+            from multiprocessing import resource_tracker
+            resource_tracker.unregister(shm._name, "shared_memory")
+        except Exception:
+            pass
     return shm
 
 
@@ -530,7 +535,7 @@ def bench_c5(rt, r, torch, dist, rank, world, stream):
     dist.all_reduce(mean_image)
     if fused:
         torch.cuda.synchronize(); dist.barrier(); r.ipc_close(); dist.barrier()
-    verdict = None
+    verdict, noise_floor = None, None
     if rank == 0:       # one GPU renders the check rows alone, all 1024 passes
         r.set_shard(check_rank, check_world, tile)
         r.pt_resize(w, h, seeds); r.pt_set_camera(cam)
@@ -539,6 +544,11 @@ def bench_c5(rt, r, torch, dist, rank, world, stream):
         same_col = bool((colors[(h - 1) - rows_t].view(torch.int32) == mean_image[(h - 1) - rows_t].view(torch.int32)).all())
         verdict = f"{len(check_rows)} rows ({len(check_rows) * w} pixels, every {check_world}th tile) re-rendered by one GPU: 8-bit frame " \
                   f"{'byte-identical' if same else 'MISMATCH'}, float radiance {'bit-identical' if same_col else 'MISMATCH'}"
+        # noise floor for the RMSE judgement below: the same rows once more in the reference's own mode, other seeds
+        r.pt_resize(w, h, rt.reference_seeds(w, h, seed=999)); r.pt_set_camera(cam)
+        r.pt_launch(0, spp); r.sync()
+        d0 = colors[(h - 1) - rows_t].double() - mean_image[(h - 1) - rows_t].double()
+        noise_floor = float(torch.sqrt((d0 * d0).mean()).item())
     dist.barrier()
     res["image_sharded"] = {"ms": round(ms, 2), "msamples_per_s": round(n_px * spp / ms / 1e3, 1),
                             "assembly": "render kernels store into rank 0's frame through CUDA-IPC peer memory + 4-byte all-reduce" if fused else "NCCL send/recv gather",
@@ -563,9 +573,11 @@ def bench_c5(rt, r, torch, dist, rank, world, stream):
     rmse = float(torch.sqrt((diff * diff).mean()).item())
     mean_level = float(mean_image.double().mean().item())
     pix_ss = dev(rt.BUF_PT_PIXELS, (h, w), "<i4")
-    verdict2 = None
+    verdict2, rmse_rows = None, None
     if rank == 0:
         sums_rows = sums[(h - 1) - rows_t].clone()
+        d1 = sums_rows.double() / float(per_rank * world) - mean_image[(h - 1) - rows_t].double()
+        rmse_rows = float(torch.sqrt((d1 * d1).mean()).item())
         # exact side of the check: ONE GPU adds the N ranks' passes of the check rows one after the other
         r.set_shard(check_rank, check_world, tile)
         for q in range(world):
@@ -585,12 +597,16 @@ def bench_c5(rt, r, torch, dist, rank, world, stream):
     r.pt_set_accumulate_sums(False)
     r.set_shard(rank, world, tile)
     dist.barrier()
-    bound = 0.05 * max(mean_level, 1e-9)
     res["sample_sharded"] = {"ms": round(ms2, 2), "msamples_per_s": round(n_px * per_rank * world / ms2 / 1e3, 1), "passes_per_rank": per_rank,
                              "collective": f"ncclAllReduce(sum, f32, {3 * n_px} floats = {3 * n_px * 4 / 1e6:.0f} MB) + resolve",
-                             "rmse_vs_running_mean_image": round(rmse, 6), "mean_radiance": round(mean_level, 4),
-                             "rmse_bound": f"5 % of the mean radiance ({bound:.4f}): two independent {spp}-spp estimates -> {'within' if rmse < bound else 'EXCEEDED'}",
-                             "check": verdict2}
+                             "rmse_vs_running_mean_image": round(rmse, 6), "mean_radiance": round(mean_level, 4), "check": verdict2}
+    if rank == 0:
+        ok = rmse_rows <= 1.25 * noise_floor
+        res["sample_sharded"]["rmse_judgement"] = {
+            "rows": f"the {len(check_rows)} check rows", "sample_sharded_vs_running_mean": round(rmse_rows, 6),
+            "running_mean_other_seeds_vs_running_mean": round(noise_floor, 6),
+            "bound": "the sample-sharded image may differ from the reference-mode image by no more than 1.25 x what a second reference-mode render with other seeds "
+                     f"does (both are independent {spp}-spp estimates; Monte-Carlo noise, heavy-tailed through the glass sphere): {'within' if ok else 'EXCEEDED'}"}
     return res
 
 

@@ -248,6 +248,11 @@ int rt_host_unregister(rt_ctx *ctx, void *ptr);
 int rt_ipc_export(rt_ctx *ctx, int which, unsigned char *handle /* RT_IPC_HANDLE_BYTES */);
 int rt_ipc_import(rt_ctx *ctx, int which, const unsigned char *handle /* RT_IPC_HANDLE_BYTES */);
 int rt_ipc_close(rt_ctx *ctx);
+/* Diagnostics.  A library built with -DRT_DEVICE_CHECKS (tools/checked_build.sh; not the product build) verifies on the device every
+ * index its kernels form -- ray FIFO depth, traversal stack depth, pixel and hit-ID addresses, work-list and class-table positions,
+ * staged-table sizes, the 3.0.06 ray tree, table look-ups -- and records a failed check as a bit (RT_CHK_* of csrc/rt_math.cuh)
+ * instead of faulting.  Returns that mask since the last call (0 = clean) after synchronising, -1 when the checks are not compiled in. */
+long long rt_debug_check_flags(rt_ctx *ctx);
 /* The context's cudaStream_t as an opaque pointer (for callers that order their own work after it). */
 void *rt_stream(rt_ctx *ctx);
 /* Makes the context issue all its work on a caller-owned cudaStream_t (e.g. torch's current stream, so

@@ -94,6 +94,7 @@ SYMBOLS = {
     "rt_pt_download_rows": (_I, [_VP, _VP]),
     "rt_host_register": (_I, [_VP, _VP, _U64]),
     "rt_host_unregister": (_I, [_VP, _VP]),
+    "rt_debug_check_flags": (C.c_longlong, [_VP]),
     "rt_stream": (_VP, [_VP]),
     "rt_set_stream": (_I, [_VP, _VP]),
     "rt_update_camera": (None, [_VP, _I, _I]),
@@ -465,6 +466,10 @@ class Renderer:
 
     def ipc_close(self):
         self._ck(self._lib.rt_ipc_close(self._ctx))
+
+    def debug_check_flags(self):
+        """Mask of failed device-side bounds checks since the last call (-DRT_DEVICE_CHECKS builds); -1 if not compiled in."""
+        return int(self._lib.rt_debug_check_flags(self._ctx))
 
     def device_buffer(self, which):
         n = C.c_uint64()

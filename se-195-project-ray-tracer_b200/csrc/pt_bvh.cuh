@@ -198,6 +198,7 @@ RT_HD void bvh_inner(float ox, float oy, float oz, float limit, const PtBvh &B, 
     const int c0 = (int)f_bits(n3.x), c1 = (int)f_bits(n3.y);
     if (h0 & h1) {
         const bool swap = lb1 < lb0;                     // nearer child first (any order is correct)
+        RT_CHECK(T.sp >= 0 && T.sp < PT_BVH_STACK, RT_CHK_STACK);
         stack[T.sp] = swap ? c0 : c1;
         stack_t[T.sp++] = swap ? lb0 : lb1;
         T.node = swap ? c1 : c0;

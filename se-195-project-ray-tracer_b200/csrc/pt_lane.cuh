@@ -163,6 +163,7 @@ RT_HD void pt_start_sample(PtLane &L, const PtFrame &F) {
 
 RT_HD void pt_begin_pixel(PtLane &L, const PtFrame &F, int x, int y, const float *colors, const uint32_t *seeds) {
     const size_t i = (size_t)(F.h - y - 1) * F.w + x;        // SPT/smallptCPU.cpp:86
+    RT_CHECK(x >= 0 && x < F.w && y >= 0 && y < F.h, RT_CHK_PIXEL);
     L.x = x; L.y = y; L.pass = F.pass0;
     L.s0 = seeds[2 * i]; L.s1 = seeds[2 * i + 1];
     L.cr = colors[3 * i]; L.cg = colors[3 * i + 1]; L.cb = colors[3 * i + 2];
@@ -183,6 +184,7 @@ RT_HD void pt_hit(PtLane &L, const PtFrame &F) {
     if (COUNT) { L.c_nearest++; L.c_tests += (uint32_t)F.n; }
     if (!(L.cumu < PT_INF)) { L.phase = PH_END; return; }            // miss: SPT/geomfunc.h:190-193
     const int id = L.hit;
+    RT_CHECK(id >= 0 && id < F.n, RT_CHK_SCENE_INDEX);
     const f4 g = F.geom_global[id];
     const f4 em = F.emis[id];
     const float t = L.cumu;
@@ -290,6 +292,7 @@ RT_HD void pt_light_step(PtLane &L, const PtFrame &F) {
     const float r = f_sqrt(0.f > inside ? 0.f : inside);
     const float phi = f_mul(f_mul(2.f, PT_PI), u2);
     float sn, cs;
+    RT_CHECK(u2_bits < (1u << 23), RT_CHK_TABLE);
     if (F.sincos_tab) { const f2 t = F.sincos_tab[u2_bits]; sn = t.x; cs = t.y; }     // phi == sincos_table_angle(u2_bits)
     else sincos_glibc(phi, &sn, &cs);
     const float ux = f_mul(r, cs), uy = f_mul(r, sn), uz = zz;

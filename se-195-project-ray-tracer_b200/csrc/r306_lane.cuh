@@ -162,6 +162,7 @@ RT_HD void r306_next_shadow_batch(R306Lane &L, const R306Frame &F) {
 RT_HD void r306_store_node(R306Lane &L, R306Tree &T, float refl, int refl_idx, const float *refl_ray, float refr, int refr_idx) {
     const WLane &q = L.q;
     const int i = L.node;
+    RT_CHECK(i >= 0 && i < R306_NODES, RT_CHK_TREE);
     T.col[i][0] = q.cr; T.col[i][1] = q.cg; T.col[i][2] = q.cb;
     if (i < R306_PARENTS) {
         T.refl[i] = refl; T.refl_idx[i] = refl_idx; T.refr[i] = refr; T.refr_idx[i] = refr_idx;
@@ -274,6 +275,7 @@ RT_HD bool r306_next_node(R306Lane &L, const R306Frame &F, R306Tree &T, bool one
     WLane &q = L.q;
     for (;;) {
         const int i = ++L.node;
+        RT_CHECK(i >= 0 && i <= R306_NODES, RT_CHK_TREE);
         if (i >= R306_NODES) break;
         const int p = (i - 1) / 2;
         if (!((L.traced >> p) & 1ull)) continue;                      // the parent was not traced: neither is this node

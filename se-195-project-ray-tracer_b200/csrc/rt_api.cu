@@ -828,6 +828,12 @@ int rt_selftest_math(rt_ctx *ctx, int op, const float *in, void *out, uint64_t n
     return RT_OK;
 }
 
+long long rt_debug_check_flags(rt_ctx *ctx) {
+    if (!ctx) return RT_ERR_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -2;
+    return rtk_read_check_flags();
+}
+
 void *rt_stream(rt_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int rt_set_stream(rt_ctx *ctx, void *cuda_stream) {

@@ -111,6 +111,7 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
             for (int hi = F.n; hi > 0; hi -= chunk) {          // descending index, chunk by chunk
                 const int lo = hi > chunk ? hi - chunk : 0;
                 __syncthreads();
+                RT_CHECK(hi - lo <= chunk && lo >= 0 && hi <= F.n, RT_CHK_STAGING);
                 for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) s_geom[i - lo] = F.geom_global[i];
                 __syncthreads();
                 pt_query_range<COUNT>(L, s_geom, lo, hi, active);
@@ -233,6 +234,7 @@ __device__ __forceinline__ void stage_scene(WFrame &F, f4 *s_raw, const f4 *&s_g
     if (MODE == 0) { s_geom_out = F.geom; s_runs_out = F.runs; return; }
     if (MODE == 3) {
         __shared__ WTables T;
+        RT_CHECK(F.n <= W_TAB_CAP && F.n_runs <= W_TAB_RUNS && F.n_lights <= W_TAB_CAP, RT_CHK_STAGING);
         const bool cull = F.pcull != nullptr;
         for (int i = threadIdx.x; i < F.n; i += blockDim.x) {
             T.geom[i] = F.geom[i]; T.ma[i] = F.mat_a[i]; T.mb[i] = F.mat_b[i]; T.rrad[i] = F.rrad[i]; T.flags[i] = F.flags[i];
@@ -377,6 +379,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
                 bool take = true;
                 if (order) {                     // walk the cost classes in turn (see whitted_classify_kernel)
                     const uint32_t n0 = class_counts[0], n1 = class_counts[1];
+                    RT_CHECK(n0 + n1 <= n_stride && (!cls || item - n_listed < n_stride || item < n_listed), RT_CHK_WORKLIST);
                     if (cls && item >= n_listed) { it = item - n_listed; take = cls[it] == 2; }     // filler: a class-2 pixel of the first blocks
                     else it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
                 }
@@ -391,6 +394,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             blk = __shfl_sync(FULL_MASK, blk, 0) + (n_filler >> 5);
             if (blk >= n_blocks) break;
             const uint32_t it = blk * 32u + lane;
+            RT_CHECK(it < n_stride, RT_CHK_WORKLIST);
             int x, y;
             if (cls[it] == 2 && item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
             if (!__any_sync(FULL_MASK, L.phase != PH_IDLE)) continue;       // a block without such pixels
@@ -415,8 +419,10 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
             if (BVH) w_bvh_shadow_round(L, B, sq);
             if (sq) w_after_shadow<COUNT, NL>(L, F);
         }
-        if (L.phase == PH_FINAL && w_finalize<COUNT>(L, F, queue))
+        if (L.phase == PH_FINAL && w_finalize<COUNT>(L, F, queue)) {
+            RT_CHECK(L.x >= 0 && L.x < F.w && L.y >= 0 && L.y < F.h, RT_CHK_PIXEL);
             pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(L.ar, L.ag, L.ab);
+        }
     }
 
 #ifndef W_ROUND_STATS
@@ -755,4 +761,16 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
                                                   p.counters, p.bvh, p.order ? p.cls : nullptr, p.filler_items);
     return cudaGetLastError();
+}
+
+// -DRT_DEVICE_CHECKS builds: the word of failed bounds checks (rt_math.cuh), read and cleared; -1 when the checks are not compiled in.
+long long rtk_read_check_flags() {
+#ifdef RT_DEVICE_CHECKS
+    unsigned v = 0, zero = 0;
+    if (cudaMemcpyFromSymbol(&v, rtb::g_rt_check_flags, sizeof v) != cudaSuccess) return -2;
+    cudaMemcpyToSymbol(rtb::g_rt_check_flags, &zero, sizeof zero);
+    return (long long)v;
+#else
+    return -1;
+#endif
 }

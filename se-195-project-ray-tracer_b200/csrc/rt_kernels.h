@@ -106,3 +106,4 @@ size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode);
 #define W_TAB_RUNS 24                             /* ... in at most this many runs */
 #define RTK_WHITTED_STAGE_LIMIT (18 * 1024)      /* per-CTA share of shared memory with 12 resident CTAs per SM */
 cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigned long long n, int sm_count, cudaStream_t stream);
+long long rtk_read_check_flags();            /* -DRT_DEVICE_CHECKS builds: bit mask of failed device-side bounds checks (cleared by the read); -1 otherwise */

@@ -26,6 +26,9 @@ namespace rtb {
 #ifndef W_PLANE_PAIRS
 #define W_PLANE_PAIRS 0
 #endif
+#ifndef W_QUEUE_CHECK_SLOTS
+#define W_QUEUE_CHECK_SLOTS W_QUEUE_SLOTS    /* tools/checked_build.sh builds a second library with 4 here: its FIFO check MUST fire */
+#endif
 #define W_SHADOW_BATCH 3          /* shadow rays per lane per shadow round */
 static_assert(W_SHADOW_BATCH == 3, "w_after_shadow picks the batch's rays with three-way selects");
 #define PH_FINAL 3                /* the current ray is complete: w_finalize() folds it into the pixel */
@@ -366,6 +369,7 @@ RT_HD void w_begin_pixel(WLane &L, const WFrame &F, int x, int y) {
 // FIFO record: 12 words = three f4.
 RT_HD void w_push(f4 *q, WLane &L, float ox, float oy, float oz, float dx, float dy, float dz,
                   float weight, float r_index, float tr, float tg, float tb, int depth, int kind, int from) {
+    RT_CHECK(L.tail - L.head < W_QUEUE_CHECK_SLOTS, RT_CHK_FIFO);      // a depth-5 binary ray tree never queues more
     f4 *slot = q + 3 * (L.tail & (W_QUEUE_SLOTS - 1));
     L.tail++;
     f4 a = { ox, oy, oz, dx }, b = { dy, dz, weight, r_index }, c = { tr, tg, tb, bits_f((uint32_t)(depth | (kind << 4) | ((from + 1) << 8))) };
@@ -476,6 +480,7 @@ template <bool COUNT, int NL = 0>
 RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
     if (COUNT) { L.c_nearest++; L.c_sphere_tests += (uint32_t)F.n_spheres; L.c_plane_tests += (uint32_t)F.n_planes; }
     L.dist = L.cumu; L.hit = L.qhit; L.hkind = L.qkind;
+    RT_CHECK(L.hit >= -1 && L.hit < F.n, RT_CHK_SCENE_INDEX);
     L.cr = L.cg = L.cb = 0.f;
     L.phase = PH_FINAL;
     if (L.hit >= 0) {
@@ -553,6 +558,7 @@ RT_HD bool w_finalize(WLane &L, const WFrame &F, f4 *q) {
     // The ray is finished: fold its colour into the pixel (RNO:351-368).
     if (L.kind == W_PRIMARY) {
         if (COUNT) L.c_samples++;
+        RT_CHECK(L.x >= 0 && L.x < F.w && L.y >= 0 && L.y < F.h && L.sub >= 0 && L.sub < 9, RT_CHK_PIXEL);
         if (F.hit_ids) F.hit_ids[((size_t)L.y * F.w + L.x) * 9 + L.sub] = L.hit;
         L.ar = f_add(L.ar, f_mul(L.cr, L.weight));
         L.ag = f_add(L.ag, f_mul(L.cg, L.weight));
