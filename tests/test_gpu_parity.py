@@ -682,6 +682,48 @@ def test_smallpt_sum_mode_matches_running_mean_within_rounding(gpu, rt, cornell)
     assert diff.max() <= 1
 
 
+# ------------------------------------------------------------------------------------------ BASELINE sizes against the oracle
+def test_config3_cornell_1024x768_256spp_equals_oracle(gpu, orc, rt, cornell):
+    """BASELINE configs[2] at its stated size: cornell.scn 1024x768 x 256 spp, path tracing, against the multi-threaded oracle
+    (201 M samples: ~15 s on 16 host threads): RNG state, float radiance and 8-bit pixels bit-identical; RMSE exactly 0."""
+    spheres, cam = cornell
+    w, h, spp = 1024, 768, 256
+    cam = cam.copy(); rt.update_camera(cam, w, h)
+    seeds = rt.reference_seeds(w, h, seed=1)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    out = gpu.pt_render(0, spp)
+    col_o, sd_o, pix_o, _ = oracle_pt(orc, 0, spheres, cam, w, h, seeds, spp)
+    assert np.array_equal(out["seeds"], sd_o)
+    assert np.array_equal(out["colors"].reshape(-1).view(np.uint32), col_o.view(np.uint32))
+    assert np.array_equal(out["pixels"].reshape(-1), pix_o)
+    assert float(np.sqrt(np.mean((out["colors"].reshape(-1).astype(np.float64) - col_o) ** 2))) == 0.0
+
+
+def test_config4_generated_scene_3840x2160_row_bands_equal_oracle(gpu, orc, rt, tmp_path):
+    """BASELINE configs[3] at its stated size: the 783-sphere scene_build_complex.pl scene at 3840x2160 x 16 spp (exact hierarchy on the
+    GPU).  The oracle cannot do the whole frame in test time, so it renders three bands of rows (top, the horizon of the sphere
+    cloud, bottom: oracle_pt_rows takes a row range): seeds, radiance and pixels of those rows bit-identical."""
+    path = tmp_path / "complex4.scn"
+    rt.write_complex_scene(str(path), 4)
+    w, h, spp = 3840, 2160, 16
+    spheres, cam = rt.read_scene(str(path), w, h)
+    seeds = rt.reference_seeds(w, h, seed=1)
+    gpu.pt_resize(w, h, seeds); gpu.pt_set_scene(spheres); gpu.pt_set_camera(cam)
+    out = gpu.pt_render(0, spp)
+    col, sd, pix = np.zeros(3 * w * h, np.float32), seeds.copy(), np.zeros(w * h, np.uint32)
+    bands = [(3, 5), (1080, 1083), (2150, 2152)]
+    for y0, y1 in bands:
+        orc.oracle_pt_rows(0, vp(spheres), spheres.size, vp(cam), w, h, y0, y1, 0, spp, vp(col), vp(sd), vp(pix), None)
+    col = col.reshape(h, w, 3); sd2 = sd.reshape(h, w, 2); pix = pix.reshape(h, w)
+    g_col, g_sd = out["colors"], out["seeds"].reshape(h, w, 2)
+    for y0, y1 in bands:
+        fl = slice(h - y1, h - y0)                   # colours and seeds are stored bottom row first (SPT/smallptCPU.cpp:86)
+        assert np.array_equal(g_sd[fl], sd2[fl]), (y0, y1)
+        assert np.array_equal(g_col[fl].view(np.uint32), col[fl].view(np.uint32)), (y0, y1)
+        assert np.array_equal(out["pixels"][y0:y1], pix[y0:y1]), (y0, y1)
+        assert out["pixels"][y0:y1].any()
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties(gpu, rt, cornell):
     """At BASELINE sizes the oracle is too slow to be the checker; size-independent properties instead:
