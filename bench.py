@@ -669,15 +669,17 @@ def bench_pt(rt, r, info, peaks, torch, stream):
         samples = PT_W * PT_H * PT_SPP
         flop = 17.0 * per["sphere_tests"] * samples
         fp32_peak = info["sm_count"] * 128 * 2 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        seeds_pin = torch.from_numpy(seeds.view(np.int32)).pin_memory().numpy().view(np.uint32)
+        pix_pin = torch.empty((PT_H, PT_W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
         t0 = time.perf_counter()
-        r.pt_resize(PT_W, PT_H, seeds); r.pt_set_camera(cam)
-        r.pt_render(integ, PT_SPP, want=("pixels",))
+        r.pt_resize(PT_W, PT_H, seeds_pin); r.pt_set_scene(spheres); r.pt_set_camera(cam)
+        r.pt_render(integ, PT_SPP, want=("pixels",), pixels_out=pix_pin)
         e2e_s = time.perf_counter() - t0
         res[tag] = {"workload": f"smallpt cornell.scn {PT_W}x{PT_H} x {PT_SPP} spp, one launch", "msamples_per_s": round(samples / ms / 1e3, 1),
                     "mrays_per_s": round(samples * (per["nearest_queries"] + per["shadow_queries"]) / ms / 1e3, 1), "kernel_ms": round(ms, 3),
                     "rays_per_sample": round(per["nearest_queries"] + per["shadow_queries"], 3), "sphere_tests_per_sample": round(per["sphere_tests"], 2),
                     "fp32_tflops_algorithmic": round(flop / ms / 1e9, 3), "frac_of_fp32_peak": round(flop / ms / 1e9 / fp32_peak, 4),
-                    "e2e_msamples_per_s": round(samples / e2e_s / 1e6, 1), "e2e_includes": "seed upload 6.3 MB + kernel + pixel read-back 3.1 MB (pageable host memory)"}
+                    "e2e_msamples_per_s": round(samples / e2e_s / 1e6, 1), "e2e_includes": "rt_pt_resize (seed upload 6.3 MB) + rt_pt_set_scene + rt_pt_set_camera + rt_pt_render (kernel + pixel read-back 3.1 MB), pinned host buffers"}
     # CPU side: the reference's own RadiancePathTracing (oracle/_ref) on a bounded sample, all cores and one core
     cam_fn = lambda sw, sh: rt.cornell_scene(sw, sh)[1]
     res["cpu_baseline"] = cpu_pt_baseline(spheres, cam_fn, 256, 192, 8, host_threads(), "cornell")
@@ -719,13 +721,24 @@ def bench_c4(rt, r, info, peaks, torch, stream):
             times.append(a.elapsed_time(b))
         ms = min(times[1:])
         pixels[tag] = r.pt_download(want=("colors",))["colors"].copy()
-        t0 = time.perf_counter()                      # end to end: scene tables (+ hierarchy build), seeds up, kernel, pixels down
-        r.pt_resize(w, h, seeds); r.pt_set_scene(spheres); r.pt_set_camera(cam)
-        r.pt_render(0, spp, want=("pixels",))
-        e2e_s = time.perf_counter() - t0
+        e2e = {}
+        for tag_h, sd_h, px_h in (("pageable", seeds, None), ("pinned", torch.from_numpy(seeds.view(np.int32)).pin_memory().numpy().view(np.uint32),
+                                                             torch.empty((h, w), dtype=torch.int32).pin_memory().numpy().view(np.uint32))):
+            t0 = time.perf_counter()                  # end to end: seeds up, scene (an unchanged table keeps its hierarchy), kernel, pixels down
+            r.pt_resize(w, h, sd_h); r.pt_set_scene(spheres); r.pt_set_camera(cam)
+            r.pt_render(0, spp, want=("pixels",), pixels_out=px_h)
+            e2e[tag_h] = time.perf_counter() - t0
+        changed = spheres.copy(); changed["c"][0] *= np.float32(0.5)      # a CHANGED table: tables re-uploaded, hierarchy rebuilt on the host
+        t0 = time.perf_counter()
+        r.pt_set_scene(changed); r.pt_launch(0, 1); r.sync()
+        t_new_scene = time.perf_counter() - t0
+        r.pt_set_scene(spheres)
+        e2e_s = e2e["pinned"]
         res[tag] = {"kernel_ms": round(ms, 2), "msamples_per_s": round(samples / ms / 1e3, 1),
                     "mrays_per_s": round(samples * (per["nearest_queries"] + per["shadow_queries"]) / ms / 1e3, 1),
-                    "e2e_ms": round(e2e_s * 1e3, 1), "e2e_includes": "scene upload (and the host build of the hierarchy), seed upload 66 MB, kernel, pixel read-back 33 MB"}
+                    "e2e_ms": round(e2e_s * 1e3, 1), "e2e_pageable_ms": round(e2e["pageable"] * 1e3, 1),
+                    "e2e_includes": "rt_pt_resize (seed upload 66 MB) + rt_pt_set_scene (same table: tables and hierarchy kept) + rt_pt_render (kernel, pixel read-back 33 MB); pinned / pageable host buffers",
+                    "new_scene_plus_1spp_ms": round(t_new_scene * 1e3, 1)}
         if mode == 0:
             res[tag]["fp32_tflops_algorithmic"] = round(flop / ms / 1e9, 2)
             res[tag]["frac_of_fp32_peak"] = round(flop / ms / 1e9 / fp32_peak, 4)

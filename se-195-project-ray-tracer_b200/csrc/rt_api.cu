@@ -84,6 +84,7 @@ struct rt_ctx {
     uint32_t *d_seeds = nullptr, *d_ppixels = nullptr;
     f4 *d_pgeom = nullptr, *d_pemis = nullptr, *d_pcolr = nullptr;
     int *d_plights = nullptr;
+    std::vector<rt_sphere> p_scene_copy;           // the table of the last rt_pt_set_scene (an identical one keeps the device tables and the hierarchy)
     PtBvhHost p_bvh;                               // hierarchy over the current scene (csrc/pt_bvh_build.h); built on first use
     bool p_bvh_ready = false;
     f4 *d_bnodes = nullptr, *d_bgeom = nullptr; int *d_bindex = nullptr;
@@ -265,9 +266,12 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     if (!prims || n < 1 || w < 1 || h < 1) return fail(ctx, RT_ERR_ARG, "rt_whitted_upload: need prims, n >= 1, w >= 1, h >= 1");
     CK(cudaSetDevice(ctx->device));
     WSoA &soa = ctx->w_soa;
-    build_w_soa(prims, n, soa);
-    ctx->w_prims.assign(prims, prims + n);
-    ctx->w_bvh_ready = false;
+    const bool same_table = ctx->d_wgeom && (int)ctx->w_prims.size() == n && memcmp(ctx->w_prims.data(), prims, (size_t)n * sizeof(rt_primitive)) == 0;
+    if (!same_table) {                     // an identical table keeps the staging copy and the hierarchy built from it
+        build_w_soa(prims, n, soa);
+        ctx->w_prims.assign(prims, prims + n);
+        ctx->w_bvh_ready = false;
+    }
     CK(upload_vec(&ctx->d_wgeom, &ctx->cap_wgeom, soa.geom, ctx->stream));
     CK(upload_vec(&ctx->d_wma, &ctx->cap_wma, soa.mat_a, ctx->stream));
     CK(upload_vec(&ctx->d_wmb, &ctx->cap_wmb, soa.mat_b, ctx->stream));
@@ -598,6 +602,13 @@ int rt_pt_set_scene(rt_ctx *ctx, const rt_sphere *spheres, uint32_t n) {
         if (spheres[i].refl < 0 || spheres[i].refl > 2)
             return fail(ctx, RT_ERR_ARG, "rt_pt_set_scene: sphere %u has material %d (expected 0, 1 or 2)", i, spheres[i].refl);
     CK(cudaSetDevice(ctx->device));
+    // The same table again (the viewer's ReInitSceneGPU after a key that moved nothing, a caller that re-sends its scene every frame):
+    // the device tables and the hierarchy built from them are still valid; only the sample counter restarts (SPT/smallptGPU.cpp:784-803).
+    if (ctx->have_scene && ctx->p_scene_copy.size() == n && memcmp(ctx->p_scene_copy.data(), spheres, (size_t)n * sizeof(rt_sphere)) == 0) {
+        ctx->current_sample = 0;
+        return RT_OK;
+    }
+    ctx->p_scene_copy.assign(spheres, spheres + n);
     PtSoA &soa = ctx->p_soa;
     build_pt_soa(spheres, n, soa);
     CK(upload_vec(&ctx->d_pgeom, &ctx->cap_pgeom, soa.geom, ctx->stream));
