@@ -129,6 +129,8 @@ enum {
                                            pixel by pixel.  Same image either way */
     RT_TUNE_WHITTED_FILLER_PCT = 10,    /* ... with BLOCKS on: the first <value> % of the frame's blocks (default 25) are still handed out pixel by pixel, after
                                            the expensive pixels, so that lanes whose expensive pixel is done do not idle.  Same image for any value */
+    RT_TUNE_WHITTED_STAGE_CAP = 11,     /* diagnostics: cap on how much of the Whitted scene tables is staged in shared memory -- 3 static tables, 2 all tables,
+                                           1 geometry / flags / runs only, 0 nothing (read through L1 / L2); -1 (default) = whatever fits.  Same image */
     RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
                                            reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };

@@ -52,6 +52,7 @@ struct rt_ctx {
     uint32_t *d_worder = nullptr; size_t worder_cap = 0;
     uint8_t *d_wcls = nullptr; size_t wcls_cap = 0;
     int whitted_blocks = 1;                        // class-2 pixels as whole screen blocks per warp (needs whitted_sort)
+    int w_stage_cap = -1;                          // RT_TUNE_WHITTED_STAGE_CAP
     int whitted_filler_pct = 25;                   // ... except this share of the frame, which fills idle lanes pixel by pixel
     unsigned *d_wclass = nullptr;
     // Whitted
@@ -254,6 +255,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_PT_SINCOS_TABLE: ctx->pt_sincos_table = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_FILLER_PCT: if (value < 0 || value > 100) break; ctx->whitted_filler_pct = value; return RT_OK;
+        case RT_TUNE_WHITTED_STAGE_CAP: if (value < -1 || value > 3) break; ctx->w_stage_cap = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
     return fail(ctx, RT_ERR_ARG, "rt_set_tuning: bad value %d for key %d", value, key);
@@ -337,6 +339,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
     p.stage_mode = rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, nr_max, 2) <= RTK_WHITTED_STAGE_LIMIT ? 2
                  : rtk_whitted_smem_bytes(ctx->w_n, ctx->w_nl, nr_max, 1) <= RTK_WHITTED_STAGE_LIMIT ? 1 : 0;
     if (p.stage_mode == 2 && ctx->w_n <= W_TAB_CAP && nr_max <= W_TAB_RUNS) p.stage_mode = 3;
+    if (ctx->w_stage_cap >= 0 && p.stage_mode > ctx->w_stage_cap) p.stage_mode = ctx->w_stage_cap;      // diagnostics: a lower mode than the tables would allow
     p.sphere_lights = ctx->w_nl;
     for (int l : ctx->w_soa.lights) if (!(ctx->w_soa.flags[l] & W_FLAG_SPHERE)) p.sphere_lights = 0;
     p.order = nullptr; p.class_counts = nullptr; p.cls = nullptr; p.filler_items = 0;
