@@ -40,6 +40,8 @@ struct PtFrame {
     int direct_only;                // 0: RadiancePathTracing, 1: RadianceDirectLighting
     const f2 *sincos_tab;           // NULL, or 2^23 (sin, cos) pairs: every angle 2*pi*GetRandom() can be (rt_math.cuh)
     int sum_mode;                   // 1: accumulate sums instead of the running mean (sample-sharded mode)
+    int defer_pack;                 // 1: the render kernel leaves `pixels` alone; pt_pack_kernel converts the colours afterwards with all lanes busy
+                                    //  (inside the render kernel the FP64 gamma ran for the 2 lanes of a warp whose pixel had just finished)
 };
 
 struct PtLane {

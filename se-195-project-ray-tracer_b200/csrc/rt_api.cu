@@ -656,7 +656,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
     F.w = ctx->p_w; F.h = ctx->p_h;
     F.inv_w = 1.f / ctx->p_w; F.inv_h = 1.f / ctx->p_h;          // SPT/smallptCPU.cpp:80-81
     F.pass0 = ctx->current_sample; F.n_passes = n_passes;
-    F.direct_only = integrator; F.sum_mode = ctx->sum_mode;
+    F.direct_only = integrator; F.sum_mode = ctx->sum_mode; F.defer_pack = ctx->sum_mode ? 0 : 1;
     F.sincos_tab = nullptr;
     if (ctx->pt_sincos_table) {
         ensure_sincos_table(ctx);          // normally already there (rt_pt_resize)
@@ -684,7 +684,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
     }
     CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches++; }
+    if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches += F.defer_pack ? 2 : 1; }
     ctx->current_sample += n_passes;
     return RT_OK;
 }

@@ -101,7 +101,7 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
                 const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
                 colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
                 seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
-                if (!F.sum_mode) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
+                if (!F.sum_mode && !F.defer_pack) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
             }
             continue;
         }
@@ -122,7 +122,7 @@ pt_kernel(PtFrame F, Shard S, uint32_t n_items, float *colors, uint32_t *seeds, 
             const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
             colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
             seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
-            if (!F.sum_mode) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
+            if (!F.sum_mode && !F.defer_pack) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
         }
     }
 
@@ -176,7 +176,7 @@ pt_bvh_kernel(PtFrame F, PtBvh B, Shard S, uint32_t n_items, float *colors, uint
                 const size_t i = (size_t)(F.h - L.y - 1) * F.w + L.x;
                 colors[3 * i] = L.cr; colors[3 * i + 1] = L.cg; colors[3 * i + 2] = L.cb;
                 seeds[2 * i] = L.s0; seeds[2 * i + 1] = L.s1;
-                if (!F.sum_mode) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
+                if (!F.sum_mode && !F.defer_pack) pixels[(size_t)L.y * F.w + L.x] = pt_pack_pixel(L.cr, L.cg, L.cb);
             }
             const bool need = (L.phase == PH_IDLE) && !exhausted;
             const uint32_t item = fetch_items(work_counter, need, lane);
@@ -201,6 +201,16 @@ __global__ void sincos_table_kernel(float *tab) {
         float sn, cs;
         sincos_glibc(sincos_table_angle(i), &sn, &cs);
         tab[2 * i] = sn; tab[2 * i + 1] = cs;
+    }
+}
+
+// toInt of every pixel this rank owns (SPT/smallptCPU.cpp:120-122), after the render kernel: one thread per pixel, all lanes busy.
+__global__ void pt_pack_kernel(Shard S, int w, int h, uint32_t n_items, const float *colors, uint32_t *pixels) {
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+        int x, y;
+        if (!item_to_pixel(S, w, item, x, y)) continue;
+        const size_t i = (size_t)(h - y - 1) * w + x;
+        pixels[(size_t)y * w + x] = pt_pack_pixel(colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
     }
 }
 
@@ -627,6 +637,14 @@ cudaError_t rtk_fill_sincos_table(float *tab, int sm_count, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+static cudaError_t rtk_launch_pt_pack(const PtLaunch &p, cudaStream_t stream) {
+    if (!p.frame.defer_pack || p.frame.sum_mode) return cudaSuccess;
+    long grid = ((long)p.n_items + 255) / 256;
+    if (grid > (long)p.sm_count * 8) grid = (long)p.sm_count * 8;
+    pt_pack_kernel<<<(unsigned)(grid > 0 ? grid : 1), 256, 0, stream>>>(p.shard, p.frame.w, p.frame.h, p.n_items, p.colors, p.pixels);
+    return cudaGetLastError();
+}
+
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
     if (p.use_bvh && !p.count) {
         int nb = 0;
@@ -637,7 +655,8 @@ cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
         const long need = ((long)p.n_items + PT_THREADS - 1) / PT_THREADS;
         if (grid > need) grid = need > 0 ? need : 1;
         pt_bvh_kernel<<<(unsigned)grid, PT_THREADS, 0, stream>>>(p.frame, p.bvh, p.shard, p.n_items, p.colors, p.seeds, p.pixels, p.work_counter);
-        return cudaGetLastError();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        return rtk_launch_pt_pack(p, stream);
     }
     const size_t geom_bytes = (size_t)p.frame.n * sizeof(f4);
     const bool chunked = geom_bytes > (size_t)p.max_smem_geom;
@@ -662,7 +681,8 @@ cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream) {
     if (grid > need) grid = need > 0 ? need : 1;
     k<<<(unsigned)grid, PT_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, p.colors, p.seeds, p.pixels,
                                                    p.work_counter, p.counters, chunk);
-    return cudaGetLastError();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    return rtk_launch_pt_pack(p, stream);
 }
 
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream) {

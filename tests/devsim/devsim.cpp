@@ -163,7 +163,7 @@ void devsim_pt(int integrator, const rt_sphere *sph, uint32_t n, const rt_camera
     F.cam_xx = cam->x.x; F.cam_xy = cam->x.y; F.cam_xz = cam->x.z;
     F.cam_yx = cam->y.x; F.cam_yy = cam->y.y; F.cam_yz = cam->y.z;
     F.w = w; F.h = h; F.inv_w = 1.f / w; F.inv_h = 1.f / h;
-    F.pass0 = pass0; F.n_passes = n_passes; F.direct_only = integrator; F.sum_mode = sum_mode; F.sincos_tab = nullptr;
+    F.pass0 = pass0; F.n_passes = n_passes; F.direct_only = integrator; F.sum_mode = sum_mode; F.defer_pack = 0; F.sincos_tab = nullptr;
     uint32_t n_items;
     Shard S = make_shard(w, h, rank, world, tile_rows, &n_items);
     uint64_t c[5] = {0, 0, 0, 0, 0};

@@ -118,3 +118,23 @@ def test_viewer_keys_equal_the_reference_callbacks(rt, cornell):
         assert ["%08x" % x for x in v.cam.view(np.uint32).reshape(-1)] == step["camera"], (i, k)
         assert hashlib.sha256(v.spheres.view(np.float32).tobytes()).hexdigest() == step["spheres_sha256"], (i, k)
     assert v.key(" ") == rt.KEY_RESTART and v.key("p") == rt.KEY_DUMP and v.key(chr(27)) == rt.KEY_QUIT
+
+
+def test_bench_reference_arm_prints_the_contract_line_without_the_product_library():
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the contract's keys, produced without loading librt_b200.so
+    (the arm may only execute oracle/), on the same metric / unit / workload string as the GPU arm prints."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LD_DEBUG="files")                          # the dynamic loader names every library it maps on stderr
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads(p.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "Mrays/s" and line["unit"] == "Mrays/s" and line["value"] > 0
+    assert line["config"]["workload"].startswith("Raytracer3.2.03 Whitted scene") and line["config"]["workload"].endswith("1920x1080")
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "librt_b200.so" not in p.stderr and "liboracle.so" in p.stderr

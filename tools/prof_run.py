@@ -17,6 +17,17 @@ if which in ("both", "pt"):
     for _ in range(2):
         r.pt_launch(0, 16)
     r.sync()
+if which == "bvh4":          # BASELINE config 4 itself: 783 spheres, 3840x2160 x 4 spp through the hierarchy, two launches
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "c4.scn")
+        rt.write_complex_scene(p, 4)
+        sph, cam = rt.read_scene(p, 3840, 2160)
+    seeds = rt.reference_seeds(3840, 2160)
+    r.pt_resize(3840, 2160, seeds); r.pt_set_scene(sph); r.pt_set_camera(cam)
+    for _ in range(2):
+        r.pt_launch(0, 4)
+    r.sync()
 if which == "bvh":           # the large-scene path tracer: 19 533 spheres, 1920x1080 x 4 spp, two launches
     import tempfile
     with tempfile.TemporaryDirectory() as d:
