@@ -326,6 +326,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
     F.DX = (WX2 - WX1) / ctx->w_w; F.DY = (WY2 - WY1) / ctx->w_h;
     F.hit_ids = ctx->w_want_hits ? ctx->d_whits : nullptr;
+    F.reject_k = ctx->w_cull.reject_k;
     if (ctx->counting) { F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; }         // counting launches execute every test
     else { F.pcull = ctx->d_wpcull; F.rbox = ctx->d_wrbox; F.cull_rp2 = ctx->w_cull.rp2; }   // the tables of runs_hot
     p.shard = make_shard(ctx->w_w, ctx->w_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
@@ -363,7 +364,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
         }
         p.bvh = soa.bvh.view(ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex);
         F.runs = ctx->d_wruns_bvh; F.n_runs = (int)soa.runs_bvh.size() / 3;
-        F.pcull = ctx->d_wpcull_bvh; F.rbox = ctx->d_wrbox_bvh; F.cull_rp2 = ctx->w_cull_bvh.rp2;
+        F.pcull = ctx->d_wpcull_bvh; F.rbox = ctx->d_wrbox_bvh; F.cull_rp2 = ctx->w_cull_bvh.rp2; F.reject_k = ctx->w_cull_bvh.reject_k;
         if (p.stage_mode >= 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
     } else memset(&p.bvh, 0, sizeof p.bvh);
     if (ctx->whitted_sort && p.n_items) {
@@ -501,7 +502,7 @@ int rt_r306_launch(rt_ctx *ctx) {
     F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.lcenter = R.lcenter; F.runs = R.runs; F.n_runs = R.nr;
     F.rrad = R.rrad; F.n = R.n; F.n_lights = R.nl; F.n_spheres = R.ns; F.n_planes = R.np;
     F.w = R.w; F.h = R.h; F.DX = R.DX; F.DY = R.DY; F.hit_ids = nullptr;
-    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f;
+    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f;
     p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;
     p.shard = make_shard(R.w, R.h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.dest = R.dest; p.work_counter = ctx->d_work; p.sm_count = ctx->sm_count;

@@ -425,7 +425,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 #ifdef W_ROUND_STATS
             { const unsigned m = __ballot_sync(FULL_MASK, sq); if (COUNT && lane == 0) { atomicAdd(&counters[2], 32ull); atomicAdd(&counters[3], (unsigned long long)__popc(m)); } }
 #endif
-            w_query_shadow<COUNT, (NL > 0 && !COUNT)>(L, s_geom, s_runs, F.n_runs, sq, F.pcull, F.rbox);     // NL > 0: the host made the cull tables
+            w_query_shadow<COUNT, (NL > 0 && !COUNT)>(L, s_geom, s_runs, F.n_runs, sq, F.pcull, F.rbox, F.reject_k);     // NL > 0: the host made the cull tables
             if (BVH) w_bvh_shadow_round(L, B, sq);
             if (sq) w_after_shadow<COUNT, NL>(L, F);
         }

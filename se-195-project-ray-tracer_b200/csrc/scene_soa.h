@@ -157,6 +157,7 @@ struct WCull {
     std::vector<f2> pcull;      // per primitive
     std::vector<f4> rbox;       // two per run
     float rp2 = 0.f;
+    float reject_k = 0.f;       // K of w_shadow_sphere_keep: (64 + 8 RP) u
     bool enabled = false;
     int planes_cullable = 0, runs_cullable = 0;     // for the record (tests, bench)
 };
@@ -246,6 +247,7 @@ inline void build_w_cull(const WSoA &soa, const std::vector<int> &runs, WCull &o
         if (any) out.runs_cullable++;
     }
     out.rp2 = w_cull_down(RP * RP * (1.0 - 8.0 * u));
+    out.reject_k = w_cull_up((64.0 + 8.0 * RP) * u);
     out.enabled = out.planes_cullable > 0 || out.runs_cullable > 0;
     if (!out.enabled) out.rp2 = 0.f;
 }

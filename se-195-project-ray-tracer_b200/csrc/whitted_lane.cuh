@@ -58,6 +58,7 @@ struct WFrame {
     const f4 *rbox;             // per run of `runs`: (lo.xyz, -) and (hi.xyz, -) of the run's spheres, grown by the proven margin; a face
                                 //  that does not separate the run from every light is at -+inf
     float cull_rp2;             // the culls' margins hold for hit points with |P|^2 < cull_rp2
+    float reject_k;             // K of w_shadow_sphere_keep for this scene
 };
 
 struct WLane {
@@ -301,8 +302,37 @@ RT_HD float w_fused_plane_side(const f4 g, float px, float py, float pz) {
     return fmaf(g.x, px, fmaf(g.y, py, fmaf(g.z, pz, g.w)));
 #endif
 }
+// Fused conservative reject of a sphere for the (up to three) shadow rays of a hit point P (SURVEY 7 "hard parts" 1).  The rays start at
+// o_k = fl(P + L_k EPS); with v0 = P - c the discriminant of ray k does not depend on the EPS offset (sliding the origin along the ray
+// keeps its line), so |v0|^2 - r^2 is shared by the batch and a ray costs one 3-term FMA dot product and two FMAs instead of 16 single
+// roundings.  A ray is rejected iff its fused discriminant is below -E, or the sphere lies behind it (q = v0.L > E) with the origin
+// outside (|v_k|^2 - r^2 > E): then the reference's det is negative, resp. its far root is <= 0 (w_sphere_behind's argument), whatever
+// the roundings, because E = K (|v0|^2 + r^2 + 1) with K = (64 + 8 RP) u exceeds every difference between the two evaluations: 20u
+// (|v|^2 + r^2) from the arithmetic itself (pt_bvh.cuh) and 7u |v| |P| from the rounding of o_k, |P| < RP.  NaN compares false: kept.
+// Returns the rays of `alive` that the exact test still has to look at.
+RT_HD float w_fma(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+RT_HD int w_shadow_sphere_keep(const WLane &L, const f4 g, int alive, float K) {
+    const float vx = L.px - g.x, vy = L.py - g.y, vz = L.pz - g.z;
+    const float vv = w_fma(vx, vx, w_fma(vy, vy, vz * vz));
+    const float c0 = vv - g.w, E = w_fma(K, vv + g.w, K), c1 = c0 + W_EPS * W_EPS;
+    int keep = 0;
+#pragma unroll
+    for (int k = 0; k < W_SHADOW_BATCH; k++) {
+        const float q = w_fma(vx, L.slx[k], w_fma(vy, L.sly[k], vz * L.slz[k]));
+        const float det = w_fma(q, q, -c0), ck = w_fma(2.0f * W_EPS, q, c1);
+        const bool rej = (det < -E) | ((q > E) & (ck > E));
+        keep |= (rej ? 0 : 1) << k;
+    }
+    return keep & alive;
+}
 template <bool COUNT, bool CULL = false>
-RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs, bool has, const f2 *pcull = nullptr, const f4 *rbox = nullptr) {
+RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs, bool has, const f2 *pcull = nullptr, const f4 *rbox = nullptr, float reject_k = 0.f) {
     for (int r = 0; r < n_runs; ++r) {
         const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
         if (fl & W_FLAG_LIGHT) continue;                                   // RNO:234: lights cast no shadow
@@ -318,6 +348,15 @@ RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs,
                 if (outside) alive = 0;
                 if (!warp_any(alive != 0)) continue;
             }
+#endif
+#ifndef W_NO_FUSED_REJECT
+            if (CULL) {                                                    // fused reject first, the exact test for what it keeps
+                for (int i = start; i < end; ++i) {
+                    const f4 g = geom[i];
+                    const int m = L.pnear ? w_shadow_sphere_keep(L, g, alive, reject_k) : alive;
+                    if (warp_any(m != 0)) w_shadow_sphere<COUNT>(L, g, m, has);
+                }
+            } else
 #endif
             for (int i = start; i < end; ++i) w_shadow_sphere<COUNT>(L, geom[i], alive, has);
 #ifndef W_NO_PLANE_CULL

@@ -55,13 +55,13 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
     F.DX = (WX2 - WX1) / w; F.DY = (WY2 - WY1) / h;
     F.hit_ids = hit_ids;
-    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f;
+    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f;
     WCull cull;
     if (use_runs == 4 || use_runs == 5) {      // what a timed launch does: the runs without dead primitives (5: + the hierarchy), the shadow-round culls, no counting
         if (use_runs == 5) { build_w_bvh(prims, n, soa); F.runs = soa.runs_bvh.data(); F.n_runs = (int)soa.runs_bvh.size() / 3; }
         else { F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3; }
         build_w_cull(soa, use_runs == 5 ? soa.runs_bvh : soa.runs_hot, cull);
-        F.pcull = cull.pcull.data(); F.rbox = cull.rbox.data(); F.cull_rp2 = cull.rp2;
+        F.pcull = cull.pcull.data(); F.rbox = cull.rbox.data(); F.cull_rp2 = cull.rp2; F.reject_k = cull.reject_k;
     }
     const PtBvh B5 = soa.bvh.view(soa.bvh.nodes.data(), soa.bvh.geom.data(), soa.bvh.index.data());
     uint32_t n_items;
@@ -81,7 +81,7 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
                 if (use_runs == 5) w_bvh_nearest(L, B5);
                 w_after_nearest<false>(L, F);
                 while (L.phase == PH_SHADOW) {
-                    w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox);
+                    w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
                     if (use_runs == 5) w_bvh_shadow(L, B5);
                     w_after_shadow<false>(L, F);
                 }
@@ -127,7 +127,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
     F.W.runs = soa.runs_hot.data(); F.W.n_runs = (int)soa.runs_hot.size() / 3;
     F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
     F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;
-    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f;
+    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f; F.W.reject_k = 0.f;
     F.sx = sx.data(); F.sy = sy.data(); F.row0 = 20; F.row1 = h - 70;
     R306Tree T;
     for (int y = F.row0; y < F.row1; y++)
