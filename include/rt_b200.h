@@ -131,6 +131,9 @@ enum {
                                            the expensive pixels, so that lanes whose expensive pixel is done do not idle.  Same image for any value */
     RT_TUNE_WHITTED_STAGE_CAP = 11,     /* diagnostics: cap on how much of the Whitted scene tables is staged in shared memory -- 3 static tables, 2 all tables,
                                            1 geometry / flags / runs only, 0 nothing (read through L1 / L2); -1 (default) = whatever fits.  Same image */
+    RT_TUNE_WHITTED_REDO_CAP = 12,      /* diagnostics: how many pixels the timed Whitted kernel can report for the exact launch that follows it (blocked lights
+                                           whose shade = 0 product is not provably 0, RNO:250, 270) before that launch redoes the whole frame; 0 .. 65536 (default).
+                                           Same image for any value */
     RT_TUNE_PT_BVH = 5                  /* path tracer: 1 = sphere queries walk an exact bounding-volume hierarchy (same hits, distances and tie winners as the
                                            reference's loop over every sphere), 0 = the loop, -1 (default) = by scene size.  Same image either way */
 };
@@ -223,6 +226,8 @@ int rt_timer_begin(rt_ctx *ctx);
 int rt_timer_end(rt_ctx *ctx, float *elapsed_ms);   /* synchronises on the end event */
 /* Render-path kernels launched by this context so far (one-time set-up kernels such as table fills are not counted). */
 uint64_t rt_launch_count(const rt_ctx *ctx);
+/* Diagnostics: how many shadow batches of the last timed rt_whitted_launch were reported for the exact launch (synchronises). */
+int rt_whitted_redo_reports(rt_ctx *ctx, uint32_t *reports_out);
 /* Device addresses of the context's buffers, for collectives issued by the caller (NCCL through
  * torch.distributed in bench.py) -- returns NULL if not allocated.  which: */
 enum { RT_BUF_WHITTED_PIXELS = 0, RT_BUF_WHITTED_HITS = 1, RT_BUF_PT_PIXELS = 2, RT_BUF_PT_COLORS = 3, RT_BUF_PT_SEEDS = 4 };

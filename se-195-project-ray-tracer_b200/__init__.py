@@ -46,7 +46,7 @@ class Counters(C.Structure):
 
 RT_DIFF_, RT_SPEC_, RT_REFR_ = 0, 1, 2
 RT_OK, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_ARG, RT_ERR_STATE, RT_ERR_CAPACITY, RT_ERR_IO = 0, -1, -2, -3, -4, -5, -6
-TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER, TUNE_PT_ALIGNED, TUNE_PT_BVH, TUNE_WHITTED_BVH, TUNE_R306_SPLIT, TUNE_PT_SINCOS_TABLE, TUNE_WHITTED_BLOCKS, TUNE_WHITTED_FILLER_PCT, TUNE_WHITTED_STAGE_CAP = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
+TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER, TUNE_PT_ALIGNED, TUNE_PT_BVH, TUNE_WHITTED_BVH, TUNE_R306_SPLIT, TUNE_PT_SINCOS_TABLE, TUNE_WHITTED_BLOCKS, TUNE_WHITTED_FILLER_PCT, TUNE_WHITTED_STAGE_CAP, TUNE_WHITTED_REDO_CAP = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12
 BUF_WHITTED_PIXELS, BUF_WHITTED_HITS, BUF_PT_PIXELS, BUF_PT_COLORS, BUF_PT_SEEDS = 0, 1, 2, 3, 4
 IPC_HANDLE_BYTES = 80
 
@@ -85,6 +85,7 @@ SYMBOLS = {
     "rt_timer_begin": (_I, [_VP]),
     "rt_timer_end": (_I, [_VP, C.POINTER(C.c_float)]),
     "rt_launch_count": (_U64, [_VP]),
+    "rt_whitted_redo_reports": (_I, [_VP, C.POINTER(_U32)]),
     "rt_device_buffer": (_VP, [_VP, _I, C.POINTER(_U64)]),
     "rt_selftest_math": (_I, [_VP, _I, _VP, _VP, _U64]),
     "rt_ipc_export": (_I, [_VP, _I, _VP]),
@@ -441,6 +442,12 @@ class Renderer:
 
     def launch_count(self):
         return int(self._lib.rt_launch_count(self._ctx))
+
+    def whitted_redo_reports(self):
+        """Shadow batches the last timed Whitted launch handed to the exact launch (see rt_whitted_redo_reports)."""
+        n = C.c_uint32(0)
+        self._ck(self._lib.rt_whitted_redo_reports(self._ctx, C.byref(n)))
+        return int(n.value)
 
     def set_stream(self, cuda_stream_handle):
         """Issue all work on the given cudaStream_t (an int, e.g. torch.cuda.current_stream().cuda_stream)."""

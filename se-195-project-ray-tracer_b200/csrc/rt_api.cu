@@ -24,7 +24,8 @@ struct rt_ctx {
     char err[512] = {0};
     int shard_rank = 0, shard_world = 1, tile_rows = 8;
     int counting = 0;
-    unsigned *d_work = nullptr;                    // two work counters (items, screen blocks), zeroed before each launch
+    unsigned *d_work = nullptr;                    // work counters (items, screen blocks, Whitted redo reports, the redo launch's items), zeroed before each launch
+    uint32_t *d_wredo = nullptr;                   // Whitted: pixels reported for the EXACT launch (RT_WHITTED_REDO_CAP entries)
     unsigned long long *d_counters = nullptr;      // 8 x u64
     uint64_t launches = 0;
     // tuning
@@ -53,6 +54,7 @@ struct rt_ctx {
     uint8_t *d_wcls = nullptr; size_t wcls_cap = 0;
     int whitted_blocks = 1;                        // class-2 pixels as whole screen blocks per warp (needs whitted_sort)
     int w_stage_cap = -1;                          // RT_TUNE_WHITTED_STAGE_CAP
+    unsigned w_redo_cap = RT_WHITTED_REDO_CAP;     // RT_TUNE_WHITTED_REDO_CAP
     int whitted_filler_pct = 25;                   // ... except this share of the frame, which fills idle lanes pixel by pixel
     unsigned *d_wclass = nullptr;
     // Whitted
@@ -172,7 +174,8 @@ int rt_init(rt_ctx **out, int device) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if ((e = cudaMalloc((void **)&ctx->d_work, 2 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_work, 4 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void **)&ctx->d_wredo, RT_WHITTED_REDO_CAP * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
     *out = ctx;
@@ -185,7 +188,7 @@ void rt_destroy(rt_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->peer_wpixels) cudaIpcCloseMemHandle(ctx->peer_wpixels);
     if (ctx->peer_ppixels) cudaIpcCloseMemHandle(ctx->peer_ppixels);
-    void *bufs[] = { ctx->d_work, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
+    void *bufs[] = { ctx->d_work, ctx->d_wredo, ctx->d_counters, ctx->d_wgeom, ctx->d_wma, ctx->d_wmb, ctx->d_wflags, ctx->d_wlights, ctx->d_wruns, ctx->d_wruns_hot, ctx->d_wlcenter, ctx->d_worder, ctx->d_wclass,
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex,
                      ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh, ctx->d_sincos,
@@ -255,6 +258,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_PT_SINCOS_TABLE: ctx->pt_sincos_table = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_FILLER_PCT: if (value < 0 || value > 100) break; ctx->whitted_filler_pct = value; return RT_OK;
+        case RT_TUNE_WHITTED_REDO_CAP: if (value < 0 || value > (int)RT_WHITTED_REDO_CAP) break; ctx->w_redo_cap = (unsigned)value; return RT_OK;
         case RT_TUNE_WHITTED_STAGE_CAP: if (value < -1 || value > 3) break; ctx->w_stage_cap = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
@@ -326,12 +330,14 @@ int rt_whitted_launch(rt_ctx *ctx) {
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
     F.DX = (WX2 - WX1) / ctx->w_w; F.DY = (WY2 - WY1) / ctx->w_h;
     F.hit_ids = ctx->w_want_hits ? ctx->d_whits : nullptr;
+    F.tame_reach[0] = ctx->w_soa.tame_reach[0]; F.tame_reach[1] = ctx->w_soa.tame_reach[1]; F.redo_count = ctx->counting ? nullptr : ctx->d_work + 2; F.redo_list = ctx->d_wredo; F.redo_cap = ctx->w_redo_cap;
     F.reject_k = ctx->w_cull.reject_k;
     if (ctx->counting) { F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; }         // counting launches execute every test
     else { F.pcull = ctx->d_wpcull; F.rbox = ctx->d_wrbox; F.cull_rp2 = ctx->w_cull.rp2; }   // the tables of runs_hot
     p.shard = make_shard(ctx->w_w, ctx->w_h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.pixels = ctx->peer_wpixels ? ctx->peer_wpixels : ctx->d_wpixels;     // fused gather: store straight into rank 0's frame
     p.work_counter = ctx->d_work; p.counters = ctx->d_counters;
+    p.redo_work_counter = (ctx->counting || ctx->w_nl == 0) ? nullptr : ctx->d_work + 3;      // no lights: no shadow batches, nothing to report
     p.count = ctx->counting; p.sm_count = ctx->sm_count; p.max_blocks_per_sm = ctx->max_blocks_per_sm;
     // sized with the LARGEST run table a launch of this scene may stage (all primitives / without the dead ones / without
     // what the hierarchy holds: splitting runs can add runs), so that the choice never overshoots the per-CTA budget
@@ -387,9 +393,9 @@ int rt_whitted_launch(rt_ctx *ctx) {
             p.filler_items = (uint32_t)((uint64_t)p.n_items * (uint32_t)ctx->whitted_filler_pct / 100u) & ~31u;
         }
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += p.order ? 2 : 1; }
+    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.redo_work_counter ? 1 : 0); }
     return RT_OK;
 }
 
@@ -502,7 +508,7 @@ int rt_r306_launch(rt_ctx *ctx) {
     F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.lcenter = R.lcenter; F.runs = R.runs; F.n_runs = R.nr;
     F.rrad = R.rrad; F.n = R.n; F.n_lights = R.nl; F.n_spheres = R.ns; F.n_planes = R.np;
     F.w = R.w; F.h = R.h; F.DX = R.DX; F.DY = R.DY; F.hit_ids = nullptr;
-    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f;
+    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f; F.tame_reach[0] = F.tame_reach[1] = 0.f; F.redo_count = nullptr; F.redo_list = nullptr; F.redo_cap = 0;
     p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;
     p.shard = make_shard(R.w, R.h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.dest = R.dest; p.work_counter = ctx->d_work; p.sm_count = ctx->sm_count;
@@ -528,7 +534,7 @@ int rt_r306_launch(rt_ctx *ctx) {
         if (!ctx->d_wclass) CK(cudaMalloc((void **)&ctx->d_wclass, 4 * sizeof(unsigned)));
         p.order = ctx->d_worder; p.class_counts = ctx->d_wclass;
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(unsigned), ctx->stream));
     if (p.n_items) { CK(rtk_launch_r306(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.subcol ? 1 : 0); }
     return RT_OK;
 }
@@ -683,7 +689,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
         }
         p.bvh = ctx->p_bvh.view(ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex);
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches += F.defer_pack ? 2 : 1; }
     ctx->current_sample += n_passes;
@@ -759,6 +765,14 @@ int rt_timer_end(rt_ctx *ctx, float *elapsed_ms) {
 }
 
 uint64_t rt_launch_count(const rt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int rt_whitted_redo_reports(rt_ctx *ctx, uint32_t *reports_out) {
+    if (!ctx || !reports_out) return RT_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(reports_out, ctx->d_work + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
 
 void *rt_device_buffer(rt_ctx *ctx, int which, uint64_t *bytes) {
     if (!ctx) return nullptr;

@@ -350,7 +350,9 @@ __device__ __forceinline__ void w_bvh_shadow_round(WLane &L, const PtBvh &B, boo
 
 // BVH: the run tables hold only what is not in the hierarchy B (planes, lights, odd spheres); after them every query
 // continues in the tree, lane by lane (whitted_bvh.cuh) -- scenes of hundreds to thousands of spheres.
-template <bool COUNT, int STAGED, int NL, bool BVH>
+// EXACT: the launch that follows the timed kernel (whitted_lane.cuh, "Blocked lights and the redo list"): the pixels of F.redo_list --
+// or every item when more were reported than the list holds -- one per lane, blocked lights shaded as the reference shades them.
+template <bool COUNT, int STAGED, int NL, bool BVH, bool EXACT = false>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
                uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B, const uint8_t *cls, uint32_t filler_items) {
@@ -376,7 +378,9 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
     // lane with most lanes idle (25 of 32 lanes per instruction in that phase).
     const uint32_t n_listed = (order && cls) ? class_counts[0] + class_counts[1] : 0u;
     const uint32_t n_filler = (order && cls) ? filler_items : 0u;            // items [0, n_filler) of class 2: by single lanes (a multiple of 32)
-    const uint32_t n_lane_items = (order && cls) ? n_listed + n_filler : n_items;
+    const unsigned n_redo = EXACT ? *F.redo_count : 0u;
+    const bool redo_all = EXACT && n_redo > F.redo_cap;
+    const uint32_t n_lane_items = EXACT ? (redo_all ? n_items : n_redo) : (order && cls) ? n_listed + n_filler : n_items;
     const uint32_t n_blocks = cls ? n_stride >> 5 : 0u;
 
     for (;;) {
@@ -393,7 +397,8 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
                     if (cls && item >= n_listed) { it = item - n_listed; take = cls[it] == 2; }     // filler: a class-2 pixel of the first blocks
                     else it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
                 }
-                if (take && item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
+                if (EXACT && !redo_all) { const uint32_t id = F.redo_list[item]; w_begin_pixel(L, F, (int)(id % (uint32_t)F.w), (int)(id / (uint32_t)F.w)); }
+                else if (take && item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
             } else exhausted = true;
         }
         if (!__any_sync(FULL_MASK, L.phase != PH_IDLE || !exhausted)) {
@@ -419,7 +424,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 #endif
         w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
         if (BVH) w_bvh_nearest_round(L, B, nq);
-        if (nq) w_after_nearest<COUNT, NL>(L, F);
+        if (nq) w_after_nearest<COUNT, NL, EXACT>(L, F);
         while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
             const bool sq = L.phase == PH_SHADOW;
 #ifdef W_ROUND_STATS
@@ -427,7 +432,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 #endif
             w_query_shadow<COUNT, (NL > 0 && !COUNT)>(L, s_geom, s_runs, F.n_runs, sq, F.pcull, F.rbox, F.reject_k);     // NL > 0: the host made the cull tables
             if (BVH) w_bvh_shadow_round(L, B, sq);
-            if (sq) w_after_shadow<COUNT, NL>(L, F);
+            if (sq) w_after_shadow<COUNT, NL, EXACT>(L, F);
         }
         if (L.phase == PH_FINAL && w_finalize<COUNT>(L, F, queue)) {
             RT_CHECK(L.x >= 0 && L.x < F.w && L.y >= 0 && L.y < F.h, RT_CHK_PIXEL);
@@ -780,6 +785,18 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     }
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
                                                   p.counters, p.bvh, p.order ? p.cls : nullptr, p.filler_items);
+    if ((e = cudaGetLastError()) != cudaSuccess || !p.redo_work_counter) return e;
+    // The pixels the timed kernel reported (blocked lights it may not skip), again, as the reference computes them.  Launched without
+    // looking at the count -- that would be a round trip to the host; a launch that finds the list empty is a few microseconds.
+    kern_t kx = bvh ? (p.stage_mode == 0 ? whitted_kernel<false, 0, 0, true, true> : whitted_kernel<false, 1, 0, true, true>)
+              : p.stage_mode == 0 ? whitted_kernel<false, 0, 0, false, true> : p.stage_mode == 1 ? whitted_kernel<false, 1, 0, false, true>
+              : p.stage_mode == 3 ? whitted_kernel<false, 3, 0, false, true> : whitted_kernel<false, 2, 0, false, true>;
+    int nbx = 0;
+    if ((e = configure_kernel(kx, W_THREADS, smem, &nbx)) != cudaSuccess) return e;
+    long gridx = (long)nbx * p.sm_count;
+    if (gridx > need) gridx = need > 0 ? need : 1;
+    kx<<<(unsigned)gridx, W_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, nullptr, nullptr, p.n_items, p.pixels, p.redo_work_counter,
+                                                    p.counters, p.bvh, nullptr, 0u);
     return cudaGetLastError();
 }
 

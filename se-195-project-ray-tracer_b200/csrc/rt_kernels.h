@@ -71,6 +71,7 @@ struct WLaunch {
     uint32_t n_items;
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
+    unsigned *redo_work_counter; // NULL: no EXACT launch after the kernel (counting launches); else its work counter (frame.redo_* name the list)
     int count, sm_count, max_blocks_per_sm;
     int stage_mode;             // 3: all tables in static shared memory (small scenes), 2: all tables in dynamic shared memory, 1: geometry / flags / runs only, 0: read through L1 / L2
     int sphere_lights;          // number of lights when all of them are spheres, else 0
@@ -104,6 +105,7 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);
 size_t rtk_whitted_smem_bytes(int n, int n_lights, int n_runs, int stage_mode);
 #define W_TAB_CAP 64                              /* stage mode 3: static shared-memory tables for scenes of at most this many primitives ... */
 #define W_TAB_RUNS 24                             /* ... in at most this many runs */
+#define RT_WHITTED_REDO_CAP 65536u               /* pixels the timed Whitted kernel can hand to the EXACT launch; more: that launch redoes the frame */
 #define RTK_WHITTED_STAGE_LIMIT (18 * 1024)      /* per-CTA share of shared memory with 12 resident CTAs per SM */
 cudaError_t rtk_launch_selftest_math(int op, const float *in, void *out, unsigned long long n, int sm_count, cudaStream_t stream);
 long long rtk_read_check_flags();            /* -DRT_DEVICE_CHECKS builds: bit mask of failed device-side bounds checks (cleared by the read); -1 otherwise */

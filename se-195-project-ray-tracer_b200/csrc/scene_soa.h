@@ -43,12 +43,24 @@ struct WSoA {
     std::vector<int> runs_hot;          // the same runs without primitives that can never be hit (timed launches use these)
     std::vector<float> rrad;
     int n_spheres = 0, n_planes = 0;
+    float tame_reach[2] = { 0.f, 0.f }; // WFrame::tame_reach of this table (w_scene_tame_reach below)
     // large scenes (build_w_bvh): the non-light spheres in the exact hierarchy of pt_bvh.cuh, and the run table of
     // everything else that can be hit (planes, lights, spheres the tree does not take) -- what every query still walks
     PtBvhHost bvh;
     std::vector<int> runs_bvh;
     int n_tree = 0;
 };
+
+
+// WFrame::tame_reach: how close to every light of its batch a hit point must be for the timed kernels to skip a BLOCKED light instead of
+// shading it with shade = 0 as the reference does (RNO:250, 270).  Skipping is right only when 0 times every factor is +-0, that is when
+// nothing in the two terms can be inf or NaN.  The kernel checks the per-ray part (|d| < 1e3, distance to each light of the batch inside
+// (1e-18, tame_reach): whitted_lane.cuh); this is the scene's part, in double with room for the float roundings: colours, m_diff and m_spec
+// finite; |N| <= nmax at any hit point that close to a light (plane: |normal|; sphere: (|P - c_l| + |c_l - c|) / r), so that
+// |N.L| m_diff <= nmax m_diff fits a float and |V.R| <= |d| |L| (1 + 2 |N|^2) to the 20th power times m_spec fits a double.
+// out[0]: the largest such distance for hit points on planes (N is the plane's own normal: any distance whose square is a float, 1e18, if the
+// normals allow it), out[1]: on spheres; 0 when there is none (every such batch is then reported, and the EXACT kernel renders those pixels).
+inline void w_scene_tame_reach(const struct WSoA &s, int n, float out[2]);
 
 inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
     out.geom.resize(n); out.mat_a.resize(n); out.mat_b.resize(n); out.flags.resize(n); out.rrad.resize(n);
@@ -74,6 +86,7 @@ inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
         f4 b = { p[i].m_diff, p[i].m_refr, p[i].m_refr_index, p[i].m_spec };
         out.geom[i] = g; out.mat_a[i] = a; out.mat_b[i] = b; out.flags[i] = fl; out.rrad[i] = p[i].r_radius;
     }
+    w_scene_tame_reach(out, n, out.tame_reach);
     // Index order is part of the result (ties), so the kernel walks the primitives in order -- but as runs
     // of equal (type, is_light), which takes the type dispatch out of the inner loop.
     out.runs.clear();
@@ -95,6 +108,44 @@ inline void build_w_soa(const rt_primitive *p, int n, WSoA &out) {
         out.runs_hot.push_back(i); out.runs_hot.push_back(j - i); out.runs_hot.push_back(out.flags[i]);
         i = j;
     }
+}
+
+inline void w_scene_tame_reach(const WSoA &s, int n, float out[2]) {
+    out[0] = out[1] = 0.f;
+    const double dmax = 1e3;                        // sqrt(W_TAME_D2)
+    double spec = 0.0, diff = 0.0, plane_n = 0.0, far = 0.0, rrad = 0.0;
+    for (int i = 0; i < n; i++) {
+        const f4 a = s.mat_a[i], b = s.mat_b[i], g = s.geom[i];
+        for (float v : { a.x, a.y, a.z, b.x, b.w }) if (!(std::fabs(v) < 1e30f)) return;         // NaN lands here too
+        spec = std::max(spec, (double)std::fabs(b.w)); diff = std::max(diff, (double)std::fabs(b.x));
+        if (s.flags[i] & W_FLAG_SPHERE) {
+            for (const f4 &c : s.lcenter) {
+                const double ex = (double)c.x - g.x, ey = (double)c.y - g.y, ez = (double)c.z - g.z;
+                const double e = std::sqrt(ex * ex + ey * ey + ez * ez);
+                if (!(e < 1e30)) return;
+                far = std::max(far, e);
+            }
+            if (!(std::fabs(s.rrad[i]) < 1e30f)) return;
+            rrad = std::max(rrad, (double)std::fabs(s.rrad[i]));
+        } else {
+            const double e = std::sqrt((double)g.x * g.x + (double)g.y * g.y + (double)g.z * g.z);
+            if (!(e < 1e30)) return;
+            plane_n = std::max(plane_n, e * 1.001);
+        }
+    }
+    // the largest |N| the two products allow
+    const double vmax = std::pow(10.0, (300.0 - std::log10(std::max(spec, 1e-300))) / 20.0);      // |V.R| below this: pow(V.R, 20) m_spec < 1e300
+    const double q = (vmax / (3.0 * 1.001 * dmax) - 1.001) / 2.004;                                // 1 + 2 |N|^2 (with roundings) below vmax / (3 |d|)
+    if (!(q > 0.0)) return;
+    double nmax = std::sqrt(q);
+    if (diff > 0.0) nmax = std::min(nmax, 1e37 / (1.01 * diff));
+    if (plane_n < nmax) out[0] = 1e18f;
+    double reach = 1e18;
+    if (rrad > 0.0) reach = std::min(reach, (nmax / (rrad * 1.001) - far) / 1.001);
+    if (!(reach > 0.0)) return;
+    float r = (float)reach;
+    if ((double)r > reach) r = nextafterf(r, 0.f);
+    out[1] = r;
 }
 
 // The hierarchy over the non-light spheres of a Whitted scene table, after build_w_soa.  Lights stay in the run table

@@ -59,6 +59,12 @@ struct WFrame {
                                 //  that does not separate the run from every light is at -+inf
     float cull_rp2;             // the culls' margins hold for hit points with |P|^2 < cull_rp2
     float reject_k;             // K of w_shadow_sphere_keep for this scene
+    // Blocked lights (see "Blocked lights and the redo list" below).
+    float tame_reach[2];        // a hit point on a plane [0] / a sphere [1] closer than this to every light of its batch may skip its blocked lights;
+                                //  0: none may (build_w_soa)
+    unsigned *redo_count;       // NULL (EXACT / counting launches), or the number of pixels reported so far
+    uint32_t *redo_list;        // pixel numbers y * w + x of the first redo_cap reports
+    unsigned redo_cap;
 };
 
 struct WLane {
@@ -464,6 +470,30 @@ RT_HD void w_shade(WLane &L, const WFrame &F, int l, float Lx, float Ly, float L
     w_shade_with(L, F.mat_a[L.hit], F.mat_b[L.hit], F.mat_a[l], nx, ny, nz, Lx, Ly, Lz, lit);
 }
 
+// Blocked lights and the redo list.  A blocked light does not add "nothing": the reference multiplies both terms by shade = 0 (RNO:250,
+// 270), and 0 times a factor that is not finite is NaN.  That happens -- a refraction direction is not re-normalised, a few bounces later
+// |d| is 10^3 .. 10^7, pow(V.R, 20) overflows the double and the pixel's accumulator turns NaN, which x86's (int) makes a black pixel (found
+// by tools/cull_fuzz.py on a random room; round 1 skipped blocked lights outright).  EXACT kernels and counting launches shade every
+// blocked light with shade = 0 as the reference does.  The timed kernel skips a blocked light -- which is only right when every factor is
+// PROVABLY finite, so that the products with 0 are +-0 and change no sum that started at +0: the scene's tables are bounded (host,
+// w_scene_tame_reach), |d|^2 < W_TAME_D2 and every distance to a light of the batch lies inside (1e-18, F.tame_reach[kind of the hit]).  This is decided
+// when a batch is set up, from values that are in registers there; a batch that fails REPORTS ITS PIXEL (w_report_untame) and carries on,
+// and an EXACT launch over the reported pixels follows the timed kernel and overwrites them (a handful per frame in scenes that have
+// any; more reports than the list holds: the EXACT launch redoes the frame).  Anything inline in the timed kernel -- keeping the distances
+// alive into the shading code, a call to an out-of-line exact shader -- cost 5-12 % of the 1080p frame through register pressure alone.
+#define W_TAME_D2 1e6f
+RT_HD bool w_reach_is_tame(float reach, float cap) { return (reach > 1e-18f) & (reach < cap); }                     // NaN: false
+RT_HD bool w_dir_is_tame(const WLane &L) { return dot3(L.dx, L.dy, L.dz, L.dx, L.dy, L.dz) < W_TAME_D2; }           // NaN: false
+RT_HD void w_report_untame(const WLane &L, const WFrame &F) {
+    if (!F.redo_count) return;
+#ifdef __CUDA_ARCH__
+    const unsigned at = atomicAdd(F.redo_count, 1u);
+#else
+    const unsigned at = (*F.redo_count)++;
+#endif
+    if (at < F.redo_cap) F.redo_list[at] = (uint32_t)L.y * (uint32_t)F.w + (uint32_t)L.x;
+}
+
 // Sets up the next batch of shadow rays (lights li, li+1, ... in index order, RNO:206-241), or marks the
 // ray complete when no light is left.  A light that is not a sphere casts no shadow ray (RNO:223) and is
 // shaded on the spot -- but only when no batch is pending before it, so that the float accumulation keeps
@@ -482,6 +512,7 @@ RT_HD void w_shade_unshadowed(WLane &L, const WFrame &F, int l, int li) {
     const float inv = f_rcp(f_sqrt(f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(ez, ez))));
     w_shade(L, F, l, f_mul(inv, ex), f_mul(inv, ey), f_mul(inv, ez), 1.0f);
 }
+template <bool EXACT>
 RT_HD void w_next_shadow_batch(WLane &L, const WFrame &F) {
     for (;;) {
         if (L.li >= F.n_lights) { L.phase = PH_FINAL; return; }
@@ -491,6 +522,8 @@ RT_HD void w_next_shadow_batch(WLane &L, const WFrame &F) {
         L.li++;
     }
     L.ns = 0; L.sblk = 0;
+    bool tame = w_dir_is_tame(L);
+    const float cap = (F.flags[L.hit] & W_FLAG_SPHERE) ? F.tame_reach[1] : F.tame_reach[0];
 #pragma unroll
     for (int k = 0; k < W_SHADOW_BATCH; k++) {
         if (L.ns == k && L.li + k < F.n_lights && (F.flags[F.lights[L.li + k]] & W_FLAG_SPHERE)) {
@@ -498,30 +531,36 @@ RT_HD void w_next_shadow_batch(WLane &L, const WFrame &F) {
             w_light_vector(F, L, F.lights[L.li + k], Lx, Ly, Lz, reach);
             L.sox[k] = f_add(L.px, f_mul(Lx, W_EPS)); L.soy[k] = f_add(L.py, f_mul(Ly, W_EPS)); L.soz[k] = f_add(L.pz, f_mul(Lz, W_EPS));
             L.slx[k] = Lx; L.sly[k] = Ly; L.slz[k] = Lz; L.sreach[k] = reach;
+            tame &= w_reach_is_tame(reach, cap);
             L.ns = k + 1;
         }
     }
+    if (!EXACT && !tame) w_report_untame(L, F);
     L.phase = PH_SHADOW;
 }
 
 // The common case as straight-line code: exactly NL (<= W_SHADOW_BATCH) lights, all of them spheres (the reference's
 // scenes: 3), so the one batch holds lights[0 .. NL-1] and no selects, cursors or type checks are needed.  Same
 // operations in the same order as the general functions (NL = 0 selects those).
-template <int NL>
+template <int NL, bool EXACT>
 RT_HD void w_shadow_batch_fixed(WLane &L, const WFrame &F) {
-    L.sblk = 0; L.ns = NL;
+    L.ns = NL; L.sblk = 0;
+    bool tame = w_dir_is_tame(L);
+    const float cap = (F.flags[L.hit] & W_FLAG_SPHERE) ? F.tame_reach[1] : F.tame_reach[0];
 #pragma unroll
     for (int k = 0; k < NL; k++) {
         float Lx, Ly, Lz, reach;
         w_light_vector(F, L, F.lights[k], Lx, Ly, Lz, reach);
         L.sox[k] = f_add(L.px, f_mul(Lx, W_EPS)); L.soy[k] = f_add(L.py, f_mul(Ly, W_EPS)); L.soz[k] = f_add(L.pz, f_mul(Lz, W_EPS));
         L.slx[k] = Lx; L.sly[k] = Ly; L.slz[k] = Lz; L.sreach[k] = reach;
+        tame &= w_reach_is_tame(reach, cap);
     }
+    if (!EXACT && !tame) w_report_untame(L, F);
     L.phase = PH_SHADOW;
 }
 
 // After the nearest-hit round (RNO:194-205).
-template <bool COUNT, int NL = 0>
+template <bool COUNT, int NL = 0, bool EXACT = false>
 RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
     if (COUNT) { L.c_nearest++; L.c_sphere_tests += (uint32_t)F.n_spheres; L.c_plane_tests += (uint32_t)F.n_planes; }
     L.dist = L.cumu; L.hit = L.qhit; L.hkind = L.qkind;
@@ -552,16 +591,17 @@ RT_HD void w_after_nearest(WLane &L, const WFrame &F) {
             if (!COUNT) { const f4 mb = F.mat_b[L.hit]; if (!(mb.x > 0.f) & !(mb.w > 0.f)) return; }
 #endif
 #endif
-            if (NL > 0) w_shadow_batch_fixed<NL>(L, F);
-            else w_next_shadow_batch(L, F);
+            if (NL > 0) w_shadow_batch_fixed<NL, (EXACT || COUNT)>(L, F);
+            else w_next_shadow_batch<(EXACT || COUNT)>(L, F);
         }
     }
 }
 
-// After a shadow round: shade the batch's lights in index order (a blocked light adds exactly 0, so it is
-// skipped), then set up the next batch or complete the ray.
-template <bool COUNT, int NL = 0>
+// After a shadow round: shade the batch's lights in index order, then set up the next batch or complete the ray.  A blocked light:
+// shaded with shade = 0 in EXACT kernels and counting launches, skipped otherwise (see "Blocked lights and the redo list").
+template <bool COUNT, int NL = 0, bool EXACT = false>
 RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
+    constexpr bool AS_REFERENCE = EXACT || COUNT;
     if (COUNT) {
         L.c_shadow += (uint32_t)L.ns;
         const f4 mbc = F.mat_b[L.hit];
@@ -580,7 +620,9 @@ RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
             const float Lx = k == 0 ? L.slx[0] : (k == 1 ? L.slx[NL > 1 ? 1 : 0] : L.slx[NL > 2 ? 2 : 0]);
             const float Ly = k == 0 ? L.sly[0] : (k == 1 ? L.sly[NL > 1 ? 1 : 0] : L.sly[NL > 2 ? 2 : 0]);
             const float Lz = k == 0 ? L.slz[0] : (k == 1 ? L.slz[NL > 1 ? 1 : 0] : L.slz[NL > 2 ? 2 : 0]);
-            if (!((L.sblk >> k) & 1)) w_shade_with(L, ma, mb, F.mat_a[F.lights[k]], nx, ny, nz, Lx, Ly, Lz, 1.0f);
+            const bool blocked = (L.sblk >> k) & 1;
+            if (AS_REFERENCE) w_shade_with(L, ma, mb, F.mat_a[F.lights[k]], nx, ny, nz, Lx, Ly, Lz, blocked ? 0.0f : 1.0f);
+            else if (!blocked) w_shade_with(L, ma, mb, F.mat_a[F.lights[k]], nx, ny, nz, Lx, Ly, Lz, 1.0f);
         }
         L.phase = PH_FINAL;
         return;
@@ -590,10 +632,12 @@ RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
         const float Lx = k == 0 ? L.slx[0] : (k == 1 ? L.slx[1] : L.slx[2]);
         const float Ly = k == 0 ? L.sly[0] : (k == 1 ? L.sly[1] : L.sly[2]);
         const float Lz = k == 0 ? L.slz[0] : (k == 1 ? L.slz[1] : L.slz[2]);
-        if (!((L.sblk >> k) & 1)) w_shade(L, F, F.lights[L.li + k], Lx, Ly, Lz, 1.0f);
+        const bool blocked = (L.sblk >> k) & 1;
+        if (AS_REFERENCE) w_shade(L, F, F.lights[L.li + k], Lx, Ly, Lz, blocked ? 0.0f : 1.0f);
+        else if (!blocked) w_shade(L, F, F.lights[L.li + k], Lx, Ly, Lz, 1.0f);
     }
     L.li += L.ns;
-    w_next_shadow_batch(L, F);
+    w_next_shadow_batch<AS_REFERENCE>(L, F);
 }
 
 // The ray is complete: fold its colour into the pixel (RNO:351-368), spawn its children (RNO:370-432) and move

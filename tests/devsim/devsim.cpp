@@ -38,6 +38,13 @@ uint32_t devsim_cover(int w, int h, int rank, int world, int tile_rows, int32_t 
     return n_items;
 }
 
+// WFrame::tame_reach the host computes for a scene table (scene_soa.h).
+void devsim_whitted_tame_reach(const rt_primitive *prims, int n, float *out2) { WSoA soa; build_w_soa(prims, n, soa); out2[0] = soa.tame_reach[0]; out2[1] = soa.tame_reach[1]; }
+
+// Pixels of the last timed-mode devsim_whitted call that went through the EXACT pass.
+static long g_redo_pixels = 0;
+long devsim_whitted_redo_pixels() { return g_redo_pixels; }
+
 // Whitted frame through the lane state machine (rows owned by rank/world/tile_rows only).
 void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_primitive *prims, int n,
                     int rank, int world, int tile_rows, uint64_t *counters5, float *acc_out /* NULL or w*h*3 */, int use_runs) {
@@ -55,6 +62,9 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
     F.DX = (WX2 - WX1) / w; F.DY = (WY2 - WY1) / h;
     F.hit_ids = hit_ids;
+    unsigned redo_count = 0;
+    uint32_t redo_one[1];
+    F.tame_reach[0] = soa.tame_reach[0]; F.tame_reach[1] = soa.tame_reach[1]; F.redo_count = nullptr; F.redo_list = redo_one; F.redo_cap = 1;
     F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f;
     WCull cull;
     if (use_runs == 4 || use_runs == 5) {      // what a timed launch does: the runs without dead primitives (5: + the hierarchy), the shadow-round culls, no counting
@@ -68,15 +78,18 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     Shard S = make_shard(w, h, rank, world, tile_rows, &n_items);
     f4 queue[3 * W_QUEUE_SLOTS];
     uint64_t c[5] = {0, 0, 0, 0, 0};
+    g_redo_pixels = 0;
     for (uint32_t it = 0; it < n_items; it++) {
         int x, y;
         if (!item_to_pixel(S, w, it, x, y)) continue;
         WLane L;
         memset(&L, 0, sizeof L);
         w_begin_pixel(L, F, x, y);
-        for (;;) {
-            // the body of the kernel's loop, for one lane
-            if (use_runs >= 4) {
+        if (use_runs >= 4) {
+            // the body of the timed kernel's loop, for one lane -- and, when the pixel reported a batch whose blocked lights may not be
+            // skipped, the pixel again as the EXACT launch computes it (whitted_lane.cuh, "Blocked lights and the redo list")
+            redo_count = 0; F.redo_count = &redo_count;
+            for (;;) {
                 w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);
                 if (use_runs == 5) w_bvh_nearest(L, B5);
                 w_after_nearest<false>(L, F);
@@ -86,8 +99,24 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
                     w_after_shadow<false>(L, F);
                 }
                 if (w_finalize<false>(L, F, queue)) break;
-                continue;
             }
+            if (redo_count) {
+                g_redo_pixels++;
+                memset(&L, 0, sizeof L);
+                w_begin_pixel(L, F, x, y);
+                for (;;) {
+                    w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);
+                    if (use_runs == 5) w_bvh_nearest(L, B5);
+                    w_after_nearest<false, 0, true>(L, F);
+                    while (L.phase == PH_SHADOW) {
+                        w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
+                        if (use_runs == 5) w_bvh_shadow(L, B5);
+                        w_after_shadow<false, 0, true>(L, F);
+                    }
+                    if (w_finalize<false>(L, F, queue)) break;
+                }
+            }
+        } else for (;;) {
             w_query_nearest<true>(L, F.geom, F.runs, F.n_runs, true);
             if (use_runs == 3) w_bvh_nearest(L, B);
             w_after_nearest<true>(L, F);
@@ -127,7 +156,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
     F.W.runs = soa.runs_hot.data(); F.W.n_runs = (int)soa.runs_hot.size() / 3;
     F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
     F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;
-    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f; F.W.reject_k = 0.f;
+    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f; F.W.reject_k = 0.f; F.W.tame_reach[0] = F.W.tame_reach[1] = 0.f; F.W.redo_count = nullptr; F.W.redo_list = nullptr; F.W.redo_cap = 0;
     F.sx = sx.data(); F.sy = sy.data(); F.row0 = 20; F.row1 = h - 70;
     R306Tree T;
     for (int y = F.row0; y < F.row1; y++)

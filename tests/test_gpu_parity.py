@@ -252,12 +252,45 @@ def test_whitted_shadow_culls_against_oracle_on_moved_lights_and_random_rooms(gp
     spec = importlib.util.spec_from_file_location("cull_fuzz", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "cull_fuzz.py"))
     fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
     rs = np.random.RandomState(11)
-    cases = [(near, 320, 240), (below, 320, 240), (inside, 320, 240)] + [(fz.random_scene(rt, rs, box), 96, 72) for _ in range(60)]
+    nan_scene = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whitted_blocked_light_nan.npy"))   # a blocked light times an overflowed pow() is NaN
+    cases = [(near, 320, 240), (below, 320, 240), (inside, 320, 240), (nan_scene, 64, 48), (nan_scene, 256, 192)] + [(fz.random_scene(rt, rs, box), 96, 72) for _ in range(60)]
     for k, (prims, w, h) in enumerate(cases):
         px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
         px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
         assert np.array_equal(hits, hits_o), k
         assert np.array_equal(px, px_o), k
+
+
+def test_whitted_blocked_lights_of_untame_batches_go_through_the_exact_launch(gpu, rt, orc):
+    """RNO:250, 270 multiply a blocked light's terms by shade = 0; 0 * inf = NaN when pow(V.R, 20) overflowed (ray directions are not
+    re-normalised after a refraction).  The timed kernel skips blocked lights, reports the pixels where that is not provably the same, and an
+    exact launch redoes them: the scene that exposed it (tools/cull_fuzz.py) must report pixels and equal the oracle -- with the list large
+    enough, too small (that launch then redoes the frame) and absent; a scene whose tables allow no skipping at all (a sphere of radius
+    1e-7: |N| is not bounded) likewise; the reference's own scene reports nothing."""
+    import os
+    nan_scene = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whitted_blocked_light_nan.npy"))
+    w, h = 256, 192
+    px_o, hits_o, _ = oracle_whitted(orc, nan_scene, w, h)
+    try:
+        for cap in (65536, 1, 0):
+            gpu.set_tuning(rt.TUNE_WHITTED_REDO_CAP, cap)
+            n0 = gpu.launch_count()
+            px, hits = gpu.whitted_render(nan_scene, w, h, want_hit_ids=True)
+            assert gpu.launch_count() - n0 == 3                  # pre-pass, timed kernel, exact launch
+            assert gpu.whitted_redo_reports() > 1, cap
+            assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o), cap
+    finally:
+        gpu.set_tuning(rt.TUNE_WHITTED_REDO_CAP, 65536)
+    prims = rt.whitted_create_scene(0)
+    px, _ = gpu.whitted_render(prims, 320, 240, want_hit_ids=True)
+    assert gpu.whitted_redo_reports() == 0
+    tiny = prims.copy()
+    k = [i for i in range(tiny.size) if tiny[i]["type"] == 1 and not tiny[i]["is_light"]][0]
+    tiny[k]["r_radius"] = np.float32(1e7); tiny[k]["sq_radius"] = np.float32(1e-14); tiny[k]["radius"] = np.float32(1e-7)
+    px, hits = gpu.whitted_render(tiny, 160, 120, want_hit_ids=True)
+    assert gpu.whitted_redo_reports() > 160 * 120               # every shadow batch of the frame
+    px_o, hits_o, _ = oracle_whitted(orc, tiny, 160, 120)
+    assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
 
 
 def test_whitted_counters_equal_oracle(gpu, orc, rt):

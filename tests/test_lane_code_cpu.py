@@ -273,6 +273,34 @@ def test_whitted_shadow_culls_change_nothing(devsim, orc, rt, tmp_path):
         assert np.array_equal(px, px_o), k
 
 
+def test_whitted_blocked_light_times_an_overflowed_specular_term_is_nan_like_the_reference(devsim, orc, rt, ref_whitted):
+    """The reference multiplies both shading terms by shade = 0 for a blocked light (RNO:250, 270); when a ray's direction has blown up
+    (refraction directions are not re-normalised), pow(V.R, 20) is inf and inf * 0 = NaN: the accumulator turns NaN and the pixel black.
+    Round 1 skipped blocked lights outright and drew such pixels lit.  The scene is the random room of tools/cull_fuzz.py that exposed it
+    (tests/golden/whitted_blocked_light_nan.npy); the reference's own code, the oracle and the lane code must agree, counting and timed."""
+    import os
+    from conftest import GOLDEN
+    prims = np.load(os.path.join(GOLDEN, "whitted_blocked_light_nan.npy"))
+    w, h = 64, 48
+    px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+    orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, None)
+    px_r = np.zeros((h, w, 4), np.uint8)
+    ref_whitted.ref_whitted_render(vp(px_r), w, h, vp(prims), prims.size)
+    assert np.array_equal(px_o, px_r)
+    assert not px_o[29, 29, :3].any() and not px_o[30, 29, :3].any()      # the two pixels whose accumulator is NaN
+    devsim.devsim_whitted_redo_pixels.restype = ctypes.c_long
+    for mode in (1, 2, 4):
+        px, hits = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, None, None, mode)
+        assert np.array_equal(px, px_o) and np.array_equal(hits, hits_o), mode
+    # the timed mode reported those pixels (and few others) for the exact pass; the reference's own scene reports none
+    assert 2 <= devsim.devsim_whitted_redo_pixels() < w * h // 8
+    box = rt.whitted_create_scene(0)
+    px, hits = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+    devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(box), box.size, 0, 1, 8, None, None, 4)
+    assert devsim.devsim_whitted_redo_pixels() == 0
+
+
 def test_hierarchy_builder_on_degenerate_inputs(devsim, rt):
     """build_pt_bvh: every sphere ends up exactly once in the tree or in the always-tested list, and the depth stays below
     the traversal stack (64) -- one sphere, a thousand identical ones, NaN / inf / huge entries, a line of 5 000, 200 000
