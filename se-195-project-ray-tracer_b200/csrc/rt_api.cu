@@ -47,6 +47,10 @@ struct rt_ctx {
     WCull w_cull, w_cull_bvh;                      // shadow-round cull tables for runs_hot / runs_bvh (scene_soa.h)
     f2 *d_wpcull = nullptr, *d_wpcull_bvh = nullptr; f4 *d_wrbox = nullptr, *d_wrbox_bvh = nullptr;
     size_t cap_wpcull = 0, cap_wpcull_bvh = 0, cap_wrbox = 0, cap_wrbox_bvh = 0;
+    float *d_wsmargin = nullptr; size_t cap_wsmargin = 0;      // shadow-candidate grid: per-sphere margins, and the cells
+    uint32_t *d_wgrid = nullptr; size_t cap_wgrid = 0;
+    bool w_grid_ready = false;
+    int w_grid = 1;                                // RT_TUNE_WHITTED_GRID
     uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
     size_t peer_wcap = 0, peer_pcap = 0;           // ... and how many pixels rank 0 said they hold
     bool exported_w = false, exported_p = false;   // this context's framebuffers are mapped by other processes: never reallocate them
@@ -192,7 +196,7 @@ void rt_destroy(rt_ctx *ctx) {
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex,
                      ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh, ctx->d_sincos,
-                     ctx->d_wpcull, ctx->d_wpcull_bvh, ctx->d_wrbox, ctx->d_wrbox_bvh, ctx->d_wcls };
+                     ctx->d_wpcull, ctx->d_wpcull_bvh, ctx->d_wrbox, ctx->d_wrbox_bvh, ctx->d_wcls, ctx->d_wsmargin, ctx->d_wgrid };
     for (void *b : bufs) if (b) cudaFree(b);
     void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter, ctx->r306.subcol };
     for (void *b : rbufs) if (b) cudaFree(b);
@@ -259,6 +263,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_FILLER_PCT: if (value < 0 || value > 100) break; ctx->whitted_filler_pct = value; return RT_OK;
         case RT_TUNE_WHITTED_REDO_CAP: if (value < 0 || value > (int)RT_WHITTED_REDO_CAP) break; ctx->w_redo_cap = (unsigned)value; return RT_OK;
+        case RT_TUNE_WHITTED_GRID: ctx->w_grid = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_STAGE_CAP: if (value < -1 || value > 3) break; ctx->w_stage_cap = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
@@ -290,6 +295,22 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
     build_w_cull(soa, soa.runs_hot, ctx->w_cull);
     CK(upload_vec(&ctx->d_wpcull, &ctx->cap_wpcull, ctx->w_cull.pcull, ctx->stream));
     CK(upload_vec(&ctx->d_wrbox, &ctx->cap_wrbox, ctx->w_cull.rbox, ctx->stream));
+    if (!same_table) ctx->w_grid_ready = false;
+    if (ctx->w_cull.grid_gz > 0 && !ctx->w_grid_ready) {          // the shadow-candidate grid of this table, computed on the device, once
+        const WGrid &G = ctx->w_cull.grid;
+        const size_t cells = (size_t)G.gx * G.gy * ctx->w_cull.grid_gz;
+        CK(upload_vec(&ctx->d_wsmargin, &ctx->cap_wsmargin, ctx->w_cull.smargin, ctx->stream));
+        if (cells > ctx->cap_wgrid) {
+            if (ctx->d_wgrid) cudaFree(ctx->d_wgrid);
+            ctx->d_wgrid = nullptr; ctx->cap_wgrid = 0;
+            CK(cudaMalloc((void **)&ctx->d_wgrid, cells * sizeof(uint32_t)));
+            ctx->cap_wgrid = cells;
+        }
+        CK(rtk_build_whitted_grid(G, ctx->w_cull.grid_gz, ctx->d_wgrid, ctx->d_wgeom, ctx->d_wflags, ctx->d_wpcull, ctx->d_wsmargin, ctx->d_wlcenter,
+                                  (int)soa.lights.size(), ctx->stream));
+        ctx->setup_launches++;
+        ctx->w_grid_ready = true;
+    }
     const size_t px = (size_t)w * h;
     if (ctx->peer_wpixels && px > ctx->peer_wcap)
         return fail(ctx, RT_ERR_STATE, "rt_whitted_upload: %dx%d exceeds the %zu pixels of the imported rank-0 framebuffer (rt_ipc_close, then share again)", w, h, ctx->peer_wcap);
@@ -373,6 +394,8 @@ int rt_whitted_launch(rt_ctx *ctx) {
         F.pcull = ctx->d_wpcull_bvh; F.rbox = ctx->d_wrbox_bvh; F.cull_rp2 = ctx->w_cull_bvh.rp2; F.reject_k = ctx->w_cull_bvh.reject_k;
         if (p.stage_mode >= 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
     } else memset(&p.bvh, 0, sizeof p.bvh);
+    memset(&F.grid, 0, sizeof F.grid);
+    if (p.stage_mode == 3 && !ctx->counting && !p.use_bvh && ctx->w_grid && ctx->w_grid_ready && ctx->w_cull.grid_gz > 0 && p.sphere_lights > 0) { F.grid = ctx->w_cull.grid; F.grid.cells = ctx->d_wgrid; }
     if (ctx->whitted_sort && p.n_items) {
         if (p.n_items > ctx->worder_cap) {
             if (ctx->d_worder) cudaFree(ctx->d_worder);
@@ -508,7 +531,7 @@ int rt_r306_launch(rt_ctx *ctx) {
     F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.lcenter = R.lcenter; F.runs = R.runs; F.n_runs = R.nr;
     F.rrad = R.rrad; F.n = R.n; F.n_lights = R.nl; F.n_spheres = R.ns; F.n_planes = R.np;
     F.w = R.w; F.h = R.h; F.DX = R.DX; F.DY = R.DY; F.hit_ids = nullptr;
-    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f; F.tame_reach[0] = F.tame_reach[1] = 0.f; F.redo_count = nullptr; F.redo_list = nullptr; F.redo_cap = 0;
+    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f; memset(&F.grid, 0, sizeof F.grid); F.tame_reach[0] = F.tame_reach[1] = 0.f; F.redo_count = nullptr; F.redo_list = nullptr; F.redo_cap = 0;
     p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;
     p.shard = make_shard(R.w, R.h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.dest = R.dest; p.work_counter = ctx->d_work; p.sm_count = ctx->sm_count;

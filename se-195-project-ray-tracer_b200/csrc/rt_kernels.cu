@@ -352,7 +352,8 @@ __device__ __forceinline__ void w_bvh_shadow_round(WLane &L, const PtBvh &B, boo
 // continues in the tree, lane by lane (whitted_bvh.cuh) -- scenes of hundreds to thousands of spheres.
 // EXACT: the launch that follows the timed kernel (whitted_lane.cuh, "Blocked lights and the redo list"): the pixels of F.redo_list --
 // or every item when more were reported than the list holds -- one per lane, blocked lights shaded as the reference shades them.
-template <bool COUNT, int STAGED, int NL, bool BVH, bool EXACT = false>
+// GRID: shadow rounds take their candidates from F.grid (the host launches these variants only with a grid).
+template <bool COUNT, int STAGED, int NL, bool BVH, bool EXACT = false, bool GRID = false>
 __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
                uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B, const uint8_t *cls, uint32_t filler_items) {
@@ -430,7 +431,8 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 #ifdef W_ROUND_STATS
             { const unsigned m = __ballot_sync(FULL_MASK, sq); if (COUNT && lane == 0) { atomicAdd(&counters[2], 32ull); atomicAdd(&counters[3], (unsigned long long)__popc(m)); } }
 #endif
-            w_query_shadow<COUNT, (NL > 0 && !COUNT)>(L, s_geom, s_runs, F.n_runs, sq, F.pcull, F.rbox, F.reject_k);     // NL > 0: the host made the cull tables
+            if (GRID) w_query_shadow_grid(L, s_geom, F.flags, sq, F.grid, F.reject_k);     // small scenes: candidates from the grid
+            else w_query_shadow<COUNT, (NL > 0 && !COUNT)>(L, s_geom, s_runs, F.n_runs, sq, F.pcull, F.rbox, F.reject_k);     // NL > 0: the host made the cull tables
             if (BVH) w_bvh_shadow_round(L, B, sq);
             if (sq) w_after_shadow<COUNT, NL, EXACT>(L, F);
         }
@@ -583,6 +585,13 @@ whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* 
     }
 }
 
+// The shadow-candidate grid of a Whitted scene (whitted_lane.cuh): one thread per cell, in double.
+__global__ void whitted_grid_kernel(WGrid G, int gz, uint32_t *cells, const f4 *geom, const int *flags, const f2 *pcull, const float *smargin, const f4 *lcenter, int n_lights) {
+    const int n = G.gx * G.gy * gz;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+        cells[c] = w_grid_build_cell(G, gz, c, geom, flags, pcull, smargin, lcenter, n_lights);
+}
+
 // Device-side evaluation of the elementary functions of rt_math.cuh on caller-supplied arguments, so
 // that tests can compare them with the host libm (tests/test_gpu_parity.py).  Not on the rendering path.
 __global__ void selftest_math_kernel(int op, const float *in, void *out, unsigned long long n) {
@@ -635,6 +644,13 @@ static cudaError_t configure_kernel(K kernel, int threads, size_t smem, int *blo
     g_cfg.push_back(KernelCfg{ (const void *)kernel, smem, threads, dev, nb });
     *blocks = nb;
     return cudaSuccess;
+}
+
+cudaError_t rtk_build_whitted_grid(const WGrid &G, int gz, uint32_t *cells, const f4 *geom, const int *flags, const f2 *pcull, const float *smargin,
+                                   const f4 *lcenter, int n_lights, cudaStream_t stream) {
+    const long n = (long)G.gx * G.gy * gz;
+    whitted_grid_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(G, gz, cells, geom, flags, pcull, smargin, lcenter, n_lights);
+    return cudaGetLastError();
 }
 
 cudaError_t rtk_fill_sincos_table(float *tab, int sm_count, cudaStream_t stream) {
@@ -762,6 +778,8 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
           : p.sphere_lights == 2 ? (p.count ? whitted_kernel<true, 2, 2, false> : whitted_kernel<false, 2, 2, false>)
           : p.sphere_lights == 1 ? (p.count ? whitted_kernel<true, 2, 1, false> : whitted_kernel<false, 2, 1, false>)
                                  : (p.count ? whitted_kernel<true, 2, 0, false> : whitted_kernel<false, 2, 0, false>);
+    if (p.frame.grid.cells && !bvh && !p.count && p.stage_mode == 3 && p.sphere_lights >= 1 && p.sphere_lights <= 3)
+        k = p.sphere_lights == 3 ? whitted_kernel<false, 3, 3, false, false, true> : p.sphere_lights == 2 ? whitted_kernel<false, 3, 2, false, false, true> : whitted_kernel<false, 3, 1, false, false, true>;
     int nb = 0, cnb = 0;
     cudaError_t e = configure_kernel(k, W_THREADS, smem, &nb);
     if (e != cudaSuccess) return e;

@@ -204,6 +204,9 @@ inline void build_w_bvh(const rt_primitive *p, int n, WSoA &out) {
 // len + 22u V lies beyond that face grown by R' - rad (the coordinate is linear in t; the ends are within 1.01 EPS + 1.8u RP
 // + 1.8u V, resp. 6u (RP + RL) + 1.8u V + EPS, of P and of the light), where no point of an inflated sphere of the run is:
 // no sphere of the run returns an accepted distance in [0, len).
+#ifndef W_GRID_CELLS
+#define W_GRID_CELLS 49152          /* about this many cells (4 bytes each) */
+#endif
 struct WCull {
     std::vector<f2> pcull;      // per primitive
     std::vector<f4> rbox;       // two per run
@@ -211,6 +214,10 @@ struct WCull {
     float reject_k = 0.f;       // K of w_shadow_sphere_keep: (64 + 8 RP) u
     bool enabled = false;
     int planes_cullable = 0, runs_cullable = 0;     // for the record (tests, bench)
+    // shadow-candidate grid (whitted_lane.cuh): per-sphere rad + grow (rounded up), and the box / cell counts; grid.cells stays NULL here
+    std::vector<float> smargin;
+    WGrid grid;
+    int grid_gz = 0;            // cells along z (0: no grid for this table)
 };
 
 inline float w_cull_up(double v) { float f = (float)v; if ((double)f < v) f = nextafterf(f, INFINITY); return f; }
@@ -224,6 +231,7 @@ inline void build_w_cull(const WSoA &soa, const std::vector<int> &runs, WCull &o
     out.rbox.assign((size_t)(n_runs > 0 ? 2 * n_runs : 2), open_lo);
     for (int r = 0; r < n_runs; r++) out.rbox[2 * r + 1] = open_hi;
     out.rp2 = 0.f; out.enabled = false; out.planes_cullable = out.runs_cullable = 0;
+    out.smargin.assign((size_t)(n > 0 ? n : 1), 0.f); memset(&out.grid, 0, sizeof out.grid); out.grid_gz = 0;
     if (soa.lights.empty()) return;
     const double u = 1.0 / 16777216.0, EPS = 0.001;
     double Rs = 0.0;
@@ -301,6 +309,61 @@ inline void build_w_cull(const WSoA &soa, const std::vector<int> &runs, WCull &o
     out.reject_k = w_cull_up((64.0 + 8.0 * RP) * u);
     out.enabled = out.planes_cullable > 0 || out.runs_cullable > 0;
     if (!out.enabled) out.rp2 = 0.f;
+    // Shadow-candidate grid: scenes of at most 32 primitives (one bit each).  The box: the spheres and the lights, stretched to the planes
+    // that are perpendicular to an axis (the walls of a room) but not beyond the culls' radius; about W_GRID_CELLS cells of equal size.
+    if (!out.enabled || n > 32) return;
+    uint32_t all = 0;
+    for (int r = 0; r < n_runs; r++) {
+        const int start = runs[3 * r], count = runs[3 * r + 1], fl = runs[3 * r + 2];
+        if (fl & W_FLAG_LIGHT) continue;
+        for (int i = start; i < start + count; i++) all |= 1u << i;
+    }
+    double lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int i = 0; i < n; i++) {
+        const f4 g = soa.geom[i];
+        if (soa.flags[i] & W_FLAG_SPHERE) {
+            const double rad = (soa.flags[i] & W_FLAG_LIGHT) ? 0.0 : std::sqrt((double)g.w), c[3] = { g.x, g.y, g.z };
+            for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], c[a] - rad); hi[a] = std::fmax(hi[a], c[a] + rad); }
+            if (!(soa.flags[i] & W_FLAG_LIGHT)) {
+                const double eta = 28.0 * u * V * V + 28.0 * u * rad * rad;
+#ifdef W_CULL_TEST_NO_MARGIN
+                const double grow = -0.02 * rad;
+#else
+                const double grow = (rad > 0.0 ? std::fmin(eta / (2.0 * rad), 1.001 * std::sqrt(eta)) : 1.001 * std::sqrt(eta)) + 3.0 * EPS + 96.0 * u * (V + RP);
+#endif
+                out.smargin[i] = w_cull_up(rad + grow);
+            }
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        if (soa.flags[i] & W_FLAG_SPHERE) continue;
+        const f4 g = soa.geom[i];
+        const int nz = (g.x != 0.f) + (g.y != 0.f) + (g.z != 0.f);
+        if (nz != 1 || !std::isfinite(g.w)) continue;
+        const int a = g.x != 0.f ? 0 : (g.y != 0.f ? 1 : 2);
+        const double wpos = -(double)g.w / (double)(a == 0 ? g.x : (a == 1 ? g.y : g.z));
+        if (!std::isfinite(wpos)) continue;
+        lo[a] = std::fmin(lo[a], wpos); hi[a] = std::fmax(hi[a], wpos);
+    }
+    double ext[3], vol = 1.0;
+    for (int a = 0; a < 3; a++) {
+        if (!(lo[a] <= hi[a])) return;
+        lo[a] = std::fmax(lo[a], -RP); hi[a] = std::fmin(hi[a], RP);
+        const double pad = 1e-3 * (hi[a] - lo[a]) + 1e-3;
+        lo[a] -= pad; hi[a] += pad;
+        ext[a] = hi[a] - lo[a];
+        vol *= ext[a];
+    }
+    const double edge = std::cbrt(vol / (double)W_GRID_CELLS);
+    int gdim[3];
+    for (int a = 0; a < 3; a++) { double c = std::ceil(ext[a] / edge); gdim[a] = c < 1.0 ? 1 : (c > 256.0 ? 256 : (int)c); }
+    WGrid &G = out.grid;
+    G.cells = nullptr; G.all = all;
+    G.x0 = (float)lo[0]; G.y0 = (float)lo[1]; G.z0 = (float)lo[2];
+    G.ix = (float)(gdim[0] / ext[0]); G.iy = (float)(gdim[1] / ext[1]); G.iz = (float)(gdim[2] / ext[2]);
+    G.fgx = (float)gdim[0]; G.fgy = (float)gdim[1]; G.fgz = (float)gdim[2];
+    G.gx = gdim[0]; G.gy = gdim[1];
+    out.grid_gz = gdim[2];
 }
 
 static_assert(sizeof(rt_r306_primitive) == 96, "rt_r306_primitive must match the reference Primitive (R306/raytracer.h:24-34)");

@@ -42,6 +42,16 @@ enum { W_PRIMARY = 0, W_REFLECTED = 1, W_REFRACTED = 2 };   /* RNO:59-63 */
 //   geom[i]  sphere: (center.xyz, sq_radius)   plane: (normal.xyz, depth)    <- all a test reads
 //   flags[i] bit0 = sphere, bit1 = is_light
 //   mat_a[i] (color.xyz, refl)     mat_b[i] (diff, refr, refr_index, spec)    rrad[i] = r_radius
+// Shadow-candidate grid (see "Shadow-candidate grid" below): one word per cell of a box around the scene.
+struct WGrid {
+    const uint32_t *cells;      // NULL: no grid.  Bit i of a cell: primitive i (< 32) may block a shadow ray from a hit point in the cell
+    float x0, y0, z0;           // low corner
+    float ix, iy, iz;           // cells per unit length
+    float fgx, fgy, fgz;        // cells per axis, as floats
+    int gx, gy;
+    uint32_t all;               // the word of a hit point outside the box: every primitive a shadow query tests
+};
+
 struct WFrame {
     const f4 *geom, *mat_a, *mat_b;
     const int *flags, *lights;
@@ -59,6 +69,7 @@ struct WFrame {
                                 //  that does not separate the run from every light is at -+inf
     float cull_rp2;             // the culls' margins hold for hit points with |P|^2 < cull_rp2
     float reject_k;             // K of w_shadow_sphere_keep for this scene
+    WGrid grid;
     // Blocked lights (see "Blocked lights and the redo list" below).
     float tame_reach[2];        // a hit point on a plane [0] / a sphere [1] closer than this to every light of its batch may skip its blocked lights;
                                 //  0: none may (build_w_soa)
@@ -337,6 +348,81 @@ RT_HD int w_shadow_sphere_keep(const WLane &L, const f4 g, int alive, float K) {
     }
     return keep & alive;
 }
+// Shadow-candidate grid (timed launches of scenes of at most 32 primitives whose lights are all spheres).  The two culls above decide per
+// hit point, with a handful of instructions per plane and per run of spheres.  Nearly all of that work has the same outcome for all hit
+// points of a neighbourhood, so it is done once per scene instead: a box around the scene is cut into cells, and for every cell the device
+// computes (w_grid_cell_mask, in double, margins rounded towards "keep") which primitives could block a shadow ray from ANY hit point in
+// the cell to ANY light:
+//   plane i    unless the plane cull's condition sgn (N.P + depth) > T holds at every point of the cell (the minimum over the cell is at a
+//              corner: the value at the centre minus sum |N_a| h_a);
+//   sphere i   iff for some light the segment from the cell's centre Pc to the light's centre passes within rad + grow + h of the sphere's
+//              centre (h = half the cell's diagonal).  build_w_cull's argument for a run's box holds for any convex region: the points the
+//              reference's test can return a distance for lie within `grow` - (R' - rad) of the real segment [P, c_l], which lies within
+//              |P - Pc| <= h of [Pc, c_l]; det >= 0 needs one of them within R' of the centre.
+// A shadow round then loads ONE word for the lane's hit point (cell index from three multiplications; the float rounding of the index is
+// covered by cells taken 0.1 % larger), ORs the words of the warp, and runs the tests of the primitives whose bit is set somewhere in the
+// warp -- typically the wall the points lie on and no sphere, or one.  A hit point outside the box or beyond the culls' radius (L.pnear)
+// takes G.all.  The tests themselves, and the fused reject in front of the sphere test, are unchanged.
+RT_HD uint32_t w_grid_cell_mask(double cx, double cy, double cz, double hx, double hy, double hz, const f4 *geom, const int *flags,
+                                const f2 *pcull, const float *smargin, uint32_t all, const f4 *lcenter, int n_lights) {
+    uint32_t m = 0;
+    const double h = sqrt(hx * hx + hy * hy + hz * hz);
+    for (int i = 0; i < 32; i++) {
+        if (!((all >> i) & 1u)) continue;
+        const f4 g = geom[i];
+        bool keep = true;
+        if (flags[i] & W_FLAG_SPHERE) {
+            keep = false;
+            const double reach = (double)smargin[i] + h;
+            for (int l = 0; l < n_lights && !keep; l++) {
+                const f4 c = lcenter[l];
+                const double vx = (double)c.x - cx, vy = (double)c.y - cy, vz = (double)c.z - cz;
+                const double wx = (double)g.x - cx, wy = (double)g.y - cy, wz = (double)g.z - cz;
+                const double vv = vx * vx + vy * vy + vz * vz;
+                double t = vv > 0.0 ? (wx * vx + wy * vy + wz * vz) / vv : 0.0;
+                t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+                const double ex = wx - t * vx, ey = wy - t * vy, ez = wz - t * vz;
+                if (!(ex * ex + ey * ey + ez * ez > reach * reach * 1.000001)) keep = true;         // NaN: keep
+            }
+        } else {
+            const f2 cu = pcull[i];
+            const double side = (double)cu.x * ((double)g.x * cx + (double)g.y * cy + (double)g.z * cz + (double)g.w);
+            const double slack = fabs((double)g.x) * hx + fabs((double)g.y) * hy + fabs((double)g.z) * hz;
+            if (side - slack > (double)cu.y * 1.000001 + 1e-30) keep = false;                       // T = inf (no cull for this plane), NaN: keep
+        }
+        if (keep) m |= 1u << i;
+    }
+    return m;
+}
+// Cell c of the grid (cell sizes from 1 / G.i*; the cells are taken 0.1 % larger than they are).
+RT_HD uint32_t w_grid_build_cell(const WGrid &G, int gz, int c, const f4 *geom, const int *flags, const f2 *pcull, const float *smargin, const f4 *lcenter, int n_lights) {
+    const int x = c % G.gx, y = (c / G.gx) % G.gy, z = c / (G.gx * G.gy);
+    (void)gz;
+    const double sx = 1.0 / (double)G.ix, sy = 1.0 / (double)G.iy, sz = 1.0 / (double)G.iz;
+    return w_grid_cell_mask((double)G.x0 + (x + 0.5) * sx, (double)G.y0 + (y + 0.5) * sy, (double)G.z0 + (z + 0.5) * sz,
+                            0.5005 * sx, 0.5005 * sy, 0.5005 * sz, geom, flags, pcull, smargin, G.all, lcenter, n_lights);
+}
+RT_HD uint32_t w_grid_lookup(const WLane &L, const WGrid &G) {
+    const float fx = (L.px - G.x0) * G.ix, fy = (L.py - G.y0) * G.iy, fz = (L.pz - G.z0) * G.iz;
+    const bool in = L.pnear & (fx >= 0.f) & (fx < G.fgx) & (fy >= 0.f) & (fy < G.fgy) & (fz >= 0.f) & (fz < G.fgz);       // NaN: outside
+    return in ? G.cells[((int)fz * G.gy + (int)fy) * G.gx + (int)fx] : G.all;
+}
+// The shadow round over the grid's candidates (same tests as w_query_shadow<false, true>, fewer of them).
+RT_HD void w_query_shadow_grid(WLane &L, const f4 *geom, const int *flags, bool has, const WGrid &G, float reject_k) {
+    int alive = w_alive_mask(L, has);
+    const uint32_t m = alive ? w_grid_lookup(L, G) : 0u;
+    for (uint32_t todo = warp_or(m); todo; todo &= todo - 1u) {
+        const int i = w_lowest_bit(todo);
+        alive = ((m >> i) & 1u) ? w_alive_mask(L, has) : 0;
+        if (!warp_any(alive != 0)) continue;
+        const f4 g = geom[i];
+        if (flags[i] & W_FLAG_SPHERE) {
+            const int keep = L.pnear ? w_shadow_sphere_keep(L, g, alive, reject_k) : alive;
+            if (warp_any(keep != 0)) w_shadow_sphere<false>(L, g, keep, has);
+        } else w_shadow_plane<false>(L, g, alive, has);
+    }
+}
+
 template <bool COUNT, bool CULL = false>
 RT_HD void w_query_shadow(WLane &L, const f4 *geom, const int *runs, int n_runs, bool has, const f2 *pcull = nullptr, const f4 *rbox = nullptr, float reject_k = 0.f) {
     for (int r = 0; r < n_runs; ++r) {

@@ -41,6 +41,10 @@ uint32_t devsim_cover(int w, int h, int rank, int world, int tile_rows, int32_t 
 // WFrame::tame_reach the host computes for a scene table (scene_soa.h).
 void devsim_whitted_tame_reach(const rt_primitive *prims, int n, float *out2) { WSoA soa; build_w_soa(prims, n, soa); out2[0] = soa.tame_reach[0]; out2[1] = soa.tame_reach[1]; }
 
+// Timed-mode devsim_whitted calls use the shadow-candidate grid (default) or only the per-hit-point culls.
+static int g_use_grid = 1;
+void devsim_whitted_use_grid(int on) { g_use_grid = on; }
+
 // Pixels of the last timed-mode devsim_whitted call that went through the EXACT pass.
 static long g_redo_pixels = 0;
 long devsim_whitted_redo_pixels() { return g_redo_pixels; }
@@ -66,12 +70,21 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     uint32_t redo_one[1];
     F.tame_reach[0] = soa.tame_reach[0]; F.tame_reach[1] = soa.tame_reach[1]; F.redo_count = nullptr; F.redo_list = redo_one; F.redo_cap = 1;
     F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f;
+    memset(&F.grid, 0, sizeof F.grid);
+    std::vector<uint32_t> grid_cells;
     WCull cull;
     if (use_runs == 4 || use_runs == 5) {      // what a timed launch does: the runs without dead primitives (5: + the hierarchy), the shadow-round culls, no counting
         if (use_runs == 5) { build_w_bvh(prims, n, soa); F.runs = soa.runs_bvh.data(); F.n_runs = (int)soa.runs_bvh.size() / 3; }
         else { F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3; }
         build_w_cull(soa, use_runs == 5 ? soa.runs_bvh : soa.runs_hot, cull);
         F.pcull = cull.pcull.data(); F.rbox = cull.rbox.data(); F.cull_rp2 = cull.rp2; F.reject_k = cull.reject_k;
+        if (use_runs == 4 && cull.grid_gz > 0 && g_use_grid) {        // the shadow-candidate grid, cell by cell as the device builds it
+            F.grid = cull.grid;
+            grid_cells.resize((size_t)F.grid.gx * F.grid.gy * cull.grid_gz);
+            for (size_t c = 0; c < grid_cells.size(); c++)
+                grid_cells[c] = w_grid_build_cell(F.grid, cull.grid_gz, (int)c, F.geom, F.flags, F.pcull, cull.smargin.data(), F.lcenter, F.n_lights);
+            F.grid.cells = grid_cells.data();
+        }
     }
     const PtBvh B5 = soa.bvh.view(soa.bvh.nodes.data(), soa.bvh.geom.data(), soa.bvh.index.data());
     uint32_t n_items;
@@ -94,7 +107,8 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
                 if (use_runs == 5) w_bvh_nearest(L, B5);
                 w_after_nearest<false>(L, F);
                 while (L.phase == PH_SHADOW) {
-                    w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
+                    if (F.grid.cells) w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);
+                    else w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
                     if (use_runs == 5) w_bvh_shadow(L, B5);
                     w_after_shadow<false>(L, F);
                 }
@@ -109,7 +123,8 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
                     if (use_runs == 5) w_bvh_nearest(L, B5);
                     w_after_nearest<false, 0, true>(L, F);
                     while (L.phase == PH_SHADOW) {
-                        w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
+                        if (F.grid.cells) w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);
+                        else w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
                         if (use_runs == 5) w_bvh_shadow(L, B5);
                         w_after_shadow<false, 0, true>(L, F);
                     }
@@ -156,7 +171,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
     F.W.runs = soa.runs_hot.data(); F.W.n_runs = (int)soa.runs_hot.size() / 3;
     F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
     F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;
-    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f; F.W.reject_k = 0.f; F.W.tame_reach[0] = F.W.tame_reach[1] = 0.f; F.W.redo_count = nullptr; F.W.redo_list = nullptr; F.W.redo_cap = 0;
+    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f; F.W.reject_k = 0.f; memset(&F.W.grid, 0, sizeof F.W.grid); F.W.tame_reach[0] = F.W.tame_reach[1] = 0.f; F.W.redo_count = nullptr; F.W.redo_list = nullptr; F.W.redo_cap = 0;
     F.sx = sx.data(); F.sy = sy.data(); F.row0 = 20; F.row1 = h - 70;
     R306Tree T;
     for (int y = F.row0; y < F.row1; y++)

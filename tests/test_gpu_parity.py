@@ -254,11 +254,16 @@ def test_whitted_shadow_culls_against_oracle_on_moved_lights_and_random_rooms(gp
     rs = np.random.RandomState(11)
     nan_scene = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whitted_blocked_light_nan.npy"))   # a blocked light times an overflowed pow() is NaN
     cases = [(near, 320, 240), (below, 320, 240), (inside, 320, 240), (nan_scene, 64, 48), (nan_scene, 256, 192)] + [(fz.random_scene(rt, rs, box), 96, 72) for _ in range(60)]
-    for k, (prims, w, h) in enumerate(cases):
-        px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
-        px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
-        assert np.array_equal(hits, hits_o), k
-        assert np.array_equal(px, px_o), k
+    try:
+        for k, (prims, w, h) in enumerate(cases):
+            px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
+            for grid in (1, 0):         # with the shadow-candidate grid (default) and with the per-hit-point culls only
+                gpu.set_tuning(rt.TUNE_WHITTED_GRID, grid)
+                px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+                assert np.array_equal(hits, hits_o), (k, grid)
+                assert np.array_equal(px, px_o), (k, grid)
+    finally:
+        gpu.set_tuning(rt.TUNE_WHITTED_GRID, 1)
 
 
 def test_whitted_blocked_lights_of_untame_batches_go_through_the_exact_launch(gpu, rt, orc):
