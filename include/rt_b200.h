@@ -132,7 +132,8 @@ enum {
     RT_TUNE_WHITTED_STAGE_CAP = 11,     /* diagnostics: cap on how much of the Whitted scene tables is staged in shared memory -- 3 static tables, 2 all tables,
                                            1 geometry / flags / runs only, 0 nothing (read through L1 / L2); -1 (default) = whatever fits.  Same image */
     RT_TUNE_WHITTED_GRID = 13,          /* Whitted tracer, scenes of at most 32 primitives with sphere lights: 1 (default) = a shadow round tests only the primitives a
-                                           per-scene grid of candidate words lists for the hit point's cell; 0 = per-hit-point culls only.  Same image either way */
+                                           per-scene grid of candidate words lists for the hit point's cell, and a nearest round of primary rays only those a per-frame-size
+                                           table lists for their 8x4-pixel tile; 2 = the grid without the tiles; 0 = per-hit-point culls only.  Same image for any value */
     RT_TUNE_WHITTED_REDO_CAP = 12,      /* diagnostics: how many pixels the timed Whitted kernel can report for the exact launch that follows it (blocked lights
                                            whose shade = 0 product is not provably 0, RNO:250, 270) before that launch redoes the whole frame; 0 .. 65536 (default).
                                            Same image for any value */

@@ -49,7 +49,9 @@ struct rt_ctx {
     size_t cap_wpcull = 0, cap_wpcull_bvh = 0, cap_wrbox = 0, cap_wrbox_bvh = 0;
     float *d_wsmargin = nullptr; size_t cap_wsmargin = 0;      // shadow-candidate grid: per-sphere margins, and the cells
     uint32_t *d_wgrid = nullptr; size_t cap_wgrid = 0;
+    uint32_t *d_wtiles = nullptr; size_t cap_wtiles = 0;      // primary-ray tile words of the current (table, frame size)
     bool w_grid_ready = false;
+    int w_tiles_w = 0, w_tiles_h = 0;              // the frame size d_wtiles was built for (0: not built)
     int w_grid = 1;                                // RT_TUNE_WHITTED_GRID
     uint32_t *peer_wpixels = nullptr, *peer_ppixels = nullptr;   // rank 0's framebuffers, mapped through CUDA IPC
     size_t peer_wcap = 0, peer_pcap = 0;           // ... and how many pixels rank 0 said they hold
@@ -196,7 +198,7 @@ void rt_destroy(rt_ctx *ctx) {
                      ctx->d_wrrad, ctx->d_wpixels, ctx->d_whits, ctx->d_colors, ctx->d_seeds, ctx->d_ppixels,
                      ctx->d_pgeom, ctx->d_pemis, ctx->d_pcolr, ctx->d_plights, ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex,
                      ctx->d_wbnodes, ctx->d_wbgeom, ctx->d_wbindex, ctx->d_wruns_bvh, ctx->d_sincos,
-                     ctx->d_wpcull, ctx->d_wpcull_bvh, ctx->d_wrbox, ctx->d_wrbox_bvh, ctx->d_wcls, ctx->d_wsmargin, ctx->d_wgrid };
+                     ctx->d_wpcull, ctx->d_wpcull_bvh, ctx->d_wrbox, ctx->d_wrbox_bvh, ctx->d_wcls, ctx->d_wsmargin, ctx->d_wgrid, ctx->d_wtiles };
     for (void *b : bufs) if (b) cudaFree(b);
     void *rbufs[] = { ctx->r306.geom, ctx->r306.ma, ctx->r306.mb, ctx->r306.flags, ctx->r306.lights, ctx->r306.runs, ctx->r306.rrad, ctx->r306.sx, ctx->r306.sy, ctx->r306.dest, ctx->r306.lcenter, ctx->r306.subcol };
     for (void *b : rbufs) if (b) cudaFree(b);
@@ -263,7 +265,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_FILLER_PCT: if (value < 0 || value > 100) break; ctx->whitted_filler_pct = value; return RT_OK;
         case RT_TUNE_WHITTED_REDO_CAP: if (value < 0 || value > (int)RT_WHITTED_REDO_CAP) break; ctx->w_redo_cap = (unsigned)value; return RT_OK;
-        case RT_TUNE_WHITTED_GRID: ctx->w_grid = value ? 1 : 0; return RT_OK;
+        case RT_TUNE_WHITTED_GRID: if (value < 0 || value > 2) break; ctx->w_grid = value; return RT_OK;
         case RT_TUNE_WHITTED_STAGE_CAP: if (value < -1 || value > 3) break; ctx->w_stage_cap = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
     }
@@ -310,6 +312,22 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
                                   (int)soa.lights.size(), ctx->stream));
         ctx->setup_launches++;
         ctx->w_grid_ready = true;
+        ctx->w_tiles_w = ctx->w_tiles_h = 0;
+    }
+    if (ctx->w_cull.grid_gz > 0 && (ctx->w_tiles_w != w || ctx->w_tiles_h != h)) {      // the primary-ray tile words of this table at this frame size
+        const int tiles_x = (w + 7) / 8, tiles_y = (h + 3) / 4;
+        const size_t tiles = (size_t)tiles_x * tiles_y;
+        if (tiles > ctx->cap_wtiles) {
+            if (ctx->d_wtiles) cudaFree(ctx->d_wtiles);
+            ctx->d_wtiles = nullptr; ctx->cap_wtiles = 0;
+            CK(cudaMalloc((void **)&ctx->d_wtiles, tiles * sizeof(uint32_t)));
+            ctx->cap_wtiles = tiles;
+        }
+        const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
+        CK(rtk_build_whitted_tiles(ctx->d_wtiles, tiles_x, tiles_y, w, h, (WX2 - WX1) / w, (WY2 - WY1) / h, ctx->d_wgeom, ctx->d_wflags, ctx->d_wsmargin,
+                                   ctx->w_cull.grid.all_nearest, ctx->stream));
+        ctx->setup_launches++;
+        ctx->w_tiles_w = w; ctx->w_tiles_h = h;
     }
     const size_t px = (size_t)w * h;
     if (ctx->peer_wpixels && px > ctx->peer_wcap)
@@ -395,7 +413,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
         if (p.stage_mode >= 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
     } else memset(&p.bvh, 0, sizeof p.bvh);
     memset(&F.grid, 0, sizeof F.grid);
-    if (p.stage_mode == 3 && !ctx->counting && !p.use_bvh && ctx->w_grid && ctx->w_grid_ready && ctx->w_cull.grid_gz > 0 && p.sphere_lights > 0) { F.grid = ctx->w_cull.grid; F.grid.cells = ctx->d_wgrid; }
+    if (p.stage_mode == 3 && !ctx->counting && !p.use_bvh && ctx->w_grid && ctx->w_grid_ready && ctx->w_cull.grid_gz > 0 && p.sphere_lights > 0) { F.grid = ctx->w_cull.grid; F.grid.cells = ctx->d_wgrid; F.grid.tiles = ctx->w_grid == 2 ? nullptr : ctx->d_wtiles; F.grid.tiles_x = (ctx->w_w + 7) / 8; }
     if (ctx->whitted_sort && p.n_items) {
         if (p.n_items > ctx->worder_cap) {
             if (ctx->d_worder) cudaFree(ctx->d_worder);

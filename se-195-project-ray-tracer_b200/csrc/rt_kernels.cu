@@ -423,7 +423,8 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
         if (COUNT && lane == 0) { atomicAdd(&counters[0], 32ull); atomicAdd(&counters[1], (unsigned long long)__popc(__ballot_sync(FULL_MASK, nq))); }
         else if (COUNT) __ballot_sync(FULL_MASK, nq);
 #endif
-        w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
+        if (GRID) w_query_nearest_tiles(L, s_geom, F.flags, s_runs, F.n_runs, nq, F.grid);       // primary rays: candidates from the tile's word
+        else w_query_nearest<COUNT>(L, s_geom, s_runs, F.n_runs, nq);
         if (BVH) w_bvh_nearest_round(L, B, nq);
         if (nq) w_after_nearest<COUNT, NL, EXACT>(L, F);
         while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
@@ -592,6 +593,13 @@ __global__ void whitted_grid_kernel(WGrid G, int gz, uint32_t *cells, const f4 *
         cells[c] = w_grid_build_cell(G, gz, c, geom, flags, pcull, smargin, lcenter, n_lights);
 }
 
+// The primary-ray tile words of a Whitted frame (whitted_lane.cuh): one thread per 8x4-pixel tile, in double.
+__global__ void whitted_tiles_kernel(uint32_t *tiles, int tiles_x, int tiles_y, int w, int h, float DX, float DY, const f4 *geom, const int *flags, const float *smargin, uint32_t all) {
+    const int n = tiles_x * tiles_y;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+        tiles[t] = w_tile_build(t % tiles_x, t / tiles_x, w, h, DX, DY, geom, flags, smargin, all);
+}
+
 // Device-side evaluation of the elementary functions of rt_math.cuh on caller-supplied arguments, so
 // that tests can compare them with the host libm (tests/test_gpu_parity.py).  Not on the rendering path.
 __global__ void selftest_math_kernel(int op, const float *in, void *out, unsigned long long n) {
@@ -650,6 +658,13 @@ cudaError_t rtk_build_whitted_grid(const WGrid &G, int gz, uint32_t *cells, cons
                                    const f4 *lcenter, int n_lights, cudaStream_t stream) {
     const long n = (long)G.gx * G.gy * gz;
     whitted_grid_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(G, gz, cells, geom, flags, pcull, smargin, lcenter, n_lights);
+    return cudaGetLastError();
+}
+
+cudaError_t rtk_build_whitted_tiles(uint32_t *tiles, int tiles_x, int tiles_y, int w, int h, float DX, float DY, const f4 *geom, const int *flags,
+                                    const float *smargin, uint32_t all, cudaStream_t stream) {
+    const long n = (long)tiles_x * tiles_y;
+    whitted_tiles_kernel<<<(unsigned)((n + 63) / 64), 64, 0, stream>>>(tiles, tiles_x, tiles_y, w, h, DX, DY, geom, flags, smargin, all);
     return cudaGetLastError();
 }
 

@@ -101,6 +101,8 @@ cudaError_t rtk_launch_r306(const R306Launch &p, cudaStream_t stream);
 cudaError_t rtk_launch_pt(const PtLaunch &p, cudaStream_t stream);
 cudaError_t rtk_build_whitted_grid(const rtb::WGrid &G, int gz, uint32_t *cells, const rtb::f4 *geom, const int *flags, const rtb::f2 *pcull, const float *smargin,
                                    const rtb::f4 *lcenter, int n_lights, cudaStream_t stream);
+cudaError_t rtk_build_whitted_tiles(uint32_t *tiles, int tiles_x, int tiles_y, int w, int h, float DX, float DY, const rtb::f4 *geom, const int *flags,
+                                    const float *smargin, uint32_t all, cudaStream_t stream);
 cudaError_t rtk_fill_sincos_table(float *tab /* 2 x 2^23 floats */, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_pt_resolve(const float *colors, uint32_t *pixels, int w, int h, float inv_total, int sm_count, cudaStream_t stream);
 cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream);

@@ -324,7 +324,8 @@ inline void build_w_cull(const WSoA &soa, const std::vector<int> &runs, WCull &o
         if (soa.flags[i] & W_FLAG_SPHERE) {
             const double rad = (soa.flags[i] & W_FLAG_LIGHT) ? 0.0 : std::sqrt((double)g.w), c[3] = { g.x, g.y, g.z };
             for (int a = 0; a < 3; a++) { lo[a] = std::fmin(lo[a], c[a] - rad); hi[a] = std::fmax(hi[a], c[a] + rad); }
-            if (!(soa.flags[i] & W_FLAG_LIGHT)) {
+            {
+                const double rad = std::sqrt((double)g.w);           // lights too: a nearest query can hit them (the primary-ray tiles)
                 const double eta = 28.0 * u * V * V + 28.0 * u * rad * rad;
 #ifdef W_CULL_TEST_NO_MARGIN
                 const double grow = -0.02 * rad;
@@ -359,6 +360,8 @@ inline void build_w_cull(const WSoA &soa, const std::vector<int> &runs, WCull &o
     for (int a = 0; a < 3; a++) { double c = std::ceil(ext[a] / edge); gdim[a] = c < 1.0 ? 1 : (c > 256.0 ? 256 : (int)c); }
     WGrid &G = out.grid;
     G.cells = nullptr; G.all = all;
+    G.tiles = nullptr; G.tiles_x = 0; G.all_nearest = 0;
+    for (int r = 0; r < n_runs; r++) for (int i = runs[3 * r]; i < runs[3 * r] + runs[3 * r + 1]; i++) G.all_nearest |= 1u << i;
     G.x0 = (float)lo[0]; G.y0 = (float)lo[1]; G.z0 = (float)lo[2];
     G.ix = (float)(gdim[0] / ext[0]); G.iy = (float)(gdim[1] / ext[1]); G.iz = (float)(gdim[2] / ext[2]);
     G.fgx = (float)gdim[0]; G.fgy = (float)gdim[1]; G.fgz = (float)gdim[2];

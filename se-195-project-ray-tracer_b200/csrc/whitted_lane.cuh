@@ -50,6 +50,10 @@ struct WGrid {
     float fgx, fgy, fgz;        // cells per axis, as floats
     int gx, gy;
     uint32_t all;               // the word of a hit point outside the box: every primitive a shadow query tests
+    // Primary-ray candidates ("Primary-ray tiles" below): one word per 8x4-pixel tile of the frame
+    const uint32_t *tiles;      // NULL: none
+    int tiles_x;
+    uint32_t all_nearest;       // the word of any other ray: every primitive a nearest query tests
 };
 
 struct WFrame {
@@ -420,6 +424,127 @@ RT_HD void w_query_shadow_grid(WLane &L, const f4 *geom, const int *flags, bool 
             const int keep = L.pnear ? w_shadow_sphere_keep(L, g, alive, reject_k) : alive;
             if (warp_any(keep != 0)) w_shadow_sphere<false>(L, g, keep, has);
         } else w_shadow_plane<false>(L, g, alive, has);
+    }
+}
+
+// Primary-ray tiles (same launches as the grid).  Every primary ray starts at the eye, so which primitives it can reach is a function of
+// the pixel; for each 8x4-pixel tile the device computes once per (scene, frame size) which primitives can be the ACCEPTED hit of some
+// primary ray of the tile (w_tile_mask, in double).  For the rectangle of un-normalised directions D = (u, v, 7) the tile's nine
+// sub-samples per pixel span (grown by a thousandth of a pixel), each primitive gets: can it be hit at all, is it certainly hit by every
+// ray, and between which distances:
+//   plane   t = -s |D| / (N.D), s = N.O + depth: N.D is linear in (u, v), so its range is taken at the corners; a range that (nearly)
+//           contains 0, or s ~ 0, leaves the plane "possible" from the smallest distance any ray can see; otherwise the sign of -s / N.D
+//           decides between "missed by all" (the reference's dist <= 0) and "hit by all" with t in |s| [min |D|, max |D|] / |N.D|;
+//   sphere  against the cone around the tile's centre ray that holds its corners: outside the sphere inflated to rad + grow (scene_soa.h:
+//           where det can still be positive) = missed; cone inside the sphere deflated by the same = hit by all, entry distance at most that
+//           of the deflated sphere along the cone's rim; never closer than |C - O| - rad - grow.
+// The float distances of the reference differ from these by parts in 10^6; the intervals carry 10^-4.  A primitive is dropped from the
+// tile's word iff it is missed by all rays or lies farther than the farthest possible distance of some primitive that all rays hit:
+// then it is never the accepted hit, and leaving out its test changes no accepted (cumu, qhit, qkind) -- the order of the remaining tests
+// (ascending index, strict '<') is unchanged.  A nearest round ORs the words of the warp's lanes (any other ray: G.all_nearest) and
+// tests the primitives whose bit is set; a warp of 8x4 wall pixels tests one or two planes instead of every primitive.
+struct WTileCam { double ox, oy, oz, u0, u1, v0, v1, dz; };
+RT_HD uint32_t w_tile_mask(const WTileCam &T, const f4 *geom, const int *flags, const float *smargin, uint32_t all) {
+    const double cu[4] = { T.u0, T.u1, T.u0, T.u1 }, cv[4] = { T.v0, T.v0, T.v1, T.v1 };
+    // |D| over the rectangle: smallest at the point closest to (0, 0), largest at a corner
+    const double un = T.u0 > 0.0 ? T.u0 : (T.u1 < 0.0 ? T.u1 : 0.0), vn = T.v0 > 0.0 ? T.v0 : (T.v1 < 0.0 ? T.v1 : 0.0);
+    const double la = sqrt(un * un + vn * vn + T.dz * T.dz);
+    double lb = 0.0;
+    for (int c = 0; c < 4; c++) { const double l = sqrt(cu[c] * cu[c] + cv[c] * cv[c] + T.dz * T.dz); lb = l > lb ? l : lb; }
+    // the cone: axis through the rectangle's centre, half-angle to the farthest corner
+    double ax = 0.5 * (T.u0 + T.u1), ay = 0.5 * (T.v0 + T.v1), az = T.dz;
+    const double al = sqrt(ax * ax + ay * ay + az * az);
+    ax /= al; ay /= al; az /= al;
+    double cmin = 1.0;
+    for (int c = 0; c < 4; c++) {
+        const double l = sqrt(cu[c] * cu[c] + cv[c] * cv[c] + T.dz * T.dz);
+        const double cs = (ax * cu[c] + ay * cv[c] + az * T.dz) / l;
+        cmin = cs < cmin ? cs : cmin;
+    }
+    const double theta = acos(cmin < -1.0 ? -1.0 : (cmin > 1.0 ? 1.0 : cmin)) + 1e-7;
+    const double olen = sqrt(T.ox * T.ox + T.oy * T.oy + T.oz * T.oz);
+    uint32_t possible = 0;
+    double tlo[32];
+    double tstar = INFINITY;                      // no accepted distance exceeds this: the farthest hit of some primitive all rays hit
+    for (int i = 0; i < 32; i++) {
+        tlo[i] = 0.0;
+        if (!((all >> i) & 1u)) continue;
+        const f4 g = geom[i];
+        bool poss = true, cert = false;
+        double lo = 0.0, hi = INFINITY;
+        if (flags[i] & W_FLAG_SPHERE) {
+            const double wx = (double)g.x - T.ox, wy = (double)g.y - T.oy, wz = (double)g.z - T.oz;
+            const double dist = sqrt(wx * wx + wy * wy + wz * wz);
+            const double rad = sqrt((double)g.w), rp = (double)smargin[i], rm = 2.0 * rad - rp;
+            if (dist > rp * 1.0001 && rp >= rad) {            // the eye is outside (else: possible, from distance 0)
+                double ca = (wx * ax + wy * ay + wz * az) / dist;
+                ca = ca < -1.0 ? -1.0 : (ca > 1.0 ? 1.0 : ca);
+                const double alpha = acos(ca), bp = asin(rp / dist);
+                if (alpha > theta + bp + 1e-6) poss = false;
+                else {
+                    lo = dist - rp;
+                    if (rm > 0.0) {
+                        const double am = alpha + theta + 1e-6, bm = asin(rm / dist);
+                        if (am < bm) {
+                            const double sn = dist * sin(am), q = rm * rm - sn * sn;
+                            if (q > 0.0) { cert = true; hi = dist * cos(am) - sqrt(q); }
+                        }
+                    }
+                }
+            }
+        } else {
+            // float side: s_f = fl(N.o + depth) within es of sv, d_f = fl(N.q) within ed of c = N.D / |D| (q the float unit direction),
+            // dist = fl(-s_f / d_f), accepted iff 0 < dist < cumu (RNO:97-108)
+            const double nn = sqrt((double)g.x * g.x + (double)g.y * g.y + (double)g.z * g.z);
+            const double sv = (double)g.x * T.ox + (double)g.y * T.oy + (double)g.z * T.oz + (double)g.w;
+            const double es = 1e-6 * (nn * olen + fabs((double)g.w)), ed = 4e-6 * nn;
+            double a = INFINITY, b = -INFINITY;
+            for (int c = 0; c < 4; c++) {
+                const double nd = (double)g.x * cu[c] + (double)g.y * cv[c] + (double)g.z * T.dz;
+                a = nd < a ? nd : a; b = nd > b ? nd : b;
+            }
+            const double amax = fabs(a) > fabs(b) ? fabs(a) : fabs(b), amin = fabs(a) < fabs(b) ? fabs(a) : fabs(b);
+            const double cmax = amax / la, cmn = amin / lb;              // |c| <= cmax; |c| >= cmn when N.D keeps its sign
+            const bool signed_nd = (a > 0.0) == (b > 0.0) && a != 0.0 && b != 0.0 && cmn > 100.0 * ed;
+            if (!(nn > 0.0) || !(fabs(sv) <= 1e300) || !(cmax <= 1e300)) { /* degenerate: possible, from 0 */ }
+            else if (signed_nd && fabs(sv) > 100.0 * es) {
+                if ((sv > 0.0) == (a > 0.0)) poss = false;             // -s_f / d_f < 0 for every ray
+                else { cert = true; lo = (fabs(sv) - es) / (cmax + ed); hi = (fabs(sv) + es) / (cmn - ed); }
+            } else lo = (fabs(sv) > es ? fabs(sv) - es : 0.0) / (cmax + ed);
+        }
+        if (!poss) continue;
+        possible |= 1u << i;
+        tlo[i] = lo * (1.0 - 1e-4) - 1e-4;
+        if (cert) { const double h = hi * (1.0 + 1e-4) + 1e-4; if (h < tstar) tstar = h; }
+    }
+    uint32_t m = 0;
+    for (int i = 0; i < 32; i++) if (((possible >> i) & 1u) && !(tlo[i] > tstar)) m |= 1u << i;       // NaN: keep
+    return m;
+}
+// Tile (tx, ty) of a w x h frame with the camera of w_start_subsample (RNO:299-328).
+RT_HD uint32_t w_tile_build(int tx, int ty, int w, int h, float DX, float DY, const f4 *geom, const int *flags, const float *smargin, uint32_t all) {
+    const int x0 = tx * 8, y0 = ty * 4, x1 = (x0 + 7 < w - 1) ? x0 + 7 : w - 1, y1 = (y0 + 3 < h - 1) ? y0 + 3 : h - 1;
+    WTileCam T;
+    T.ox = 0.0; T.oy = 0.25; T.oz = -7.0; T.dz = 7.0;
+    const double dx = (double)DX, dy = (double)DY;
+    const double ua = -3.0 + (x0 - 0.5) * dx, ub = -3.0 + (x1 + 0.5) * dx, va = 2.0 + (y0 - 0.5) * dy, vb = 2.0 + (y1 + 0.5) * dy;
+    const double pu = 1e-3 * fabs(dx) + 1e-5, pv = 1e-3 * fabs(dy) + 1e-5;
+    T.u0 = (ua < ub ? ua : ub) - pu; T.u1 = (ua < ub ? ub : ua) + pu;
+    T.v0 = (va < vb ? va : vb) - pv; T.v1 = (va < vb ? vb : va) + pv;
+    return w_tile_mask(T, geom, flags, smargin, all);
+}
+RT_HD void w_query_nearest_tiles(WLane &L, const f4 *geom, const int *flags, const int *runs, int n_runs, bool has, const WGrid &G) {
+    if (!G.tiles) { w_query_nearest<false>(L, geom, runs, n_runs, has); return; }       // RT_TUNE_WHITTED_GRID = 2: the grid without the tiles
+    uint32_t m = 0;
+    if (has) m = (L.kind == W_PRIMARY) ? G.tiles[(L.y >> 2) * G.tiles_x + (L.x >> 3)] : G.all_nearest;
+    uint32_t todo = warp_or(m);
+    if (todo == G.all_nearest) { w_query_nearest<false>(L, geom, runs, n_runs, has); return; }       // nothing to leave out: the paired loops
+    for (; todo; todo &= todo - 1u) {
+        const int i = w_lowest_bit(todo);
+        const bool live = (m >> i) & 1u;
+        const f4 g = geom[i];
+        if (flags[i] & W_FLAG_SPHERE) w_sphere<false>(L, g, i, live);
+        else w_plane<false>(L, g, i, live);
     }
 }
 

@@ -71,7 +71,7 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     F.tame_reach[0] = soa.tame_reach[0]; F.tame_reach[1] = soa.tame_reach[1]; F.redo_count = nullptr; F.redo_list = redo_one; F.redo_cap = 1;
     F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f;
     memset(&F.grid, 0, sizeof F.grid);
-    std::vector<uint32_t> grid_cells;
+    std::vector<uint32_t> grid_cells, tile_words;
     WCull cull;
     if (use_runs == 4 || use_runs == 5) {      // what a timed launch does: the runs without dead primitives (5: + the hierarchy), the shadow-round culls, no counting
         if (use_runs == 5) { build_w_bvh(prims, n, soa); F.runs = soa.runs_bvh.data(); F.n_runs = (int)soa.runs_bvh.size() / 3; }
@@ -84,6 +84,11 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
             for (size_t c = 0; c < grid_cells.size(); c++)
                 grid_cells[c] = w_grid_build_cell(F.grid, cull.grid_gz, (int)c, F.geom, F.flags, F.pcull, cull.smargin.data(), F.lcenter, F.n_lights);
             F.grid.cells = grid_cells.data();
+            F.grid.tiles_x = (w + 7) / 8;
+            tile_words.resize((size_t)F.grid.tiles_x * ((h + 3) / 4));
+            for (size_t t = 0; t < tile_words.size(); t++)
+                tile_words[t] = w_tile_build((int)(t % F.grid.tiles_x), (int)(t / F.grid.tiles_x), w, h, F.DX, F.DY, F.geom, F.flags, cull.smargin.data(), F.grid.all_nearest);
+            F.grid.tiles = tile_words.data();
         }
     }
     const PtBvh B5 = soa.bvh.view(soa.bvh.nodes.data(), soa.bvh.geom.data(), soa.bvh.index.data());
@@ -103,7 +108,8 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
             // skipped, the pixel again as the EXACT launch computes it (whitted_lane.cuh, "Blocked lights and the redo list")
             redo_count = 0; F.redo_count = &redo_count;
             for (;;) {
-                w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);
+                if (F.grid.cells) w_query_nearest_tiles(L, F.geom, F.flags, F.runs, F.n_runs, true, F.grid);
+                else w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);
                 if (use_runs == 5) w_bvh_nearest(L, B5);
                 w_after_nearest<false>(L, F);
                 while (L.phase == PH_SHADOW) {
@@ -119,7 +125,8 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
                 memset(&L, 0, sizeof L);
                 w_begin_pixel(L, F, x, y);
                 for (;;) {
-                    w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);
+                    if (F.grid.cells) w_query_nearest_tiles(L, F.geom, F.flags, F.runs, F.n_runs, true, F.grid);
+                    else w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);
                     if (use_runs == 5) w_bvh_nearest(L, B5);
                     w_after_nearest<false, 0, true>(L, F);
                     while (L.phase == PH_SHADOW) {

@@ -12,7 +12,7 @@ for scene in (0,):
     for (w, h) in sizes:
         out, frames = [], []
         for rep in range(2):
-            for grid in (1, 0):
+            for grid in (1, 2, 0):
                 r.set_tuning(rt.TUNE_WHITTED_GRID, grid)
                 r.whitted_upload(prims, w, h)
                 for _ in range(3): r.whitted_launch()
