@@ -19,6 +19,9 @@ struct rt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t aux_stream = nullptr;             // Whitted: whitted_split_kernel runs here, next to the main kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int w_split = 1;                               // RT_TUNE_WHITTED_SPLIT
     int sm_count = 0, clock_khz = 0, max_smem_optin = 0;
     char name[256] = {0};
     char err[512] = {0};
@@ -180,7 +183,10 @@ int rt_init(rt_ctx **out, int device) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail(e, "cudaEventCreate");
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail(e, "cudaEventCreate");
-    if ((e = cudaMalloc((void **)&ctx->d_work, 4 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc((void **)&ctx->d_work, 6 * sizeof(unsigned))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_wredo, RT_WHITTED_REDO_CAP * sizeof(uint32_t))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMalloc((void **)&ctx->d_counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset");
@@ -204,6 +210,9 @@ void rt_destroy(rt_ctx *ctx) {
     for (void *b : rbufs) if (b) cudaFree(b);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -265,6 +274,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_FILLER_PCT: if (value < 0 || value > 100) break; ctx->whitted_filler_pct = value; return RT_OK;
         case RT_TUNE_WHITTED_REDO_CAP: if (value < 0 || value > (int)RT_WHITTED_REDO_CAP) break; ctx->w_redo_cap = (unsigned)value; return RT_OK;
+        case RT_TUNE_WHITTED_SPLIT: ctx->w_split = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_GRID: if (value < 0 || value > 2) break; ctx->w_grid = value; return RT_OK;
         case RT_TUNE_WHITTED_STAGE_CAP: if (value < -1 || value > 3) break; ctx->w_stage_cap = value; return RT_OK;
         default: return fail(ctx, RT_ERR_ARG, "rt_set_tuning: unknown key %d", key);
@@ -413,7 +423,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
         if (p.stage_mode >= 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
     } else memset(&p.bvh, 0, sizeof p.bvh);
     memset(&F.grid, 0, sizeof F.grid);
-    if (p.stage_mode == 3 && !ctx->counting && !p.use_bvh && ctx->w_grid && ctx->w_grid_ready && ctx->w_cull.grid_gz > 0 && p.sphere_lights > 0) { F.grid = ctx->w_cull.grid; F.grid.cells = ctx->d_wgrid; F.grid.tiles = ctx->w_grid == 2 ? nullptr : ctx->d_wtiles; F.grid.tiles_x = (ctx->w_w + 7) / 8; }
+    if (p.stage_mode == 3 && !ctx->counting && !p.use_bvh && ctx->w_grid && ctx->w_grid_ready && ctx->w_cull.grid_gz > 0 && p.sphere_lights >= 1 && p.sphere_lights <= 3) { F.grid = ctx->w_cull.grid; F.grid.cells = ctx->d_wgrid; F.grid.tiles = ctx->w_grid == 2 ? nullptr : ctx->d_wtiles; F.grid.tiles_x = (ctx->w_w + 7) / 8; }
     if (ctx->whitted_sort && p.n_items) {
         if (p.n_items > ctx->worder_cap) {
             if (ctx->d_worder) cudaFree(ctx->d_worder);
@@ -434,9 +444,12 @@ int rt_whitted_launch(rt_ctx *ctx) {
             p.filler_items = (uint32_t)((uint64_t)p.n_items * (uint32_t)ctx->whitted_filler_pct / 100u) & ~31u;
         }
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(unsigned), ctx->stream));
+    // class 0 one lane per sub-sample, next to the main kernel: needs the class lists and the tables of the grid variants
+    F.split0 = (ctx->w_split && p.order && F.grid.cells && F.grid.tiles) ? 1 : 0;
+    p.split_work_counter = ctx->d_work + 4; p.aux_stream = ctx->aux_stream; p.ev_fork = ctx->ev_fork; p.ev_join = ctx->ev_join;
+    CK(cudaMemsetAsync(ctx->d_work, 0, 6 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.redo_work_counter ? 1 : 0); }
+    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.redo_work_counter ? 1 : 0) + F.split0; }
     return RT_OK;
 }
 
@@ -549,7 +562,7 @@ int rt_r306_launch(rt_ctx *ctx) {
     F.geom = R.geom; F.mat_a = R.ma; F.mat_b = R.mb; F.flags = R.flags; F.lights = R.lights; F.lcenter = R.lcenter; F.runs = R.runs; F.n_runs = R.nr;
     F.rrad = R.rrad; F.n = R.n; F.n_lights = R.nl; F.n_spheres = R.ns; F.n_planes = R.np;
     F.w = R.w; F.h = R.h; F.DX = R.DX; F.DY = R.DY; F.hit_ids = nullptr;
-    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f; memset(&F.grid, 0, sizeof F.grid); F.tame_reach[0] = F.tame_reach[1] = 0.f; F.redo_count = nullptr; F.redo_list = nullptr; F.redo_cap = 0;
+    F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f; memset(&F.grid, 0, sizeof F.grid); F.split0 = 0; F.tame_reach[0] = F.tame_reach[1] = 0.f; F.redo_count = nullptr; F.redo_list = nullptr; F.redo_cap = 0;
     p.frame.sx = R.sx; p.frame.sy = R.sy; p.frame.row0 = 20; p.frame.row1 = R.h - 70;
     p.shard = make_shard(R.w, R.h, ctx->shard_rank, ctx->shard_world, ctx->tile_rows, &p.n_items);
     p.dest = R.dest; p.work_counter = ctx->d_work; p.sm_count = ctx->sm_count;
@@ -575,7 +588,7 @@ int rt_r306_launch(rt_ctx *ctx) {
         if (!ctx->d_wclass) CK(cudaMalloc((void **)&ctx->d_wclass, 4 * sizeof(unsigned)));
         p.order = ctx->d_worder; p.class_counts = ctx->d_wclass;
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 6 * sizeof(unsigned), ctx->stream));
     if (p.n_items) { CK(rtk_launch_r306(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.subcol ? 1 : 0); }
     return RT_OK;
 }
@@ -730,7 +743,7 @@ int rt_pt_launch(rt_ctx *ctx, int integrator, int n_passes) {
         }
         p.bvh = ctx->p_bvh.view(ctx->d_bnodes, ctx->d_bgeom, ctx->d_bindex);
     }
-    CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_work, 0, 6 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
     if (p.n_items) { CK(rtk_launch_pt(p, ctx->stream)); ctx->launches += F.defer_pack ? 2 : 1; }
     ctx->current_sample += n_passes;

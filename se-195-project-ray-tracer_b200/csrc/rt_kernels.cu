@@ -377,11 +377,12 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
     // The first `n_items` / 32 blocks ("filler", a launch parameter) are handed out pixel by pixel as well, after the lists: a
     // lane gets fewer than two class-0/1 pixels at 1080p, so without cheap pixels to fill in with, a warp waits for its slowest
     // lane with most lanes idle (25 of 32 lanes per instruction in that phase).
-    const uint32_t n_listed = (order && cls) ? class_counts[0] + class_counts[1] : 0u;
+    const uint32_t n_class0 = (order && !F.split0) ? class_counts[0] : 0u;       // split0: class 0 belongs to whitted_split_kernel
+    const uint32_t n_listed = (order && cls) ? n_class0 + class_counts[1] : 0u;
     const uint32_t n_filler = (order && cls) ? filler_items : 0u;            // items [0, n_filler) of class 2: by single lanes (a multiple of 32)
     const unsigned n_redo = EXACT ? *F.redo_count : 0u;
     const bool redo_all = EXACT && n_redo > F.redo_cap;
-    const uint32_t n_lane_items = EXACT ? (redo_all ? n_items : n_redo) : (order && cls) ? n_listed + n_filler : n_items;
+    const uint32_t n_lane_items = EXACT ? (redo_all ? n_items : n_redo) : (order && cls) ? n_listed + n_filler : (order && F.split0) ? n_items - class_counts[0] : n_items;
     const uint32_t n_blocks = cls ? n_stride >> 5 : 0u;
 
     for (;;) {
@@ -393,7 +394,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
                 uint32_t it = item;
                 bool take = true;
                 if (order) {                     // walk the cost classes in turn (see whitted_classify_kernel)
-                    const uint32_t n0 = class_counts[0], n1 = class_counts[1];
+                    const uint32_t n0 = n_class0, n1 = class_counts[1];
                     RT_CHECK(n0 + n1 <= n_stride && (!cls || item - n_listed < n_stride || item < n_listed), RT_CHK_WORKLIST);
                     if (cls && item >= n_listed) { it = item - n_listed; take = cls[it] == 2; }     // filler: a class-2 pixel of the first blocks
                     else it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
@@ -456,6 +457,69 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
         if (lane == 0) atomicAdd(&counters[5], (unsigned long long)f);
     }
 #endif
+}
+
+// The pixels of cost class 0 (a refracting surface behind the centre ray), one lane per SUB-SAMPLE: a warp takes three pixels at a time,
+// lanes 9g .. 9g+8 trace the nine sub-samples of pixel g side by side (lanes 27-31 idle), every lane logging what its rays add to the
+// pixel (w_finalize<.., SPLIT>); when all are done the nine logs of a pixel are added in the reference's order -- lane 9g first, the
+// running sum handed from lane to lane -- and lane 9g+8 stores the pixel.  Same bits as one lane tracing the nine sub-samples in turn
+// (whitted_kernel), but the longest chain of rays one lane traces back to back is 63 instead of 567: such a pixel alone took 1.7 ms of
+// the 2.4 ms 1080p frame and bounded small frames and strong scaling outright.  Runs next to the main kernel on a second stream
+// (rtk_launch_whitted); GRID tables as there.
+template <int NL>
+__global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
+whitted_split_kernel(WFrame F, Shard S, const uint32_t *order, const unsigned *class_counts, uint32_t *pixels, unsigned *work_counter) {
+    extern __shared__ f4 s_raw[];
+    const uint32_t lane = threadIdx.x & 31u;
+    const f4 *s_geom; const int *s_runs;
+    stage_scene<3>(F, s_raw, s_geom, s_runs);
+    f4 queue[3 * W_QUEUE_SLOTS];
+    float log[3 * 63];
+    WLane L;
+    L.phase = PH_IDLE;
+    L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_sphere_tests = L.c_plane_tests = 0; L.c_shadow_lit = 0;
+    const uint32_t n0 = class_counts[0];
+    const int group = (int)lane / 9, sub = (int)lane % 9;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(work_counter, 3u);
+        base = __shfl_sync(FULL_MASK, base, 0);
+        if (base >= n0) break;
+        bool mine = false;
+        if (lane < 27u && base + (uint32_t)group < n0) {
+            int x, y;
+            if (item_to_pixel(S, F.w, order[base + group], x, y)) {
+                L.x = x; L.y = y; L.sub = sub; L.nlog = 0;
+                w_start_subsample(L, F);
+                mine = true;
+            }
+        }
+        while (__any_sync(FULL_MASK, L.phase != PH_IDLE)) {
+            const bool nq = L.phase == PH_NEAREST;
+            w_query_nearest_tiles(L, s_geom, F.flags, s_runs, F.n_runs, nq, F.grid);
+            if (nq) w_after_nearest<false, NL, false>(L, F);
+            while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
+                const bool sq = L.phase == PH_SHADOW;
+                w_query_shadow_grid(L, s_geom, F.flags, sq, F.grid, F.reject_k);
+                if (sq) w_after_shadow<false, NL, false>(L, F);
+            }
+            if (L.phase == PH_FINAL) w_finalize<false, true>(L, F, queue, log);
+        }
+        // the nine logs of each pixel, in order
+        float ar = 0.f, ag = 0.f, ab = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < 9; s++) {
+            const float pr = __shfl_up_sync(FULL_MASK, ar, 1), pg = __shfl_up_sync(FULL_MASK, ag, 1), pb = __shfl_up_sync(FULL_MASK, ab, 1);
+            if (mine && sub == s) {
+                if (s > 0) { ar = pr; ag = pg; ab = pb; }
+                for (int k = 0; k < L.nlog; k++) { ar = f_add(ar, log[3 * k]); ag = f_add(ag, log[3 * k + 1]); ab = f_add(ab, log[3 * k + 2]); }
+            }
+        }
+        if (mine && sub == 8) {
+            RT_CHECK(L.x >= 0 && L.x < F.w && L.y >= 0 && L.y < F.h, RT_CHK_PIXEL);
+            pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(ar, ag, ab);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -816,9 +880,23 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         n_work = p.n_valid;
     }
+    const bool split = p.frame.split0 != 0;
+    if (split) {         // class 0, one lane per sub-sample, on the second stream: its blocks take the SMs first, the main kernel's follow as they retire
+        auto ks = p.sphere_lights == 3 ? whitted_split_kernel<3> : p.sphere_lights == 2 ? whitted_split_kernel<2> : whitted_split_kernel<1>;
+        int nbs = 0;
+        if ((e = configure_kernel(ks, W_THREADS, smem, &nbs)) != cudaSuccess) return e;
+        if (p.max_blocks_per_sm > 0 && nbs > p.max_blocks_per_sm) nbs = p.max_blocks_per_sm;
+        if ((e = cudaEventRecord(p.ev_fork, stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(p.aux_stream, p.ev_fork, 0)) != cudaSuccess) return e;
+        ks<<<(unsigned)((long)nbs * p.sm_count), W_THREADS, smem, p.aux_stream>>>(p.frame, p.shard, p.order, p.class_counts, p.pixels, p.split_work_counter);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(p.ev_join, p.aux_stream)) != cudaSuccess) return e;
+    }
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
                                                   p.counters, p.bvh, p.order ? p.cls : nullptr, p.filler_items);
-    if ((e = cudaGetLastError()) != cudaSuccess || !p.redo_work_counter) return e;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (split && (e = cudaStreamWaitEvent(stream, p.ev_join, 0)) != cudaSuccess) return e;
+    if (!p.redo_work_counter) return e;
     // The pixels the timed kernel reported (blocked lights it may not skip), again, as the reference computes them.  Launched without
     // looking at the count -- that would be a round trip to the host; a launch that finds the list empty is a few microseconds.
     kern_t kx = bvh ? (p.stage_mode == 0 ? whitted_kernel<false, 0, 0, true, true> : whitted_kernel<false, 1, 0, true, true>)

@@ -71,6 +71,8 @@ struct WLaunch {
     uint32_t n_items;
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
+    // frame.split0: class 0 goes to whitted_split_kernel on aux_stream (forked from / joined to the launch stream with the two events)
+    unsigned *split_work_counter; cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
     unsigned *redo_work_counter; // NULL: no EXACT launch after the kernel (counting launches); else its work counter (frame.redo_* name the list)
     int count, sm_count, max_blocks_per_sm;
     int stage_mode;             // 3: all tables in static shared memory (small scenes), 2: all tables in dynamic shared memory, 1: geometry / flags / runs only, 0: read through L1 / L2

@@ -74,6 +74,7 @@ struct WFrame {
     float cull_rp2;             // the culls' margins hold for hit points with |P|^2 < cull_rp2
     float reject_k;             // K of w_shadow_sphere_keep for this scene
     WGrid grid;
+    int split0;                 // 1: the pixels of cost class 0 are rendered by whitted_split_kernel; this launch starts at class 1
     // Blocked lights (see "Blocked lights and the redo list" below).
     float tame_reach[2];        // a hit point on a plane [0] / a sphere [1] closer than this to every light of its batch may skip its blocked lights;
                                 //  0: none may (build_w_soa)
@@ -85,6 +86,7 @@ struct WFrame {
 struct WLane {
     int x, y, sub;
     float ar, ag, ab;                               // pixel accumulator
+    int nlog;                                       // SPLIT: triples in the lane's log
     int head, tail;                                 // FIFO cursors of the current sub-sample
     float dx, dy, dz;                               // direction of the ray being processed
     float weight, r_index, tr, tg, tb;              // its weight, medium index, transparency
@@ -853,26 +855,37 @@ RT_HD void w_after_shadow(WLane &L, const WFrame &F) {
 
 // The ray is complete: fold its colour into the pixel (RNO:351-368), spawn its children (RNO:370-432) and move
 // on to the next ray of the FIFO, the next sub-sample, or the end of the pixel (returns true).
-template <bool COUNT>
-RT_HD bool w_finalize(WLane &L, const WFrame &F, f4 *q) {
+// SPLIT (whitted_split_kernel: one lane per SUB-SAMPLE of a pixel): the pixel's accumulator runs through all rays of all nine sub-samples
+// in turn (RNO:351-368), so a lane that traces sub-sample s cannot add to it -- it appends what each of its rays would have added to
+// `log` (at most 63 triples: a depth-5 binary ray tree), L.tail of the NEXT free slot kept in L.nlog, and the nine logs are added in the
+// reference's order afterwards.  A triple of zeros is not logged: the accumulator starts at +0 and x + (+-0) = x for every x that is
+// not -0, which a sum that started at +0 never is.  The sub-sample ends the lane's work (returns true).
+template <bool COUNT, bool SPLIT = false>
+RT_HD bool w_finalize(WLane &L, const WFrame &F, f4 *q, float *log = nullptr) {
     // The ray is finished: fold its colour into the pixel (RNO:351-368).
+    float ar, ag, ab;
     if (L.kind == W_PRIMARY) {
         if (COUNT) L.c_samples++;
         RT_CHECK(L.x >= 0 && L.x < F.w && L.y >= 0 && L.y < F.h && L.sub >= 0 && L.sub < 9, RT_CHK_PIXEL);
         if (F.hit_ids) F.hit_ids[((size_t)L.y * F.w + L.x) * 9 + L.sub] = L.hit;
-        L.ar = f_add(L.ar, f_mul(L.cr, L.weight));
-        L.ag = f_add(L.ag, f_mul(L.cg, L.weight));
-        L.ab = f_add(L.ab, f_mul(L.cb, L.weight));
+        ar = f_mul(L.cr, L.weight); ag = f_mul(L.cg, L.weight); ab = f_mul(L.cb, L.weight);
     } else if (L.kind == W_REFLECTED) {
         const f4 fa = F.mat_a[L.from];
-        L.ar = f_add(L.ar, f_mul(f_mul(f_mul(L.cr, L.weight), fa.x), L.tr));
-        L.ag = f_add(L.ag, f_mul(f_mul(f_mul(L.cg, L.weight), fa.y), L.tg));
-        L.ab = f_add(L.ab, f_mul(f_mul(f_mul(L.cb, L.weight), fa.z), L.tb));
+        ar = f_mul(f_mul(f_mul(L.cr, L.weight), fa.x), L.tr);
+        ag = f_mul(f_mul(f_mul(L.cg, L.weight), fa.y), L.tg);
+        ab = f_mul(f_mul(f_mul(L.cb, L.weight), fa.z), L.tb);
     } else {
-        L.ar = f_add(L.ar, f_mul(f_mul(L.cr, L.weight), L.tr));
-        L.ag = f_add(L.ag, f_mul(f_mul(L.cg, L.weight), L.tg));
-        L.ab = f_add(L.ab, f_mul(f_mul(L.cb, L.weight), L.tb));
+        ar = f_mul(f_mul(L.cr, L.weight), L.tr);
+        ag = f_mul(f_mul(L.cg, L.weight), L.tg);
+        ab = f_mul(f_mul(L.cb, L.weight), L.tb);
     }
+    if (SPLIT) {
+        if (!((ar == 0.f) & (ag == 0.f) & (ab == 0.f))) {          // NaN: logged
+            RT_CHECK(L.nlog < 63, RT_CHK_FIFO);
+            log[3 * L.nlog] = ar; log[3 * L.nlog + 1] = ag; log[3 * L.nlog + 2] = ab;
+            L.nlog++;
+        }
+    } else { L.ar = f_add(L.ar, ar); L.ag = f_add(L.ag, ag); L.ab = f_add(L.ab, ab); }
     // Children (RNO:370-432).  A miss spawns nothing (the reference reads prims[-1] there; its shipped
     // scenes are closed boxes, so it never happens -- SURVEY.md 2.3).
     if (L.hit >= 0 && L.depth < W_TRACEDEPTH) {
@@ -910,8 +923,10 @@ RT_HD bool w_finalize(WLane &L, const WFrame &F, f4 *q) {
         }
     }
     if (L.head < L.tail) { w_pop(q, L); return false; }
-    L.sub++;
-    if (L.sub < 9) { w_start_subsample(L, F); return false; }
+    if (!SPLIT) {
+        L.sub++;
+        if (L.sub < 9) { w_start_subsample(L, F); return false; }
+    }
     L.phase = PH_IDLE;
     return true;
 }

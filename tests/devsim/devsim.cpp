@@ -70,9 +70,11 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
     uint32_t redo_one[1];
     F.tame_reach[0] = soa.tame_reach[0]; F.tame_reach[1] = soa.tame_reach[1]; F.redo_count = nullptr; F.redo_list = redo_one; F.redo_cap = 1;
     F.pcull = nullptr; F.rbox = nullptr; F.cull_rp2 = 0.f; F.reject_k = 0.f;
-    memset(&F.grid, 0, sizeof F.grid);
+    memset(&F.grid, 0, sizeof F.grid); F.split0 = 0;
     std::vector<uint32_t> grid_cells, tile_words;
     WCull cull;
+    const bool split = use_runs == 6;          // 6: like 4, every pixel the way whitted_split_kernel renders class-0 pixels (one lane per sub-sample, logs added in order)
+    if (split) use_runs = 4;
     if (use_runs == 4 || use_runs == 5) {      // what a timed launch does: the runs without dead primitives (5: + the hierarchy), the shadow-round culls, no counting
         if (use_runs == 5) { build_w_bvh(prims, n, soa); F.runs = soa.runs_bvh.data(); F.n_runs = (int)soa.runs_bvh.size() / 3; }
         else { F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3; }
@@ -103,7 +105,41 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
         WLane L;
         memset(&L, 0, sizeof L);
         w_begin_pixel(L, F, x, y);
-        if (use_runs >= 4) {
+        if (split) {
+            float ar = 0.f, ag = 0.f, ab = 0.f;
+            std::vector<float> log(3 * 63);
+            redo_count = 0; F.redo_count = &redo_count;
+            for (int sub = 0; sub < 9; sub++) {
+                memset(&L, 0, sizeof L);
+                L.x = x; L.y = y; L.sub = sub; L.nlog = 0;
+                w_start_subsample(L, F);
+                for (;;) {
+                    w_query_nearest_tiles(L, F.geom, F.flags, F.runs, F.n_runs, true, F.grid);
+                    w_after_nearest<false>(L, F);
+                    while (L.phase == PH_SHADOW) {
+                        w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);
+                        w_after_shadow<false>(L, F);
+                    }
+                    if (w_finalize<false, true>(L, F, queue, log.data())) break;
+                }
+                for (int k = 0; k < L.nlog; k++) { ar = f_add(ar, log[3 * k]); ag = f_add(ag, log[3 * k + 1]); ab = f_add(ab, log[3 * k + 2]); }
+            }
+            L.ar = ar; L.ag = ag; L.ab = ab;
+            if (redo_count) {           // reported: the pixel again, one lane, as the EXACT launch computes it
+                g_redo_pixels++;
+                memset(&L, 0, sizeof L);
+                w_begin_pixel(L, F, x, y);
+                for (;;) {
+                    w_query_nearest_tiles(L, F.geom, F.flags, F.runs, F.n_runs, true, F.grid);
+                    w_after_nearest<false, 0, true>(L, F);
+                    while (L.phase == PH_SHADOW) {
+                        w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);
+                        w_after_shadow<false, 0, true>(L, F);
+                    }
+                    if (w_finalize<false>(L, F, queue)) break;
+                }
+            }
+        } else if (use_runs >= 4) {
             // the body of the timed kernel's loop, for one lane -- and, when the pixel reported a batch whose blocked lights may not be
             // skipped, the pixel again as the EXACT launch computes it (whitted_lane.cuh, "Blocked lights and the redo list")
             redo_count = 0; F.redo_count = &redo_count;
@@ -178,7 +214,7 @@ void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, i
     F.W.runs = soa.runs_hot.data(); F.W.n_runs = (int)soa.runs_hot.size() / 3;
     F.W.n = n; F.W.n_lights = (int)soa.lights.size(); F.W.n_spheres = soa.n_spheres; F.W.n_planes = soa.n_planes;
     F.W.w = w; F.W.h = h; F.W.hit_ids = nullptr;
-    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f; F.W.reject_k = 0.f; memset(&F.W.grid, 0, sizeof F.W.grid); F.W.tame_reach[0] = F.W.tame_reach[1] = 0.f; F.W.redo_count = nullptr; F.W.redo_list = nullptr; F.W.redo_cap = 0;
+    F.W.pcull = nullptr; F.W.rbox = nullptr; F.W.cull_rp2 = 0.f; F.W.reject_k = 0.f; memset(&F.W.grid, 0, sizeof F.W.grid); F.W.split0 = 0; F.W.tame_reach[0] = F.W.tame_reach[1] = 0.f; F.W.redo_count = nullptr; F.W.redo_list = nullptr; F.W.redo_cap = 0;
     F.sx = sx.data(); F.sy = sy.data(); F.row0 = 20; F.row1 = h - 70;
     R306Tree T;
     for (int y = F.row0; y < F.row1; y++)

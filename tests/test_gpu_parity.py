@@ -281,7 +281,7 @@ def test_whitted_blocked_lights_of_untame_batches_go_through_the_exact_launch(gp
             gpu.set_tuning(rt.TUNE_WHITTED_REDO_CAP, cap)
             n0 = gpu.launch_count()
             px, hits = gpu.whitted_render(nan_scene, w, h, want_hit_ids=True)
-            assert gpu.launch_count() - n0 == 3                  # pre-pass, timed kernel, exact launch
+            assert gpu.launch_count() - n0 >= 3                  # pre-pass, timed kernel(s), exact launch
             assert gpu.whitted_redo_reports() > 1, cap
             assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o), cap
     finally:
@@ -296,6 +296,25 @@ def test_whitted_blocked_lights_of_untame_batches_go_through_the_exact_launch(gp
     assert gpu.whitted_redo_reports() > 160 * 120               # every shadow batch of the frame
     px_o, hits_o, _ = oracle_whitted(orc, tiny, 160, 120)
     assert np.array_equal(hits, hits_o) and np.array_equal(px, px_o)
+
+
+def test_whitted_split_kernel_and_tables_change_nothing(gpu, orc, rt):
+    """Class-0 pixels one lane per sub-sample on a second stream (RT_TUNE_WHITTED_SPLIT), the shadow-candidate grid and the primary-ray
+    tiles (RT_TUNE_WHITTED_GRID 1 / 2 / 0): every combination gives the oracle's bytes and hit IDs -- on sizes with padding, under
+    sharding, and on the second scene of the reference."""
+    box = rt.whitted_create_scene(0)
+    try:
+        for prims, (w, h, rank, world, tile) in [(box, (333, 250, 0, 1, 8)), (box, (640, 360, 0, 1, 8)), (box, (61, 37, 1, 3, 4)), (box, (200, 150, 1, 2, 8))]:
+            gpu.set_shard(rank, world, tile)
+            px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
+            rows = np.array([(y // tile) % world == rank for y in range(h)])
+            for split, grid in [(1, 1), (0, 1), (1, 2), (0, 2), (1, 0), (0, 0)]:
+                gpu.set_tuning(rt.TUNE_WHITTED_SPLIT, split); gpu.set_tuning(rt.TUNE_WHITTED_GRID, grid)
+                a, ha = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+                assert np.array_equal(a[rows], px_o[rows]) and np.array_equal(ha[rows], hits_o[rows]), (w, h, split, grid)
+    finally:
+        gpu.set_shard(0, 1, 8)
+        gpu.set_tuning(rt.TUNE_WHITTED_SPLIT, 1); gpu.set_tuning(rt.TUNE_WHITTED_GRID, 1)
 
 
 def test_whitted_counters_equal_oracle(gpu, orc, rt):

@@ -301,6 +301,22 @@ def test_whitted_blocked_light_times_an_overflowed_specular_term_is_nan_like_the
     assert devsim.devsim_whitted_redo_pixels() == 0
 
 
+def test_whitted_one_lane_per_subsample_with_ordered_logs_equals_one_lane_per_pixel(devsim, orc, rt):
+    """whitted_split_kernel's arithmetic on the lane simulator (mode 6): every sub-sample of a pixel traced on its own with the addends of
+    its rays logged (w_finalize<.., SPLIT>, zero triples skipped), the nine logs added in order -- the same bytes and hit IDs as the
+    reference's one running accumulator, on the reference's scenes, through the grid and the primary-ray tiles, and on the room whose
+    accumulators turn NaN."""
+    import os
+    from conftest import GOLDEN
+    for prims, (w, h) in [(rt.whitted_create_scene(0), (160, 90)), (rt.whitted_create_scene(0), (61, 37)),
+                          (np.load(os.path.join(GOLDEN, "whitted_blocked_light_nan.npy")), (64, 48))]:
+        px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, None)
+        px, hits = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
+        devsim.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, None, None, 6)
+        assert np.array_equal(px, px_o) and np.array_equal(hits, hits_o), (w, h)
+
+
 def test_hierarchy_builder_on_degenerate_inputs(devsim, rt):
     """build_pt_bvh: every sphere ends up exactly once in the tree or in the always-tested list, and the depth stays below
     the traversal stack (64) -- one sphere, a thousand identical ones, NaN / inf / huge entries, a line of 5 000, 200 000

@@ -12,15 +12,15 @@ for scene in (0,):
     for (w, h) in sizes:
         out, frames = [], []
         for rep in range(2):
-            for grid in (1, 2, 0):
-                r.set_tuning(rt.TUNE_WHITTED_GRID, grid)
+            for grid, split in ((1, 1), (1, 0), (2, 0), (0, 0)):
+                r.set_tuning(rt.TUNE_WHITTED_GRID, grid); r.set_tuning(rt.TUNE_WHITTED_SPLIT, split)
                 r.whitted_upload(prims, w, h)
                 for _ in range(3): r.whitted_launch()
                 r.sync()
                 ts = []
                 for _ in range(9):
                     r.timer_begin(); r.whitted_launch(); ts.append(r.timer_end())
-                out.append("grid=%d %.3f ms" % (grid, min(ts)))
+                out.append("grid=%d split=%d %.3f ms" % (grid, split, min(ts)))
                 frames.append(r.whitted_download())
         same = all(np.array_equal(frames[0], f) for f in frames[1:])
         print("%-22s scene %d %dx%d: %s | same bytes: %s" % (os.path.basename(os.environ.get("RT_B200_LIB", "product")), scene, w, h, " | ".join(out), same))
