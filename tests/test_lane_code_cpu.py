@@ -285,7 +285,10 @@ def test_whitted_blocked_light_times_an_overflowed_specular_term_is_nan_like_the
     px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
     orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 4, None)
     px_r = np.zeros((h, w, 4), np.uint8)
-    ref_whitted.ref_whitted_render(vp(px_r), w, h, vp(prims), prims.size)
+    # the room is open and the reference reads prims[-1] after a miss (RNO:370-432): give it an all-zero record there (spawns nothing,
+    # what the oracle defines) instead of whatever the allocator left in front of the table
+    padded = np.zeros(prims.size + 1, prims.dtype); padded[1:] = prims
+    ref_whitted.ref_whitted_render(vp(px_r), w, h, ctypes.c_void_p(padded.ctypes.data + prims.dtype.itemsize), prims.size)
     assert np.array_equal(px_o, px_r)
     assert not px_o[29, 29, :3].any() and not px_o[30, 29, :3].any()      # the two pixels whose accumulator is NaN
     devsim.devsim_whitted_redo_pixels.restype = ctypes.c_long
