@@ -46,7 +46,7 @@ class Counters(C.Structure):
 
 RT_DIFF_, RT_SPEC_, RT_REFR_ = 0, 1, 2
 RT_OK, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_ARG, RT_ERR_STATE, RT_ERR_CAPACITY, RT_ERR_IO = 0, -1, -2, -3, -4, -5, -6
-TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER, TUNE_PT_ALIGNED, TUNE_PT_BVH, TUNE_WHITTED_BVH, TUNE_R306_SPLIT, TUNE_PT_SINCOS_TABLE, TUNE_WHITTED_BLOCKS, TUNE_WHITTED_FILLER_PCT, TUNE_WHITTED_STAGE_CAP, TUNE_WHITTED_REDO_CAP, TUNE_WHITTED_GRID, TUNE_WHITTED_SPLIT = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14
+TUNE_PT_MAX_RESIDENT_BYTES, TUNE_PT_CHUNK_SPHERES, TUNE_MAX_BLOCKS_PER_SM, TUNE_WHITTED_COST_ORDER, TUNE_PT_ALIGNED, TUNE_PT_BVH, TUNE_WHITTED_BVH, TUNE_R306_SPLIT, TUNE_PT_SINCOS_TABLE, TUNE_WHITTED_BLOCKS, TUNE_WHITTED_FILLER_PCT, TUNE_WHITTED_STAGE_CAP, TUNE_WHITTED_REDO_CAP, TUNE_WHITTED_GRID, TUNE_WHITTED_SPLIT, TUNE_WHITTED_SPLIT_BLOCKS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
 BUF_WHITTED_PIXELS, BUF_WHITTED_HITS, BUF_PT_PIXELS, BUF_PT_COLORS, BUF_PT_SEEDS = 0, 1, 2, 3, 4
 IPC_HANDLE_BYTES = 80
 

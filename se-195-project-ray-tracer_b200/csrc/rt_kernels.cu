@@ -628,14 +628,23 @@ whitted_classify_kernel(WFrame F, Shard S, uint32_t n_items, uint32_t *lists /* 
         const uint32_t item = base + threadIdx.x;
         int x = 0, y = 0;
         const bool valid = item < n_items && item_to_pixel(S, F.w, item, x, y);
-        WLane L;
-        L.phase = PH_IDLE; L.qhit = -1; L.cumu = 0.f; L.qkind = 0;
-        L.qox = L.qoy = L.qoz = 0.f; L.qdx = L.qdy = L.qdz = 0.f;
-        if (valid) { L.x = x; L.y = y; L.sub = 4; w_start_subsample(L, F); }
-        w_query_nearest<false>(L, s_geom, s_runs, F.n_runs, valid);
-        if (use_bvh && valid) w_bvh_nearest(L, B);
         int cls = W_COST_CLASSES - 1;
-        if (valid && L.qhit >= 0) cls = F.mat_b[L.qhit].y > 0.f ? 0 : (F.mat_a[L.qhit].w > 0.f ? 1 : 2);
+        if (F.split0) {
+            // With the primary-ray tiles nothing needs tracing: a pixel is class 0 -- rendered one lane per sub-sample by whitted_split_kernel --
+            // iff SOME primary ray of its 8x4 tile can reach a reflecting or refracting primitive (the tile's word), else class 2: nine
+            // primary rays that spawn nothing, the same cost for every pixel of the block.  (The centre ray's first hit is a poor guide: a
+            // mirror sphere shows the glass ones, a wall pixel on a silhouette has glass behind some of its sub-samples -- pixels "of
+            // class 1 or 2" with ray trees of hundreds of rays kept single lanes busy for 0.8 ms of any frame.)
+            if (valid && (F.grid.tiles[(y >> 2) * F.grid.tiles_x + (x >> 3)] & F.grid.deep)) cls = 0;
+        } else {
+            WLane L;
+            L.phase = PH_IDLE; L.qhit = -1; L.cumu = 0.f; L.qkind = 0;
+            L.qox = L.qoy = L.qoz = 0.f; L.qdx = L.qdy = L.qdz = 0.f;
+            if (valid) { L.x = x; L.y = y; L.sub = 4; w_start_subsample(L, F); }
+            w_query_nearest<false>(L, s_geom, s_runs, F.n_runs, valid);
+            if (use_bvh && valid) w_bvh_nearest(L, B);
+            if (valid && L.qhit >= 0) cls = F.mat_b[L.qhit].y > 0.f ? 0 : (F.mat_a[L.qhit].w > 0.f ? 1 : 2);
+        }
         const uint32_t below = (1u << lane) - 1u;
         if (cls_out && item < n_items) cls_out[item] = valid ? (uint8_t)cls : (uint8_t)255;
 #pragma unroll
@@ -886,6 +895,7 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         int nbs = 0;
         if ((e = configure_kernel(ks, W_THREADS, smem, &nbs)) != cudaSuccess) return e;
         if (p.max_blocks_per_sm > 0 && nbs > p.max_blocks_per_sm) nbs = p.max_blocks_per_sm;
+        if (p.split_blocks_per_sm > 0 && nbs > p.split_blocks_per_sm) nbs = p.split_blocks_per_sm;
         if ((e = cudaEventRecord(p.ev_fork, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(p.aux_stream, p.ev_fork, 0)) != cudaSuccess) return e;
         ks<<<(unsigned)((long)nbs * p.sm_count), W_THREADS, smem, p.aux_stream>>>(p.frame, p.shard, p.order, p.class_counts, p.pixels, p.split_work_counter);

@@ -72,6 +72,7 @@ struct WLaunch {
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
     // frame.split0: class 0 goes to whitted_split_kernel on aux_stream (forked from / joined to the launch stream with the two events)
+    int split_blocks_per_sm;    // cap on that kernel's resident CTAs per SM (0: as many as fit); the main kernel's CTAs take the rest at once
     unsigned *split_work_counter; cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
     unsigned *redo_work_counter; // NULL: no EXACT launch after the kernel (counting launches); else its work counter (frame.redo_* name the list)
     int count, sm_count, max_blocks_per_sm;

@@ -54,6 +54,7 @@ struct WGrid {
     const uint32_t *tiles;      // NULL: none
     int tiles_x;
     uint32_t all_nearest;       // the word of any other ray: every primitive a nearest query tests
+    uint32_t deep;              // the primitives that reflect or refract (m_refl > 0 or m_refr > 0): a ray that hits one has children
 };
 
 struct WFrame {

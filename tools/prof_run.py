@@ -7,7 +7,7 @@ r = rt.Renderer(0)
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 if which in ("both", "whitted"):
     prims = rt.whitted_create_scene(0)
-    r.whitted_upload(prims, 1920, 1080)
+    r.whitted_upload(prims, int(os.environ.get("PROF_W", 1920)), int(os.environ.get("PROF_H", 1080)))
     for _ in range(2):
         r.whitted_launch()
     r.sync()
