@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
 whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const unsigned *class_counts, uint32_t n_stride,
                uint32_t *pixels, unsigned *work_counter, unsigned long long *counters, PtBvh B, const uint8_t *cls, uint32_t filler_items) {
     extern __shared__ f4 s_raw[];
+    if (EXACT && *F.redo_count == 0u) return;            // nothing was reported (nearly every frame): not even the tables are staged
     const uint32_t lane = threadIdx.x & 31u;
     const f4 *s_geom; const int *s_runs;
     stage_scene<STAGED>(F, s_raw, s_geom, s_runs);

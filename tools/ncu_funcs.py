@@ -5,7 +5,7 @@ Usage: ncu_funcs.py <nvdisasm -gi listing> <kernel substr> <src.csv> [depth=3]""
 import bisect, collections, csv, os, re, sys
 sass, kname, ncsv = sys.argv[1:4]
 depth = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "se-195-project-ray-tracer_b200", "csrc")
+CSRC = os.environ.get("NCU_FUNCS_CSRC") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "se-195-project-ray-tracer_b200", "csrc")
 funcs = {}
 for f in os.listdir(CSRC):
     starts = []
