@@ -4,7 +4,9 @@ against the oracle, on random rooms -- planes of random orientation and length o
 anywhere including a hair's breadth from a wall, between two walls' sides, inside the sphere cluster.  Pixels and hit IDs must
 be identical.  `--self-check` runs the same scenes against a devsim built with -DW_CULL_TEST_NO_MARGIN (T = 0, boxes not
 grown, every face usable): that build MUST be caught, otherwise the fuzz proves nothing.
-Usage: python tools/cull_fuzz.py [n_scenes] [seed] [--self-check]"""
+Since round 2 mode 4 includes the shadow-candidate grid, the primary-ray tiles and the exact re-render of reported pixels; `--split` runs
+mode 6 (every pixel one lane per sub-sample with ordered logs, as whitted_split_kernel renders them).
+Usage: python tools/cull_fuzz.py [n_scenes] [seed] [--self-check] [--split]"""
 import ctypes, os, subprocess, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -93,6 +95,7 @@ def main():
     n_scenes = int(args[0]) if args else 200
     seed = int(args[1]) if len(args) > 1 else 1
     self_check = "--self-check" in sys.argv
+    mode = 6 if "--split" in sys.argv else 4
     rt = g.load(); orc = g.oracle()
     dev = build_no_margin() if self_check else ctypes.CDLL(os.path.join(g.DEVSIM_DIR, "libdevsim.so"))
     rs = np.random.RandomState(seed)
@@ -106,14 +109,14 @@ def main():
         dev.devsim_whitted_cull_stats(vp(prims), prims.size, vp(st))
         culled_scenes += int(st[0])
         px, hits = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
-        dev.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, None, None, 4)
+        dev.devsim_whitted(vp(px), vp(hits), w, h, vp(prims), prims.size, 0, 1, 8, None, None, mode)
         px_o, hits_o = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 9), np.int32)
         orc.oracle_whitted_render(vp(px_o), vp(hits_o), w, h, vp(prims), prims.size, 8, None)
         if not (np.array_equal(px, px_o) and np.array_equal(hits, hits_o)):
             bad += 1
             if bad <= 10:
                 print(f"MISMATCH scene {it}: n={prims.size}, {int(np.count_nonzero((px != px_o).any(axis=2)))} pixels differ", flush=True)
-    print(f"cull fuzz{' (NO-MARGIN self-check build)' if self_check else ''}: {n_scenes} scenes {w}x{h}, culls active in {culled_scenes}: "
+    print(f"cull fuzz{' (NO-MARGIN self-check build)' if self_check else ''}{' (split mode)' if mode == 6 else ''}: {n_scenes} scenes {w}x{h}, culls active in {culled_scenes}: "
           f"{bad} mismatches ({time.time() - t0:.0f} s)")
     if self_check:
         sys.exit(0 if bad > 0 else 1)               # the broken build must be caught
