@@ -117,7 +117,8 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
                     w_query_nearest_tiles(L, F.geom, F.flags, F.runs, F.n_runs, true, F.grid);
                     w_after_nearest<false>(L, F);
                     while (L.phase == PH_SHADOW) {
-                        w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);
+                        if (F.grid.cells) w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);       // (a table without a grid: the GPU does not split it)
+                        else w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
                         w_after_shadow<false>(L, F);
                     }
                     if (w_finalize<false, true>(L, F, queue, log.data())) break;
@@ -133,7 +134,8 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
                     w_query_nearest_tiles(L, F.geom, F.flags, F.runs, F.n_runs, true, F.grid);
                     w_after_nearest<false, 0, true>(L, F);
                     while (L.phase == PH_SHADOW) {
-                        w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);
+                        if (F.grid.cells) w_query_shadow_grid(L, F.geom, F.flags, true, F.grid, F.reject_k);
+                        else w_query_shadow<false, true>(L, F.geom, F.runs, F.n_runs, true, F.pcull, F.rbox, F.reject_k);
                         w_after_shadow<false, 0, true>(L, F);
                     }
                     if (w_finalize<false>(L, F, queue)) break;
