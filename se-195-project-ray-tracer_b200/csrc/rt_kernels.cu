@@ -460,18 +460,23 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
 #endif
 }
 
-// The pixels of cost class 0 (a refracting surface behind the centre ray), one lane per SUB-SAMPLE: a warp takes three pixels at a time,
-// lanes 9g .. 9g+8 trace the nine sub-samples of pixel g side by side (lanes 27-31 idle), every lane logging what its rays add to the
-// pixel (w_finalize<.., SPLIT>); when all are done the nine logs of a pixel are added in the reference's order -- lane 9g first, the
-// running sum handed from lane to lane -- and lane 9g+8 stores the pixel.  Same bits as one lane tracing the nine sub-samples in turn
-// (whitted_kernel), but the longest chain of rays one lane traces back to back is 63 instead of 567: such a pixel alone took 1.7 ms of
-// the 2.4 ms 1080p frame and bounded small frames and strong scaling outright.  Runs next to the main kernel on a second stream
-// (rtk_launch_whitted); GRID tables as there.
+// The pixels of cost class 0 (their primary-ray tile can see a reflecting or refracting primitive), one lane per SUB-SAMPLE.  A CTA is
+// nine warps and takes 32 pixels of the class list at a time: warp s traces sub-sample s of all 32 (neighbouring pixels, the same
+// sub-pixel offset: 32 coherent rays, every lane busy), every lane logging what its rays add to its pixel (w_finalize<.., SPLIT>).  When
+// the nine warps are done, the nine logs of each pixel are added in the reference's order: warp 0 adds its logs (32 pixels side by
+// side) and leaves the running sums in shared memory, warp 1 continues from them, ... and warp 8 stores the pixels.  Same bits as one
+// lane tracing the nine sub-samples in turn (whitted_kernel), but the longest chain of rays one lane traces back to back is 63 instead
+// of 567: such a pixel alone took 1.7 ms of the 2.4 ms 1080p frame and bounded small frames and strong scaling outright.  (First form:
+// three pixels per warp, lanes 9g..9g+8 one pixel, sums handed on by shuffles -- 27 of 32 lanes, and the sums ran at one lane of
+// nine: 12 % of the kernel.)  Runs next to the main kernel on a second stream (rtk_launch_whitted); GRID tables as there.
 template <int NL>
-__global__ void __launch_bounds__(W_THREADS, W_MIN_BLOCKS)
+__global__ void __launch_bounds__(W_SPLIT_THREADS, W_SPLIT_MIN_BLOCKS)
 whitted_split_kernel(WFrame F, Shard S, const uint32_t *order, const unsigned *class_counts, uint32_t *pixels, unsigned *work_counter) {
     extern __shared__ f4 s_raw[];
+    __shared__ float s_sum[3][32];
+    __shared__ uint32_t s_base;
     const uint32_t lane = threadIdx.x & 31u;
+    const int sub = (int)(threadIdx.x >> 5);                 // this warp's sub-sample, 0 .. 8
     const f4 *s_geom; const int *s_runs;
     stage_scene<3>(F, s_raw, s_geom, s_runs);
     f4 queue[3 * W_QUEUE_SLOTS];
@@ -480,16 +485,15 @@ whitted_split_kernel(WFrame F, Shard S, const uint32_t *order, const unsigned *c
     L.phase = PH_IDLE;
     L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_sphere_tests = L.c_plane_tests = 0; L.c_shadow_lit = 0;
     const uint32_t n0 = class_counts[0];
-    const int group = (int)lane / 9, sub = (int)lane % 9;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(work_counter, 3u);
-        base = __shfl_sync(FULL_MASK, base, 0);
-        if (base >= n0) break;
+        if (threadIdx.x == 0) s_base = atomicAdd(work_counter, 32u);
+        __syncthreads();
+        const uint32_t base = s_base;
+        if (base >= n0) break;                               // the same for every thread of the CTA
         bool mine = false;
-        if (lane < 27u && base + (uint32_t)group < n0) {
+        if (base + lane < n0) {
             int x, y;
-            if (item_to_pixel(S, F.w, order[base + group], x, y)) {
+            if (item_to_pixel(S, F.w, order[base + lane], x, y)) {
                 L.x = x; L.y = y; L.sub = sub; L.nlog = 0;
                 w_start_subsample(L, F);
                 mine = true;
@@ -506,19 +510,20 @@ whitted_split_kernel(WFrame F, Shard S, const uint32_t *order, const unsigned *c
             }
             if (L.phase == PH_FINAL) w_finalize<false, true>(L, F, queue, log);
         }
-        // the nine logs of each pixel, in order
-        float ar = 0.f, ag = 0.f, ab = 0.f;
+        // the nine logs of each pixel, in order: warp s continues the sums warp s-1 left
 #pragma unroll 1
         for (int s = 0; s < 9; s++) {
-            const float pr = __shfl_up_sync(FULL_MASK, ar, 1), pg = __shfl_up_sync(FULL_MASK, ag, 1), pb = __shfl_up_sync(FULL_MASK, ab, 1);
-            if (mine && sub == s) {
-                if (s > 0) { ar = pr; ag = pg; ab = pb; }
+            if (sub == s && mine) {
+                float ar = 0.f, ag = 0.f, ab = 0.f;
+                if (s > 0) { ar = s_sum[0][lane]; ag = s_sum[1][lane]; ab = s_sum[2][lane]; }
                 for (int k = 0; k < L.nlog; k++) { ar = f_add(ar, log[3 * k]); ag = f_add(ag, log[3 * k + 1]); ab = f_add(ab, log[3 * k + 2]); }
+                if (s < 8) { s_sum[0][lane] = ar; s_sum[1][lane] = ag; s_sum[2][lane] = ab; }
+                else {
+                    RT_CHECK(L.x >= 0 && L.x < F.w && L.y >= 0 && L.y < F.h, RT_CHK_PIXEL);
+                    pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(ar, ag, ab);
+                }
             }
-        }
-        if (mine && sub == 8) {
-            RT_CHECK(L.x >= 0 && L.x < F.w && L.y >= 0 && L.y < F.h, RT_CHK_PIXEL);
-            pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(ar, ag, ab);
+            __syncthreads();
         }
     }
 }
@@ -894,12 +899,12 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     if (split) {         // class 0, one lane per sub-sample, on the second stream: its blocks take the SMs first, the main kernel's follow as they retire
         auto ks = p.sphere_lights == 3 ? whitted_split_kernel<3> : p.sphere_lights == 2 ? whitted_split_kernel<2> : whitted_split_kernel<1>;
         int nbs = 0;
-        if ((e = configure_kernel(ks, W_THREADS, smem, &nbs)) != cudaSuccess) return e;
+        if ((e = configure_kernel(ks, W_SPLIT_THREADS, smem, &nbs)) != cudaSuccess) return e;
         if (p.max_blocks_per_sm > 0 && nbs > p.max_blocks_per_sm) nbs = p.max_blocks_per_sm;
         if (p.split_blocks_per_sm > 0 && nbs > p.split_blocks_per_sm) nbs = p.split_blocks_per_sm;
         if ((e = cudaEventRecord(p.ev_fork, stream)) != cudaSuccess) return e;
         if ((e = cudaStreamWaitEvent(p.aux_stream, p.ev_fork, 0)) != cudaSuccess) return e;
-        ks<<<(unsigned)((long)nbs * p.sm_count), W_THREADS, smem, p.aux_stream>>>(p.frame, p.shard, p.order, p.class_counts, p.pixels, p.split_work_counter);
+        ks<<<(unsigned)((long)nbs * p.sm_count), W_SPLIT_THREADS, smem, p.aux_stream>>>(p.frame, p.shard, p.order, p.class_counts, p.pixels, p.split_work_counter);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = cudaEventRecord(p.ev_join, p.aux_stream)) != cudaSuccess) return e;
     }
