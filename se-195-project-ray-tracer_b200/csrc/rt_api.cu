@@ -425,7 +425,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
         if (p.stage_mode >= 2) p.stage_mode = 1;        // the hierarchy kernels read the materials through L1 / L2
     } else memset(&p.bvh, 0, sizeof p.bvh);
     memset(&F.grid, 0, sizeof F.grid);
-    if (p.stage_mode == 3 && !ctx->counting && !p.use_bvh && ctx->w_grid && ctx->w_grid_ready && ctx->w_cull.grid_gz > 0 && p.sphere_lights >= 1 && p.sphere_lights <= 3) { F.grid = ctx->w_cull.grid; F.grid.cells = ctx->d_wgrid; F.grid.tiles = ctx->w_grid == 2 ? nullptr : ctx->d_wtiles; F.grid.tiles_x = (ctx->w_w + 7) / 8; }
+    if (p.stage_mode == 3 && !ctx->counting && !p.use_bvh && ctx->w_grid && ctx->w_grid_ready && ctx->w_cull.grid_gz > 0 && p.sphere_lights >= 1 && p.sphere_lights <= 3) { F.grid = ctx->w_cull.grid; F.grid.cells = ctx->d_wgrid; F.grid.tiles = ctx->w_grid == 2 ? nullptr : ctx->d_wtiles; F.grid.tiles_x = (ctx->w_w + 7) / 8; F.grid.tiles_y = (ctx->w_h + 3) / 4; }
     if (ctx->whitted_sort && p.n_items) {
         if (p.n_items > ctx->worder_cap) {
             if (ctx->d_worder) cudaFree(ctx->d_worder);

@@ -400,7 +400,7 @@ whitted_kernel(WFrame F, Shard S, uint32_t n_items, const uint32_t *order, const
                     if (cls && item >= n_listed) { it = item - n_listed; take = cls[it] == 2; }     // filler: a class-2 pixel of the first blocks
                     else it = item < n0 ? order[item] : (item < n0 + n1 ? order[n_stride + item - n0] : order[2 * (size_t)n_stride + item - n0 - n1]);
                 }
-                if (EXACT && !redo_all) { const uint32_t id = F.redo_list[item]; w_begin_pixel(L, F, (int)(id % (uint32_t)F.w), (int)(id / (uint32_t)F.w)); }
+                if (EXACT && !redo_all) { RT_CHECK(item < F.redo_cap, RT_CHK_WORKLIST); const uint32_t id = F.redo_list[item]; w_begin_pixel(L, F, (int)(id % (uint32_t)F.w), (int)(id / (uint32_t)F.w)); }
                 else if (take && item_to_pixel(S, F.w, it, x, y)) w_begin_pixel(L, F, x, y);
             } else exhausted = true;
         }

@@ -360,13 +360,13 @@ inline void build_w_cull(const WSoA &soa, const std::vector<int> &runs, WCull &o
     for (int a = 0; a < 3; a++) { double c = std::ceil(ext[a] / edge); gdim[a] = c < 1.0 ? 1 : (c > 256.0 ? 256 : (int)c); }
     WGrid &G = out.grid;
     G.cells = nullptr; G.all = all;
-    G.tiles = nullptr; G.tiles_x = 0; G.all_nearest = 0; G.deep = 0;
+    G.tiles = nullptr; G.tiles_x = 0; G.tiles_y = 0; G.all_nearest = 0; G.deep = 0;
     for (int i = 0; i < n; i++) if (soa.mat_a[i].w > 0.f || soa.mat_b[i].y > 0.f) G.deep |= 1u << i;
     for (int r = 0; r < n_runs; r++) for (int i = runs[3 * r]; i < runs[3 * r] + runs[3 * r + 1]; i++) G.all_nearest |= 1u << i;
     G.x0 = (float)lo[0]; G.y0 = (float)lo[1]; G.z0 = (float)lo[2];
     G.ix = (float)(gdim[0] / ext[0]); G.iy = (float)(gdim[1] / ext[1]); G.iz = (float)(gdim[2] / ext[2]);
     G.fgx = (float)gdim[0]; G.fgy = (float)gdim[1]; G.fgz = (float)gdim[2];
-    G.gx = gdim[0]; G.gy = gdim[1];
+    G.gx = gdim[0]; G.gy = gdim[1]; G.gz = gdim[2];
     out.grid_gz = gdim[2];
 }
 

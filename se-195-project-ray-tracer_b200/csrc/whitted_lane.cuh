@@ -48,11 +48,11 @@ struct WGrid {
     float x0, y0, z0;           // low corner
     float ix, iy, iz;           // cells per unit length
     float fgx, fgy, fgz;        // cells per axis, as floats
-    int gx, gy;
+    int gx, gy, gz;
     uint32_t all;               // the word of a hit point outside the box: every primitive a shadow query tests
     // Primary-ray candidates ("Primary-ray tiles" below): one word per 8x4-pixel tile of the frame
     const uint32_t *tiles;      // NULL: none
-    int tiles_x;
+    int tiles_x, tiles_y;
     uint32_t all_nearest;       // the word of any other ray: every primitive a nearest query tests
     uint32_t deep;              // the primitives that reflect or refract (m_refl > 0 or m_refr > 0): a ray that hits one has children
 };
@@ -412,6 +412,7 @@ RT_HD uint32_t w_grid_build_cell(const WGrid &G, int gz, int c, const f4 *geom, 
 RT_HD uint32_t w_grid_lookup(const WLane &L, const WGrid &G) {
     const float fx = (L.px - G.x0) * G.ix, fy = (L.py - G.y0) * G.iy, fz = (L.pz - G.z0) * G.iz;
     const bool in = L.pnear & (fx >= 0.f) & (fx < G.fgx) & (fy >= 0.f) & (fy < G.fgy) & (fz >= 0.f) & (fz < G.fgz);       // NaN: outside
+    RT_CHECK(!in || ((int)fx < G.gx && (int)fy < G.gy && (int)fz < G.gz), RT_CHK_TABLE);
     return in ? G.cells[((int)fz * G.gy + (int)fy) * G.gx + (int)fx] : G.all;
 }
 // The shadow round over the grid's candidates (same tests as w_query_shadow<false, true>, fewer of them).
@@ -539,6 +540,7 @@ RT_HD uint32_t w_tile_build(int tx, int ty, int w, int h, float DX, float DY, co
 RT_HD void w_query_nearest_tiles(WLane &L, const f4 *geom, const int *flags, const int *runs, int n_runs, bool has, const WGrid &G) {
     if (!G.tiles) { w_query_nearest<false>(L, geom, runs, n_runs, has); return; }       // RT_TUNE_WHITTED_GRID = 2: the grid without the tiles
     uint32_t m = 0;
+    RT_CHECK(!has || L.kind != W_PRIMARY || ((L.x >> 3) < G.tiles_x && (L.y >> 2) < G.tiles_y && L.x >= 0 && L.y >= 0), RT_CHK_TABLE);
     if (has) m = (L.kind == W_PRIMARY) ? G.tiles[(L.y >> 2) * G.tiles_x + (L.x >> 3)] : G.all_nearest;
     uint32_t todo = warp_or(m);
     if (todo == G.all_nearest) { w_query_nearest<false>(L, geom, runs, n_runs, has); return; }       // nothing to leave out: the paired loops

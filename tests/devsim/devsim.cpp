@@ -86,7 +86,7 @@ void devsim_whitted(uint8_t *pixels, int32_t *hit_ids, int w, int h, const rt_pr
             for (size_t c = 0; c < grid_cells.size(); c++)
                 grid_cells[c] = w_grid_build_cell(F.grid, cull.grid_gz, (int)c, F.geom, F.flags, F.pcull, cull.smargin.data(), F.lcenter, F.n_lights);
             F.grid.cells = grid_cells.data();
-            F.grid.tiles_x = (w + 7) / 8;
+            F.grid.tiles_x = (w + 7) / 8; F.grid.tiles_y = (h + 3) / 4;
             tile_words.resize((size_t)F.grid.tiles_x * ((h + 3) / 4));
             for (size_t t = 0; t < tile_words.size(); t++)
                 tile_words[t] = w_tile_build((int)(t % F.grid.tiles_x), (int)(t / F.grid.tiles_x), w, h, F.DX, F.DY, F.geom, F.flags, cull.smargin.data(), F.grid.all_nearest);

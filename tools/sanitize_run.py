@@ -19,6 +19,14 @@ def single():
         r.set_tuning(rt.TUNE_WHITTED_BLOCKS, blocks); r.set_tuning(rt.TUNE_WHITTED_FILLER_PCT, filler); r.set_tuning(rt.TUNE_WHITTED_COST_ORDER, order)
         px, hits = r.whitted_render(prims, 160, 120, want_hit_ids=True)
     r.set_tuning(rt.TUNE_WHITTED_BLOCKS, 1); r.set_tuning(rt.TUNE_WHITTED_FILLER_PCT, 25); r.set_tuning(rt.TUNE_WHITTED_COST_ORDER, 1)
+    # the tables, the split kernel and the exact re-launch (with a report list that overflows, too), a frame size with padding
+    import numpy as np
+    nan_scene = np.load(os.path.join(g.ROOT, "tests", "golden", "whitted_blocked_light_nan.npy"))
+    for grid, split, cap in ((1, 1, 65536), (1, 0, 65536), (2, 0, 65536), (0, 0, 65536), (1, 1, 1)):
+        r.set_tuning(rt.TUNE_WHITTED_GRID, grid); r.set_tuning(rt.TUNE_WHITTED_SPLIT, split); r.set_tuning(rt.TUNE_WHITTED_REDO_CAP, cap)
+        r.whitted_render(prims, 333, 250, want_hit_ids=True)
+        r.whitted_render(nan_scene, 97, 61, want_hit_ids=True)
+    r.set_tuning(rt.TUNE_WHITTED_GRID, 1); r.set_tuning(rt.TUNE_WHITTED_SPLIT, 1); r.set_tuning(rt.TUNE_WHITTED_REDO_CAP, 65536)
     r.set_counting(True); r.whitted_upload(prims, 64, 48); r.whitted_launch(); r.counters(); r.set_counting(False)
     r.whitted_render(rt.whitted_create_scene(1), 96, 72, want_hit_ids=True)                 # 64 primitives: the hierarchy path
     with tempfile.TemporaryDirectory() as d:
