@@ -204,6 +204,67 @@ void devsim_whitted_cull_stats(const rt_primitive *prims, int n, int32_t *out4) 
     out4[0] = cull.enabled; out4[1] = cull.planes_cullable; out4[2] = cull.runs_cullable; out4[3] = (int)soa.runs_hot.size() / 3;
 }
 
+// The two per-scene tables of whitted_lane.cuh checked DIRECTLY against the tests they stand in front of, on the primary rays of a w x h
+// frame: out[0] primary rays whose accepted hit (every primitive tested, reference order) is NOT in their tile's word (must be 0),
+// out[1] = sum of the bits of the tile words over those rays, out[2] = rays; out[3] shadow batches with a blocker (every primitive tested)
+// that is NOT in the word of the hit point's grid cell (must be 0), out[4] = sum of the bits of those words, out[5] = batches;
+// out[6] = 1 if the table has a grid at all.
+void devsim_whitted_table_check(const rt_primitive *prims, int n, int w, int h, int64_t *out) {
+    for (int k = 0; k < 7; k++) out[k] = 0;
+    WSoA soa;
+    build_w_soa(prims, n, soa);
+    WCull cull;
+    build_w_cull(soa, soa.runs_hot, cull);
+    if (cull.grid_gz <= 0) return;
+    out[6] = 1;
+    WFrame F;
+    memset(&F, 0, sizeof F);
+    F.geom = soa.geom.data(); F.mat_a = soa.mat_a.data(); F.mat_b = soa.mat_b.data();
+    F.flags = soa.flags.data(); F.lights = soa.lights.data(); F.lcenter = soa.lcenter.data(); F.rrad = soa.rrad.data();
+    F.runs = soa.runs_hot.data(); F.n_runs = (int)soa.runs_hot.size() / 3;
+    F.n = n; F.n_lights = (int)soa.lights.size(); F.n_spheres = soa.n_spheres; F.n_planes = soa.n_planes;
+    F.w = w; F.h = h;
+    const float WX1 = -3.0f, WX2 = 3.0f, WY1 = 2.25f, WY2 = -2.25f;
+    F.DX = (WX2 - WX1) / w; F.DY = (WY2 - WY1) / h;
+    F.cull_rp2 = cull.rp2; F.reject_k = cull.reject_k;
+    F.tame_reach[0] = soa.tame_reach[0]; F.tame_reach[1] = soa.tame_reach[1];
+    F.grid = cull.grid;
+    std::vector<uint32_t> cells((size_t)F.grid.gx * F.grid.gy * cull.grid_gz), tiles((size_t)((w + 7) / 8) * ((h + 3) / 4));
+    for (size_t c = 0; c < cells.size(); c++)
+        cells[c] = w_grid_build_cell(F.grid, cull.grid_gz, (int)c, F.geom, F.flags, cull.pcull.data(), cull.smargin.data(), F.lcenter, F.n_lights);
+    F.grid.cells = cells.data(); F.grid.tiles_x = (w + 7) / 8; F.grid.tiles_y = (h + 3) / 4;
+    for (size_t t = 0; t < tiles.size(); t++)
+        tiles[t] = w_tile_build((int)(t % F.grid.tiles_x), (int)(t / F.grid.tiles_x), w, h, F.DX, F.DY, F.geom, F.flags, cull.smargin.data(), F.grid.all_nearest);
+    F.grid.tiles = tiles.data();
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int sub = 0; sub < 9; sub++) {
+                WLane L;
+                memset(&L, 0, sizeof L);
+                L.x = x; L.y = y; L.sub = sub;
+                w_start_subsample(L, F);
+                w_query_nearest<false>(L, F.geom, F.runs, F.n_runs, true);          // every primitive, the reference's order
+                const uint32_t tw = tiles[(size_t)(y >> 2) * F.grid.tiles_x + (x >> 3)];
+                out[2]++; out[1] += __builtin_popcount(tw);
+                if (L.qhit >= 0 && !((tw >> L.qhit) & 1u)) out[0]++;
+                w_after_nearest<false>(L, F);
+                if (L.phase != PH_SHADOW) continue;
+                // the batch's blockers one primitive at a time, without any cull
+                const uint32_t gw = w_grid_lookup(L, F.grid);
+                out[5]++; out[4] += __builtin_popcount(gw);
+                for (int i = 0; i < n; i++) {
+                    if (!((F.grid.all >> i) & 1u)) continue;
+                    const int before = L.sblk;
+                    L.sblk = 0;
+                    const int alive = w_alive_mask(L, true);
+                    if (F.flags[i] & W_FLAG_SPHERE) w_shadow_sphere<false>(L, F.geom[i], alive, true);
+                    else w_shadow_plane<false>(L, F.geom[i], alive, true);
+                    if (L.sblk && !((gw >> i) & 1u)) out[3]++;
+                    L.sblk = before;
+                }
+            }
+}
+
 // raytracer3.0.06 frame through the lane state machine (rows 20 .. h-71, like Engine_Render).
 void devsim_r306(uint32_t *dest, int w, int h, const rt_r306_primitive *prims, int n) {
     WSoA soa;

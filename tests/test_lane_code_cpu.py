@@ -320,6 +320,30 @@ def test_whitted_one_lane_per_subsample_with_ordered_logs_equals_one_lane_per_pi
         assert np.array_equal(px, px_o) and np.array_equal(hits, hits_o), (w, h)
 
 
+def test_whitted_tile_and_grid_words_contain_every_accepted_hit_and_every_blocker(devsim, rt):
+    """The per-scene tables of whitted_lane.cuh checked directly (not through a rendered frame): for every primary ray of a frame the hit the
+    reference's loop accepts must be in the ray's tile word, and every primitive that blocks a shadow ray of the hit point must be in the
+    word of the point's grid cell -- on the reference's scene and on random rooms of tools/cull_fuzz.py.  The words must also stay SHARP
+    on the reference's scene (a table of all-ones would pass the first two checks and cost the kernels their speed)."""
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("cull_fuzz", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "cull_fuzz.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    box = rt.whitted_create_scene(0)
+    out = np.zeros(7, np.int64)
+    devsim.devsim_whitted_table_check(vp(box), box.size, 240, 135, vp(out))
+    assert out[6] == 1 and out[0] == 0 and out[3] == 0, out
+    assert out[1] / out[2] < 2.5            # primitives a primary ray still tests (of 16): 1.6 on this frame
+    assert out[4] / out[5] < 2.0            # primitives a shadow batch still tests (of 13): 1.3
+    rs = np.random.RandomState(5)
+    with_grid = 0
+    for _ in range(40):
+        prims = fz.random_scene(rt, rs, box)
+        devsim.devsim_whitted_table_check(vp(prims), prims.size, 64, 48, vp(out))
+        assert out[0] == 0 and out[3] == 0, out
+        with_grid += int(out[6])
+    assert with_grid >= 30
+
+
 def test_hierarchy_builder_on_degenerate_inputs(devsim, rt):
     """build_pt_bvh: every sphere ends up exactly once in the tree or in the always-tested list, and the depth stays below
     the traversal stack (64) -- one sphere, a thousand identical ones, NaN / inf / huge entries, a line of 5 000, 200 000
