@@ -136,7 +136,8 @@ enum {
                                            table lists for their 8x4-pixel tile; 2 = the grid without the tiles; 0 = per-hit-point culls only.  Same image for any value */
     RT_TUNE_WHITTED_SPLIT = 14,         /* Whitted tracer, with COST_ORDER and GRID = 1: 1 (default) = the pixels with a refracting surface behind their centre ray are
                                            rendered one lane per SUB-SAMPLE by a second kernel next to the main one, their accumulators added in the reference's
-                                           order afterwards (the longest chain of rays one lane traces is 63 instead of 567); 0 = one lane per pixel.  Same image */
+                                           order afterwards (the longest chain of rays one lane traces is 63 instead of 567), and the remaining pure wall blocks by a
+                                           straight-line kernel; 2 = the latter by the general kernel; 0 = everything one lane per pixel.  Same image */
     RT_TUNE_WHITTED_SPLIT_BLOCKS = 15,  /* ... resident CTAs per SM of that second kernel (0 = as many as fit, default); the main kernel's CTAs take the rest at once */
     RT_TUNE_WHITTED_REDO_CAP = 12,      /* diagnostics: how many pixels the timed Whitted kernel can report for the exact launch that follows it (blocked lights
                                            whose shade = 0 product is not provably 0, RNO:250, 270) before that launch redoes the whole frame; 0 .. 65536 (default).

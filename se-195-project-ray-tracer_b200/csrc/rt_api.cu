@@ -275,7 +275,7 @@ int rt_set_tuning(rt_ctx *ctx, int key, int value) {
         case RT_TUNE_WHITTED_BLOCKS: ctx->whitted_blocks = value ? 1 : 0; return RT_OK;
         case RT_TUNE_WHITTED_FILLER_PCT: if (value < 0 || value > 100) break; ctx->whitted_filler_pct = value; return RT_OK;
         case RT_TUNE_WHITTED_REDO_CAP: if (value < 0 || value > (int)RT_WHITTED_REDO_CAP) break; ctx->w_redo_cap = (unsigned)value; return RT_OK;
-        case RT_TUNE_WHITTED_SPLIT: ctx->w_split = value ? 1 : 0; return RT_OK;
+        case RT_TUNE_WHITTED_SPLIT: if (value < 0 || value > 2) break; ctx->w_split = value; return RT_OK;
         case RT_TUNE_WHITTED_SPLIT_BLOCKS: if (value < 0) break; ctx->w_split_blocks = value; return RT_OK;
         case RT_TUNE_WHITTED_GRID: if (value < 0 || value > 2) break; ctx->w_grid = value; return RT_OK;
         case RT_TUNE_WHITTED_STAGE_CAP: if (value < -1 || value > 3) break; ctx->w_stage_cap = value; return RT_OK;
@@ -450,6 +450,7 @@ int rt_whitted_launch(rt_ctx *ctx) {
     F.split0 = (ctx->w_split && p.order && F.grid.cells && F.grid.tiles) ? 1 : 0;
     if (F.split0) p.filler_items = 0;            // no listed pixels in the main kernel: nothing to fill in behind
     p.split_blocks_per_sm = ctx->w_split_blocks;
+    p.wall_kernel = ctx->w_split == 1 ? 1 : 0;      // RT_TUNE_WHITTED_SPLIT = 2: the general kernel for the wall blocks
     p.split_work_counter = ctx->d_work + 4; p.aux_stream = ctx->aux_stream; p.ev_fork = ctx->ev_fork; p.ev_join = ctx->ev_join;
     CK(cudaMemsetAsync(ctx->d_work, 0, 6 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));

@@ -528,6 +528,56 @@ whitted_split_kernel(WFrame F, Shard S, const uint32_t *order, const unsigned *c
     }
 }
 
+// The pixels of cost class 2 when class 0 goes to whitted_split_kernel: 8x4 blocks whose tile word holds no reflecting or refracting
+// primitive, so NO primary ray of the block can have children (the word lists every primitive that can be the accepted hit).  A pixel is
+// then nine primary rays, each with its nearest round (the one or two planes of the tile word), its shadow batch and its shading, added
+// to the accumulator in turn -- written as that straight line instead of whitted_kernel's general state machine (no ray queue, no
+// children, no phases to dispatch on): fewer registers, no local memory, 31.9 of 32 lanes per instruction.  Same lane functions, same
+// order of operations, same bits.  A hit that does have children would be a broken table: checked builds test for it.
+template <int NL>
+__global__ void __launch_bounds__(W_THREADS, W_WALL_MIN_BLOCKS)
+whitted_wall_kernel(WFrame F, Shard S, uint32_t n_stride, uint32_t *pixels, unsigned *block_counter, const uint8_t *cls) {
+    extern __shared__ f4 s_raw[];
+    const uint32_t lane = threadIdx.x & 31u;
+    const f4 *s_geom; const int *s_runs;
+    stage_scene<3>(F, s_raw, s_geom, s_runs);
+    WLane L;
+    L.c_nearest = L.c_shadow = L.c_samples = 0; L.c_sphere_tests = L.c_plane_tests = 0; L.c_shadow_lit = 0;
+    const uint32_t n_blocks = n_stride >> 5;
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = atomicAdd(block_counter, 1u);
+        blk = __shfl_sync(FULL_MASK, blk, 0);
+        if (blk >= n_blocks) break;
+        const uint32_t it = blk * 32u + lane;
+        int x = 0, y = 0;
+        const bool mine = cls[it] == 2 && item_to_pixel(S, F.w, it, x, y);
+        if (!__any_sync(FULL_MASK, mine)) continue;
+        L.phase = PH_IDLE;
+        L.x = x; L.y = y; L.ar = L.ag = L.ab = 0.f;
+#pragma unroll 1
+        for (int sub = 0; sub < 9; sub++) {
+            if (mine) { L.sub = sub; w_start_subsample(L, F); }
+            w_query_nearest_tiles(L, s_geom, F.flags, s_runs, F.n_runs, mine, F.grid);
+            if (mine) w_after_nearest<false, NL, false>(L, F);
+            while (__any_sync(FULL_MASK, L.phase == PH_SHADOW)) {
+                const bool sq = L.phase == PH_SHADOW;
+                w_query_shadow_grid(L, s_geom, F.flags, sq, F.grid, F.reject_k);
+                if (sq) w_after_shadow<false, NL, false>(L, F);
+            }
+            if (mine) {                                   // the fold of w_finalize for a primary ray (RNO:351-356); no children by construction
+                RT_CHECK(L.hit < 0 || !((F.grid.deep >> L.hit) & 1u), RT_CHK_TABLE);
+                if (F.hit_ids) F.hit_ids[((size_t)L.y * F.w + L.x) * 9 + sub] = L.hit;
+                L.ar = f_add(L.ar, f_mul(L.cr, L.weight));
+                L.ag = f_add(L.ag, f_mul(L.cg, L.weight));
+                L.ab = f_add(L.ab, f_mul(L.cb, L.weight));
+                L.phase = PH_IDLE;
+            }
+        }
+        if (mine) pixels[(size_t)L.y * F.w + L.x] = w_pack_pixel(L.ar, L.ag, L.ab);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // raytracer3.0.06 (BASELINE config 1): the frame of Engine_Render (R306/raytracer.cpp:301-530) on the GPU.  Same shape as
 // the Whitted kernel -- persistent warps, one lane per pixel, a nearest round then batched shadow rounds over the
@@ -908,6 +958,15 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = cudaEventRecord(p.ev_join, p.aux_stream)) != cudaSuccess) return e;
     }
+    if (split && p.cls && p.wall_kernel) {      // what is left for this stream: pure wall blocks
+        auto kw = p.sphere_lights == 3 ? whitted_wall_kernel<3> : p.sphere_lights == 2 ? whitted_wall_kernel<2> : whitted_wall_kernel<1>;
+        int nbw = 0;
+        if ((e = configure_kernel(kw, W_THREADS, smem, &nbw)) != cudaSuccess) return e;
+        if (p.max_blocks_per_sm > 0 && nbw > p.max_blocks_per_sm) nbw = p.max_blocks_per_sm;
+        long gridw = (long)nbw * p.sm_count;
+        if (gridw > need) gridw = need > 0 ? need : 1;
+        kw<<<(unsigned)gridw, W_THREADS, smem, stream>>>(p.frame, p.shard, p.n_items, p.pixels, p.work_counter + 1, p.cls);
+    } else
     k<<<(unsigned)grid, W_THREADS, smem, stream>>>(p.frame, p.shard, n_work, p.order, p.class_counts, p.n_items, p.pixels, p.work_counter,
                                                   p.counters, p.bvh, p.order ? p.cls : nullptr, p.filler_items);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

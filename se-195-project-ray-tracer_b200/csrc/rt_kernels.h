@@ -48,6 +48,9 @@
 #ifndef W_SPLIT_MIN_BLOCKS
 #define W_SPLIT_MIN_BLOCKS 3     /* 27 warps per SM at 72 registers: 1.49 ms against 1.56 at 2 (94 registers, no spills), 1080p */
 #endif
+#ifndef W_WALL_MIN_BLOCKS
+#define W_WALL_MIN_BLOCKS 16          /* whitted_wall_kernel: 32 warps per SM at 64 registers */
+#endif
 #ifndef W_MIN_BLOCKS
 #define W_MIN_BLOCKS 12
 #endif
@@ -76,6 +79,7 @@ struct WLaunch {
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
     // frame.split0: class 0 goes to whitted_split_kernel on aux_stream (forked from / joined to the launch stream with the two events)
+    int wall_kernel;            // with split0 and cls: 1 = the class-2 blocks go to whitted_wall_kernel, 0 = to the general kernel
     int split_blocks_per_sm;    // cap on that kernel's resident CTAs per SM (0: as many as fit); the main kernel's CTAs take the rest at once
     unsigned *split_work_counter; cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;
     unsigned *redo_work_counter; // NULL: no EXACT launch after the kernel (counting launches); else its work counter (frame.redo_* name the list)

@@ -308,7 +308,7 @@ def test_whitted_split_kernel_and_tables_change_nothing(gpu, orc, rt):
             gpu.set_shard(rank, world, tile)
             px_o, hits_o, _ = oracle_whitted(orc, prims, w, h)
             rows = np.array([(y // tile) % world == rank for y in range(h)])
-            for split, grid in [(1, 1), (0, 1), (1, 2), (0, 2), (1, 0), (0, 0)]:
+            for split, grid in [(1, 1), (2, 1), (0, 1), (1, 2), (0, 2), (1, 0), (0, 0)]:
                 gpu.set_tuning(rt.TUNE_WHITTED_SPLIT, split); gpu.set_tuning(rt.TUNE_WHITTED_GRID, grid)
                 a, ha = gpu.whitted_render(prims, w, h, want_hit_ids=True)
                 assert np.array_equal(a[rows], px_o[rows]) and np.array_equal(ha[rows], hits_o[rows]), (w, h, split, grid)

@@ -12,7 +12,7 @@ for scene in (0,):
     for (w, h) in sizes:
         out, frames = [], []
         for rep in range(2):
-            for grid, split in ((1, 1), (1, 0), (2, 0), (0, 0)):
+            for grid, split in ((1, 1), (1, 2), (1, 0), (2, 0), (0, 0)):
                 r.set_tuning(rt.TUNE_WHITTED_GRID, grid); r.set_tuning(rt.TUNE_WHITTED_SPLIT, split)
                 r.whitted_upload(prims, w, h)
                 for _ in range(3): r.whitted_launch()
