@@ -22,6 +22,9 @@ struct rt_ctx {
     cudaStream_t aux_stream = nullptr;             // Whitted: whitted_split_kernel runs here, next to the main kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int w_split = 1;                               // RT_TUNE_WHITTED_SPLIT
+    // the cost classes of the last split launch (a function of the table, the frame size and the shard only): kept while those stay the same
+    struct { bool valid = false; uint64_t gen = 0; int w = 0, h = 0, rank = 0, world = 0, tile = 0; const void *order = nullptr, *cls = nullptr; } w_classes;
+    uint64_t w_table_gen = 0;                      // counts the Whitted tables uploaded so far
     int w_split_blocks = 0;                        // RT_TUNE_WHITTED_SPLIT_BLOCKS (0: as many as fit)
     int sm_count = 0, clock_khz = 0, max_smem_optin = 0;
     char name[256] = {0};
@@ -296,6 +299,7 @@ int rt_whitted_upload(rt_ctx *ctx, const rt_primitive *prims, int n, int w, int 
         build_w_soa(prims, n, soa);
         ctx->w_prims.assign(prims, prims + n);
         ctx->w_bvh_ready = false;
+        ctx->w_table_gen++;
     }
     CK(upload_vec(&ctx->d_wgeom, &ctx->cap_wgeom, soa.geom, ctx->stream));
     CK(upload_vec(&ctx->d_wma, &ctx->cap_wma, soa.mat_a, ctx->stream));
@@ -449,12 +453,23 @@ int rt_whitted_launch(rt_ctx *ctx) {
     // class 0 one lane per sub-sample, next to the main kernel: needs the class lists and the tables of the grid variants
     F.split0 = (ctx->w_split && p.order && F.grid.cells && F.grid.tiles) ? 1 : 0;
     if (F.split0) p.filler_items = 0;            // no listed pixels in the main kernel: nothing to fill in behind
+    {   // tile-word classes depend on nothing but (table, frame size, shard): an unchanged frame keeps its lists and skips the pre-pass
+        auto &K = ctx->w_classes;
+        p.classes_ready = F.split0 && K.valid && K.gen == ctx->w_table_gen && K.w == ctx->w_w && K.h == ctx->w_h && K.rank == ctx->shard_rank &&
+                          K.world == ctx->shard_world && K.tile == ctx->tile_rows && K.order == (const void *)p.order && K.cls == (const void *)p.cls;
+        K.valid = false;                                // until this launch has been issued: its pre-pass writes the list buffers
+    }
     p.split_blocks_per_sm = ctx->w_split_blocks;
     p.wall_kernel = ctx->w_split == 1 ? 1 : 0;      // RT_TUNE_WHITTED_SPLIT = 2: the general kernel for the wall blocks
     p.split_work_counter = ctx->d_work + 4; p.aux_stream = ctx->aux_stream; p.ev_fork = ctx->ev_fork; p.ev_join = ctx->ev_join;
     CK(cudaMemsetAsync(ctx->d_work, 0, 6 * sizeof(unsigned), ctx->stream));
     if (ctx->counting) CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
-    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.redo_work_counter ? 1 : 0) + F.split0; }
+    if (p.n_items) { CK(rtk_launch_whitted(p, ctx->stream)); ctx->launches += ((p.order && !p.classes_ready) ? 2 : 1) + (p.redo_work_counter ? 1 : 0) + F.split0; }
+    if (p.n_items && F.split0) {
+        auto &K = ctx->w_classes;
+        K.valid = true; K.gen = ctx->w_table_gen; K.w = ctx->w_w; K.h = ctx->w_h; K.rank = ctx->shard_rank; K.world = ctx->shard_world;
+        K.tile = ctx->tile_rows; K.order = p.order; K.cls = p.cls;
+    }
     return RT_OK;
 }
 
@@ -593,6 +608,7 @@ int rt_r306_launch(rt_ctx *ctx) {
         if (!ctx->d_wclass) CK(cudaMalloc((void **)&ctx->d_wclass, 4 * sizeof(unsigned)));
         p.order = ctx->d_worder; p.class_counts = ctx->d_wclass;
     }
+    ctx->w_classes.valid = false;                 // this launch's pre-pass writes the same list buffers
     CK(cudaMemsetAsync(ctx->d_work, 0, 6 * sizeof(unsigned), ctx->stream));
     if (p.n_items) { CK(rtk_launch_r306(p, ctx->stream)); ctx->launches += (p.order ? 2 : 1) + (p.subcol ? 1 : 0); }
     return RT_OK;

@@ -932,7 +932,8 @@ cudaError_t rtk_launch_whitted(const WLaunch &p, cudaStream_t stream) {
     const long need = ((long)p.n_items + W_THREADS - 1) / W_THREADS;
     if (grid > need) grid = need > 0 ? need : 1;
     uint32_t n_work = p.n_items;
-    if (p.order) {
+    if (p.order && p.classes_ready) n_work = p.n_valid;
+    else if (p.order) {
         // scheduling pre-pass: order[] = expensive pixels first; the number of valid entries is known on the host
         size_t csmem = p.stage_mode ? (size_t)p.frame.n * sizeof(f4) + (size_t)p.frame.n_runs * 3 * sizeof(int) : 16;
         if (csmem < 16) csmem = 16;

@@ -79,6 +79,7 @@ struct WLaunch {
     uint32_t *pixels;
     unsigned *work_counter; unsigned long long *counters;
     // frame.split0: class 0 goes to whitted_split_kernel on aux_stream (forked from / joined to the launch stream with the two events)
+    int classes_ready;          // 1: order / class_counts / cls still hold this frame's classes (same table, size and shard): no pre-pass
     int wall_kernel;            // with split0 and cls: 1 = the class-2 blocks go to whitted_wall_kernel, 0 = to the general kernel
     int split_blocks_per_sm;    // cap on that kernel's resident CTAs per SM (0: as many as fit); the main kernel's CTAs take the rest at once
     unsigned *split_work_counter; cudaStream_t aux_stream; cudaEvent_t ev_fork, ev_join;

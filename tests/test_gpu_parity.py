@@ -317,6 +317,37 @@ def test_whitted_split_kernel_and_tables_change_nothing(gpu, orc, rt):
         gpu.set_tuning(rt.TUNE_WHITTED_SPLIT, 1); gpu.set_tuning(rt.TUNE_WHITTED_GRID, 1)
 
 
+def test_whitted_kept_cost_classes_stay_valid(gpu, orc, rt):
+    """An unchanged frame (same table, size and shard) keeps its cost-class lists and skips the pre-pass; anything that writes the list
+    buffers or changes what they depend on -- another size, another shard, another table, a counting launch, an r306 frame -- must make
+    the next launch classify again.  Every frame equals the oracle's."""
+    box = rt.whitted_create_scene(0)
+    moved = box.copy(); moved["center"][3, 0] += np.float32(1.5)
+    ref = {}
+    def check(prims, w, h, key):
+        if key not in ref:
+            ref[key] = oracle_whitted(orc, prims, w, h)[:2]
+        px, hits = gpu.whitted_render(prims, w, h, want_hit_ids=True)
+        assert np.array_equal(px, ref[key][0]) and np.array_equal(hits, ref[key][1]), key
+    try:
+        n0 = gpu.launch_count(); check(box, 320, 180, "a"); first = gpu.launch_count() - n0
+        n0 = gpu.launch_count(); check(box, 320, 180, "a"); again = gpu.launch_count() - n0
+        assert again == first - 1                       # no pre-pass the second time
+        check(box, 200, 150, "b"); check(box, 320, 180, "a"); check(moved, 320, 180, "c"); check(box, 320, 180, "a")
+        gpu.set_counting(True); gpu.whitted_render(box, 320, 180); gpu.set_counting(False)
+        check(box, 320, 180, "a")
+        gpu.r306_render(rt.r306_create_scene(), 160, 140)
+        check(box, 320, 180, "a"); check(box, 320, 180, "a")
+        gpu.set_shard(1, 2, 8)
+        px, hits = gpu.whitted_render(box, 320, 180, want_hit_ids=True)
+        rows = np.array([(y // 8) % 2 == 1 for y in range(180)])
+        assert np.array_equal(px[rows], ref["a"][0][rows]) and np.array_equal(hits[rows], ref["a"][1][rows])
+        gpu.set_shard(0, 1, 8)
+        check(box, 320, 180, "a")
+    finally:
+        gpu.set_shard(0, 1, 8); gpu.set_counting(False)
+
+
 def test_whitted_counters_equal_oracle(gpu, orc, rt):
     prims = rt.whitted_create_scene(0)
     gpu.set_counting(True)
